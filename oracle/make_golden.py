@@ -1,0 +1,412 @@
+"""ORACLE / TEST INFRASTRUCTURE ONLY -- generates golden vectors by RUNNING THE UNMODIFIED REFERENCE.
+
+The reference (/root/reference, read-only) is imported as-is, with oracle/lietorch standing in for
+the missing third-party ``lietorch``.  Runs only in the build container (the GPU box has no
+/root/reference); its outputs travel:
+
+  tests/golden/*.npz            small, committed
+  oracle/_ref/golden_full.npz   full 640x512 stage dump, git-ignored, shipped by gpurun
+  oracle/_ref/trained/*.pth     the reference's shipped checkpoints (data, not source), git-ignored
+
+Reference entry points exercised:
+  PoseEstimator.forward                 core/pose/pose_estimator.py:50-96   (3 frames -> 2 pairs)
+  PoseNet.infer                         core/pose/pose_net.py:60-85
+  RAFT.forward / CorrBlock              core/RAFT/core/raft.py:79-137, core/RAFT/core/corr.py:12-60
+  remap_from_flow(_nearest)             core/interpol/flow_utils.py:4-26
+  DPoseSE3Head.objective / solve        core/pose/pose_head.py:53-79
+
+usage: python oracle/make_golden.py [--full]
+"""
+import argparse
+import os
+import shutil
+import sys
+import importlib.util
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("RPE_REFERENCE_ROOT", "/root/reference")
+sys.path.insert(0, HERE)
+sys.path.insert(0, REF)
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+
+def _load_synth():
+    spec = importlib.util.spec_from_file_location(
+        "rpe_synth", os.path.join(ROOT, "robust-pose-estimator_b200", "dataset", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def det_uniform(shape, seed, lo=-1.0, hi=1.0):
+    """Platform-exact pseudo-random floats (integer LCG -> float32); shared with the tests."""
+    n = int(np.prod(shape))
+    idx = np.arange(1, n + 1, dtype=np.uint64)
+    x = (idx * np.uint64(6364136223846793005) + np.uint64(seed) * np.uint64(1442695040888963407)
+         + np.uint64(1013904223))
+    x ^= x >> np.uint64(29)
+    x = x * np.uint64(0xBF58476D1CE4E5B9)
+    x ^= x >> np.uint64(32)
+    u = (x >> np.uint64(40)).astype(np.float64) / float(1 << 24)          # 24-bit mantissa, exact
+    return (lo + (hi - lo) * u).astype(np.float32).reshape(shape)
+
+
+def pack(mask):
+    return np.packbits(np.asarray(mask).astype(bool).reshape(-1))
+
+
+class Recorder:
+    def __init__(self):
+        self.lbfgs = []       # per objective evaluation: (pose7, grad6 before clipping)
+        self.corr = []
+        self.stage = {}
+
+
+def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True):
+    """Run the reference tracker over a synthetic sequence and record every stage of the last pair."""
+    from core.pose.pose_estimator import PoseEstimator
+    import core.pose.pose_net as pose_net_mod
+    import core.RAFT.core.raft as raft_mod
+    from core.RAFT.core.corr import CorrBlock
+    from lietorch import SE3
+
+    synth = _load_synth()
+    seq = synth.SyntheticStereoSequence(n_frames, size, seed=seed, holes=holes)
+    with open(os.path.join(REF, "configuration", "infer_f2f.yaml")) as f:
+        config = yaml.load(f, Loader=yaml.SafeLoader)
+    config["slam"]["conf_weighing"] = conf
+    config["img_size"] = list(size)
+    est = PoseEstimator(config["slam"], torch.tensor(seq.calib["intrinsics"]["left"]), baseline=seq.calib["bf"],
+                        checkpoint=ckpt, img_shape=config["img_size"], init_pose=SE3.Identity(1))
+    model = est.model
+    rec = Recorder()
+
+    # ---- hooks (wrap, never modify, the reference callables) ------------------------------
+    class RecCorrBlock(CorrBlock):
+        def __init__(self, fmap1, fmap2, **kw):
+            super().__init__(fmap1, fmap2, **kw)
+            self._rec = {"fmap1": fmap1.clone(), "fmap2": fmap2.clone(), "lookups": []}
+            rec.corr.append(self)
+
+        def __call__(self, coords):
+            out = super().__call__(coords)
+            if rec_corr:
+                self._rec["lookups"].append((coords.clone(), out.clone()))
+            return out
+
+    raft_mod.CorrBlock = RecCorrBlock
+
+    orig_clip = torch.nn.utils.clip_grad_norm_
+
+    def clip_hook(params, max_norm, *a, **k):
+        p = params
+        rec.lbfgs.append((p.group.data.detach().clone().reshape(-1), p.grad.detach().clone().reshape(-1)))
+        return orig_clip(params, max_norm, *a, **k)
+
+    torch.nn.utils.clip_grad_norm_ = clip_hook
+
+    orig_gwm = model.get_weight_maps
+
+    def gwm_hook(pcl1, pcl2, image1l, image2l, mask2, time_flow, stereo_flow1, stereo_flow2, gru, ctx):
+        rec.stage.update(pcl1=pcl1.clone(), pcl2=pcl2.clone(), mask2_valid=mask2.clone(),
+                         time_flow=time_flow.clone(), stereo_flow1=stereo_flow1.clone(),
+                         stereo_flow2=stereo_flow2.clone(), gru=gru.clone(), ctx=ctx.clone())
+        out = orig_gwm(pcl1, pcl2, image1l, image2l, mask2, time_flow, stereo_flow1, stereo_flow2, gru, ctx)
+        conf1, conf2, pcl2w, mask2w = out
+        rec.stage.update(conf1=conf1.clone(), conf2=conf2.clone(), pcl2w=pcl2w.clone(), mask2w=mask2w.clone())
+        return out
+
+    model.get_weight_maps = gwm_hook
+
+    orig_remap = pose_net_mod.remap_from_flow
+
+    def remap_hook(x, flow):
+        y, valid = orig_remap(x, flow)
+        rec.stage.setdefault("remaps", []).append(y.clone())
+        return y, valid
+
+    pose_net_mod.remap_from_flow = remap_hook
+
+    orig_solve = model.pose_head.problem.solve
+
+    def solve_hook(*xs):
+        rec.stage["xs"] = [x.detach().clone() for x in xs]
+        rec.lbfgs.clear()
+        return orig_solve(*xs)
+
+    model.pose_head.problem.solve = solve_hook
+
+    out = {"K": seq.calib["intrinsics"]["left"], "bf": np.float64(seq.calib["bf"]), "size": np.array(size),
+           "seed": np.int64(seed), "gt_rel_xi": seq.rel_xi}
+    frames = []
+    poses = []
+    rel = []
+    try:
+        with torch.no_grad():
+            for i in range(n_frames):
+                limg, rimg, mask, _ = seq[i]
+                frames.append((limg.astype(np.uint8), rimg.astype(np.uint8), mask.copy()))
+                rec.corr.clear()
+                pose, _, flow, weights = est(torch.from_numpy(limg)[None], torch.from_numpy(rimg)[None],
+                                             torch.from_numpy(mask)[None])
+                poses.append(pose.vec().detach().clone().numpy().reshape(7))
+                if i > 0:
+                    xs = rec.stage["xs"]
+                    rel.append(dict(evals=[(p.numpy().copy(), g.numpy().copy()) for p, g in rec.lbfgs]))
+                print(f"  frame {i}: pose {poses[-1]}  evals {len(rec.lbfgs)}")
+    finally:
+        raft_mod.CorrBlock = CorrBlock
+        torch.nn.utils.clip_grad_norm_ = orig_clip
+        pose_net_mod.remap_from_flow = orig_remap
+
+    out["imgs_l"] = np.stack([f[0] for f in frames])
+    out["imgs_r"] = np.stack([f[1] for f in frames])
+    out["masks_in"] = np.stack([pack(f[2]) for f in frames])
+    out["traj"] = np.stack(poses)
+    for k, r in enumerate(rel):
+        out[f"pair{k}_eval_pose"] = np.stack([e[0] for e in r["evals"]])
+        out[f"pair{k}_eval_grad"] = np.stack([e[1] for e in r["evals"]])
+    return out, rec, est
+
+
+def stage_dict(rec, est, full):
+    """Stage tensors of the LAST pair.  `full` keeps every tensor; otherwise floats are sub-sampled."""
+    st = rec.stage
+    xs = st["xs"]
+    flow, pcl1, pcl2w, w1, w2, m1, m2w, K, lw = xs
+    head = est.model.pose_head.problem
+    d = {}
+    f32 = lambda t: t.detach().numpy().astype(np.float32)
+    d["time_flow"] = f32(st["time_flow"][0])
+    d["stereo_flow1"] = f32(st["stereo_flow1"][0]) if full else None
+    d["stereo_flow2"] = f32(st["stereo_flow2"][0])
+    d["mask1"] = pack(m1)
+    d["mask2_valid"] = pack(st["mask2_valid"])          # mask2 &= stereo-valid   (pose_net.py:77)
+    d["mask2w"] = pack(m2w)
+    d["loss_weight"] = f32(lw[0])
+    d["depth1_norm"] = f32(est.last_frame.depth[0, 0] * est.scale) if est.last_frame is not None else None
+    keep = (lambda a: a) if full else (lambda a: a.reshape(a.shape[0], -1)[:, ::7].copy())
+    d["pcl1"] = keep(f32(st["pcl1"][0]))
+    d["pcl2"] = keep(f32(st["pcl2"][0]))
+    d["pcl2w"] = keep(f32(pcl2w[0]))
+    d["img2w"] = keep(f32(st["remaps"][-2][0]))
+    d["sflow2w"] = keep(f32(st["remaps"][-1][0]))
+    d["conf1"] = f32(w1[0]) if full else f32(w1[0]).astype(np.float16)
+    d["conf2"] = f32(w2[0]) if full else f32(w2[0]).astype(np.float16)
+    d["gru"] = f32(st["gru"][0]) if full else None
+    d["ctx"] = f32(st["ctx"][0]) if full else None
+    d = {k: v for k, v in d.items() if v is not None}
+    # objective + autograd gradient of the reference at a few poses (fp64 like solve())
+    from lietorch import SE3, LieGroupParameter
+    xs64 = [x.double() if x.dtype == torch.float32 else x for x in xs]
+    probe = [np.zeros(6), np.array([0.01, -0.02, 0.015, 0.004, -0.003, 0.002]),
+             np.array([-0.03, 0.01, 0.02, -0.01, 0.008, 0.012])]
+    vals = []
+    for xi in probe:
+        with torch.enable_grad():
+            G = SE3.exp(torch.tensor(xi, dtype=torch.float64).view(1, 1, 6))
+            y = LieGroupParameter(G)
+            loss = head.objective(*xs64, y=(y,)).sum()
+            loss.backward()
+            l3 = head.depth_objective(xs64[1], xs64[2], xs64[4], xs64[5], xs64[6], y)
+            l2 = head.reprojection_objective(xs64[0], xs64[1], xs64[3], xs64[5], xs64[7], y)
+        vals.append(np.concatenate((G.data.numpy().reshape(7), [loss.item(), l2.item(), l3.item()],
+                                    y.grad.numpy().reshape(6))))
+    d["objective_probe"] = np.stack(vals)                # [pose7 | f, L2d, L3d | grad6]
+    return d
+
+
+def small_stage_goldens():
+    """Reference operators on platform-exact pseudo-random tensors (no network, no checkpoint)."""
+    from core.RAFT.core.corr import CorrBlock
+    from core.interpol.flow_utils import remap_from_flow, remap_from_flow_nearest
+    from core.geometry.pinhole_transforms import create_img_coords_t
+    import torch.nn.functional as F
+    g = {}
+    # --- CorrBlock (corr.py:12-60): B=2, C=32, 16x16 grid (levels 16x16, 8x8, 4x4, 2x2)
+    B, C, h, w = 2, 32, 16, 16
+    f1 = torch.from_numpy(det_uniform((B, C, h, w), 11))
+    f2 = torch.from_numpy(det_uniform((B, C, h, w), 12))
+    cb = CorrBlock(f1, f2, num_levels=4, radius=4)
+    for l, lvl in enumerate(cb.corr_pyramid):
+        lv = lvl.numpy().reshape(B, h * w, *lvl.shape[-2:])
+        g[f"corr_l{l}"] = lv[:1] if l == 0 else lv          # level 0 of batch 0 only (size)
+    coords = torch.stack(torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")[::-1], 0).float()[None]
+    coords = coords.repeat(B, 1, 1, 1) + torch.from_numpy(det_uniform((B, 2, h, w), 13, -9.0, 9.0))
+    coords[0, :, 0, 0] = torch.tensor([3.0, 5.0])           # exactly-integer coordinates
+    coords[0, :, 0, 1] = torch.tensor([-7.5, 40.0])         # far out of range
+    g["corr_coords"] = coords.numpy()
+    g["corr_lookup"] = cb(coords).numpy()
+    # --- warps (flow_utils.py:4-26) on a 40x56 image, flow up to +-12 px, with exact .5 cases
+    H, W = 40, 56
+    x8 = torch.from_numpy(det_uniform((1, 8, H, W), 21, -2.0, 2.0))
+    flow = torch.from_numpy(det_uniform((1, 2, H, W), 22, -12.0, 12.0))
+    flow[0, :, 1, :8] = torch.tensor([0.5, 1.5, 2.5, -0.5, 3.5, 4.5, 0.0, -1.5])[None]
+    flow[0, :, 2, :4] = torch.tensor([[60.0, -60.0, 0.25, 0.75], [0.0, 0.0, 45.0, -45.0]])
+    m = torch.from_numpy(det_uniform((1, 1, H, W), 23, 0.0, 1.0) > 0.2)
+    g["warp_flow"] = flow.numpy()
+    g["warp_bilinear"] = remap_from_flow(x8, flow)[0].numpy()
+    wm, valid = remap_from_flow_nearest(m, flow)
+    g["warp_mask_in"] = pack(m)
+    g["warp_mask_out"] = pack(valid & wm.to(bool))           # pose_net.py:107-108
+    # --- 1/8 bilinear down-sampling (pose_net.py:110-113)
+    g["down8"] = F.interpolate(x8, scale_factor=0.125, mode="bilinear").numpy()
+    # --- depth from stereo flow + back-projection (pose_net.py:73-79,121-125)
+    K = torch.tensor([[[35.0, 0.0, 28.0], [0.0, 35.0, 20.0], [0.0, 0.0, 1.0]]])
+    sflow = torch.from_numpy(det_uniform((1, 2, H, W), 24, -30.0, 4.0))
+    sflow[0, 0, 0, :3] = torch.tensor([0.0, -8.8, -8.8000001])
+    bfs = torch.tensor([8.8])
+    depth = bfs[:, None, None] / -sflow[:, 0]
+    valid = (depth > 0) & (depth <= 1.0)
+    depth[~valid] = 1.0
+    ic = create_img_coords_t(y=H, x=W)
+    pcl = (depth.view(1, 1, -1) * (torch.linalg.inv(K) @ ic.view(1, 3, -1))).view(1, 3, H, W)
+    g["geom_K"] = K.numpy()
+    g["geom_sflow"] = sflow.numpy()
+    g["geom_depth"] = depth.numpy()
+    g["geom_valid"] = pack(valid)
+    g["geom_pcl"] = pcl.numpy()
+    return g
+
+
+def posehead_unit_golden():
+    """The reference's own pose-head recipe (tests/unit_test_pose_head.py:13-50) on exact inputs, n=2."""
+    from lietorch import SE3
+    from core.geometry.pinhole_transforms import transform, project, reproject, create_img_coords_t
+    from core.pose.pose_head import DPoseSE3Head
+    n, R = 2, 128
+    kmat = torch.diag(torch.tensor([107.0, 107, 1]))
+    kmat[0, -1] = R // 2
+    kmat[1, -1] = R // 2
+    kmat = kmat.repeat((n, 1, 1))
+    depth = 100 * torch.clamp(torch.from_numpy(det_uniform((n, 1, R, R), 31, 0.0, 1.0)), 0.01, 1)
+    ic = create_img_coords_t(R, R)
+    pcl = reproject(depth, kmat, ic)[:, :3].view(n, 3, R, R)
+    xi = torch.from_numpy(det_uniform((n, 1, 6), 32, -0.02, 0.02))
+    poses = SE3.exp(xi)
+    flow_off = project(pcl.view(n, 3, -1), kmat, poses)[:, :2].reshape(n, 2, R, R)
+    valid = ((flow_off[:, 0] >= 0) & (flow_off[:, 0] < R) & (flow_off[:, 1] >= 0) & (flow_off[:, 1] < R)).unsqueeze(1)
+    flow = flow_off - ic[:2].reshape(1, 2, R, R)
+    pcl_t = transform(pcl.view(n, 3, -1), poses).view(n, 3, R, R)
+    ones = torch.ones((n, 1, R, R))
+    masks = torch.ones((n, 1, R, R), dtype=torch.bool)
+    g = {"xi_gt": xi.numpy().reshape(n, 6), "depth": depth.numpy(), "K": kmat[0].numpy(),
+         "flow": flow.numpy(), "pcl": pcl.numpy(), "pcl_t": pcl_t.numpy(), "valid": pack(valid)}
+    vec, log, nev = [], [], []
+    for i in range(n):                                    # per sample: batch>1 couples L-BFGS
+        head = DPoseSE3Head(ic, lbgfs_iters=100)
+        evals = []
+        orig_clip = torch.nn.utils.clip_grad_norm_
+        torch.nn.utils.clip_grad_norm_ = lambda p, m, *a, **k: (evals.append(1), orig_clip(p, m, *a, **k))[1]
+        try:
+            xs = (flow[i:i + 1], pcl[i:i + 1], pcl_t[i:i + 1], ones[i:i + 1], ones[i:i + 1], valid[i:i + 1],
+                  masks[i:i + 1], kmat[i:i + 1], torch.tensor([[0.001, 1.0]]))
+            y = head.solve(*xs)[0]
+        finally:
+            torch.nn.utils.clip_grad_norm_ = orig_clip
+        vec.append(y.group.vec().detach().numpy().reshape(7))
+        log.append(y.log().detach().numpy().reshape(6))
+        nev.append(len(evals))
+    g["sol_vec"] = np.stack(vec)
+    g["sol_log"] = np.stack(log)
+    g["n_evals"] = np.array(nev)
+    return g
+
+
+def posehead_real_golden(rec, est, step=3):
+    """Pose-head inputs of a real network run, decimated by `step`, fed to the reference's DPoseSE3Head
+    as a smaller problem (pins objective, autograd gradient, L-BFGS trajectory on realistic
+    residuals, masks and confidence weights)."""
+    from lietorch import SE3, LieGroupParameter
+    from core.geometry.pinhole_transforms import create_img_coords_t
+    from core.pose.pose_head import DPoseSE3Head
+    flow, pcl1, pcl2w, w1, w2, m1, m2w, K, lw = [x.clone() for x in rec.stage["xs"]]
+    sub = lambda t: t[..., ::step, ::step].contiguous()
+    flow, pcl1, pcl2w, w1, w2, m1, m2w = map(sub, (flow, pcl1, pcl2w, w1, w2, m1, m2w))
+    flow = flow / step
+    K = K.clone()
+    K[:, :2] = K[:, :2] / step
+    h, w = flow.shape[-2:]
+    head = DPoseSE3Head(create_img_coords_t(h, w), lbgfs_iters=20)
+    xs = (flow, pcl1, pcl2w, w1, w2, m1, m2w, K, lw)
+    evals = []
+    orig_clip = torch.nn.utils.clip_grad_norm_
+
+    def hook(p, m, *a, **k):
+        evals.append((p.group.data.detach().clone().reshape(-1).numpy(), p.grad.detach().clone().reshape(-1).numpy()))
+        return orig_clip(p, m, *a, **k)
+
+    torch.nn.utils.clip_grad_norm_ = hook
+    try:
+        y = head.solve(*xs)[0]
+    finally:
+        torch.nn.utils.clip_grad_norm_ = orig_clip
+    g = {"flow": flow[0].numpy(), "pcl1": pcl1[0].numpy(), "pcl2w": pcl2w[0].numpy(), "w1": w1[0, 0].numpy(),
+         "w2": w2[0, 0].numpy(), "m1": pack(m1), "m2w": pack(m2w), "K": K[0].numpy(), "lw": lw[0].numpy(),
+         "shape": np.array([h, w]),
+         "eval_pose": np.stack([e[0] for e in evals]), "eval_grad": np.stack([e[1] for e in evals]),
+         "sol_vec": y.group.vec().detach().numpy().reshape(7), "sol_log": y.log().detach().numpy().reshape(6)}
+    xs64 = [x.double() if x.dtype == torch.float32 else x for x in xs]
+    vals = []
+    for xi in (np.zeros(6), np.array([0.01, -0.02, 0.015, 0.004, -0.003, 0.002]), np.array([-0.03, 0.01, 0.02, -0.01, 0.008, 0.012])):
+        with torch.enable_grad():
+            G = SE3.exp(torch.tensor(xi, dtype=torch.float64).view(1, 1, 6))
+            yy = LieGroupParameter(G)
+            loss = head.objective(*xs64, y=(yy,)).sum()
+            loss.backward()
+            l3 = head.depth_objective(xs64[1], xs64[2], xs64[4], xs64[5], xs64[6], yy)
+            l2 = head.reprojection_objective(xs64[0], xs64[1], xs64[3], xs64[5], xs64[7], yy)
+        vals.append(np.concatenate((G.data.numpy().reshape(7), [loss.item(), l2.item(), l3.item()], yy.grad.numpy().reshape(6))))
+    g["objective_probe"] = np.stack(vals)
+    return g
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also write the 640x512 dump to oracle/_ref")
+    ap.add_argument("--skip-small", action="store_true")
+    args = ap.parse_args()
+    assert os.path.isdir(REF), "reference not mounted"
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    gold = os.path.join(ROOT, "tests", "golden")
+    refdir = os.path.join(HERE, "_ref")
+    os.makedirs(gold, exist_ok=True)
+    os.makedirs(os.path.join(refdir, "trained"), exist_ok=True)
+    for name in ("poseNet_2xf8up4b.pth", "only3d_1a7ix98y.pth", "only2d_18bl5o77.pth"):
+        dst = os.path.join(refdir, "trained", name)
+        if not os.path.isfile(dst):
+            shutil.copyfile(os.path.join(REF, "trained", name), dst)
+    ckpt = os.path.join(REF, "trained", "poseNet_2xf8up4b.pth")
+
+    if not args.skip_small:
+        print("stage goldens (reference operators on exact inputs)")
+        np.savez_compressed(os.path.join(gold, "stages_small.npz"), **small_stage_goldens())
+        print("pose-head unit recipe")
+        np.savez_compressed(os.path.join(gold, "posehead_unit.npz"), **posehead_unit_golden())
+        print("e2e 384x352, 3 frames, conf heads on")
+        out, rec, est = run_sequence((384, 352), seed=1, n_frames=3, ckpt=ckpt)
+        out.update({f"s_{k}": v for k, v in stage_dict(rec, est, full=False).items()})
+        np.savez_compressed(os.path.join(gold, "e2e_384x352.npz"), **out)
+        np.savez_compressed(os.path.join(gold, "posehead_real.npz"), **posehead_real_golden(rec, est))
+    if args.full:
+        print("e2e 640x512, 3 frames (full dump)")
+        out, rec, est = run_sequence((640, 512), seed=0, n_frames=3, ckpt=ckpt, rec_corr=True)
+        out.update({f"s_{k}": v for k, v in stage_dict(rec, est, full=True).items()})
+        cb = rec.corr[-1]                                   # the batch-2 RAFT pass of the last pair
+        out["c_fmap1"] = cb._rec["fmap1"].numpy()
+        out["c_fmap2"] = cb._rec["fmap2"].numpy()
+        for it in (0, 11):
+            out[f"c_coords{it}"] = cb._rec["lookups"][it][0].numpy()
+            out[f"c_lookup{it}"] = cb._rec["lookups"][it][1].numpy()
+        np.savez(os.path.join(refdir, "golden_full.npz"), **out)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
