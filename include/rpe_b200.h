@@ -1,0 +1,175 @@
+/*
+ * rpe_b200 -- C ABI of the B200-native (sm_100a) per-frame frame-to-frame pose path of
+ * aimi-lab/robust-pose-estimator.
+ *
+ * The reference has NO C ABI / FFI / plugin registry on this path: it is a
+ * pure-Python API over torch + lietorch.  Each entry point below therefore cites the reference
+ * Python callable it replaces.  Conventions for every call:
+ *   - all pointers are DEVICE pointers unless the name ends in _host; tensors are dense, row-major,
+ *     laid out exactly like the reference's torch tensors (NCHW planar fp32, bool masks as 1 byte);
+ *   - `stream` is a cudaStream_t (CUstream) passed as void*; every call is asynchronous on it;
+ *   - no hidden allocation: workspaces are caller-provided, sized by the *_workspace_bytes queries;
+ *   - the return value is 0 (RPE_OK) or a negative rpe_status; nothing throws;
+ *   - numerical failure (NaN pose, non-convergence) is NOT an error, exactly as in the reference
+ *     (core/pose/pose_estimator.py:81-85 handles it on the host).
+ * INTEGRATION.md shows the ctypes binding a reference maintainer would add.
+ */
+#ifndef RPE_B200_H
+#define RPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rpe_status {
+    RPE_OK = 0,
+    RPE_ERR_INVALID_ARG = -1,   /* null pointer, non-positive size, unsupported shape        */
+    RPE_ERR_ALIGNMENT = -2,     /* pointer / stride not aligned as the entry point requires  */
+    RPE_ERR_WORKSPACE = -3,     /* workspace too small                                        */
+    RPE_ERR_CUDA = -4,          /* a CUDA runtime / driver call failed (see rpe_last_cuda_error) */
+    RPE_ERR_UNSUPPORTED_DEVICE = -5 /* not an sm_100 device                                    */
+} rpe_status;
+
+/* Library / device introspection. */
+int rpe_version(void);
+const char *rpe_status_string(int status);
+int rpe_last_cuda_error(void);                 /* cudaError_t of the last failing CUDA call      */
+int rpe_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 2 -- stereo depth lifting and pinhole back-projection (coalesced per-pixel kernels).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces PoseNet.infer's depth block + PoseNet.proj
+ *   (/root/reference/core/pose/pose_net.py:73-79, 121-125; flow2depth :127-135;
+ *    reproject: core/geometry/pinhole_transforms.py:79-87, create_img_coords_t :7-19).
+ *   depth = bf / -stereo_flow.x ; valid = (depth > 0) & (depth <= 1) ; depth[~valid] = 1 ;
+ *   mask &= valid (in place, only if mask_inout != NULL) ; pcl = depth * K^-1 [u+.5, v+.5, 1].
+ * stereo_flow (n,2,H,W) f32, bf (n) f32, K (n,3,3) f32, mask_inout (n,1,H,W) u8 or NULL,
+ * depth (n,1,H,W) f32 out, valid (n,1,H,W) u8 out (may be NULL), pcl (n,3,H,W) f32 out (may be NULL). */
+int rpe_depth_proj(const float *stereo_flow, const float *bf, const float *K, uint8_t *mask_inout,
+                   float *depth, uint8_t *valid, float *pcl, int n, int H, int W, void *stream);
+
+/* Replaces PoseNet.proj (/root/reference/core/pose/pose_net.py:121-125) for a given depth map.
+ * The depth fed to the projection is ((depth * pre_div_recip_a) * pre_mul_b) evaluated in fp32 with
+ * one rounding per operation when `rescale` != 0 -- this reproduces the tracker's
+ * `frame.depth = depth / scale` ... `depth1 = frame.depth * scale` round trip
+ * (core/pose/pose_estimator.py:115,121): pass rescale=1, scale=the tracker's fp32 scale.
+ * depth (n,1,H,W) f32, K (n,3,3) f32, pcl (n,3,H,W) f32 out. */
+int rpe_proj(const float *depth, const float *K, float *pcl, int rescale, float scale,
+             int n, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 5 -- flow warping.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Replaces the three remap_from_flow calls + remap_from_flow_nearest + mask combination of
+ * PoseNet.get_weight_maps (/root/reference/core/pose/pose_net.py:104-108;
+ * core/interpol/flow_utils.py:4-26): bilinear backward warp (align_corners=True, zeros padding) of
+ * pcl2 (n,3,H,W), img2 (n,3,H,W), sflow2 (n,2,H,W) by `flow` (n,2,H,W), and nearest warp of
+ * mask2 (n,1,H,W) u8 with  mask2w = (warped > 0) & warped.  Sampling coordinates follow the
+ * reference's fp32 operation order exactly so that mask2w is bit-exact.
+ * Any of the (src, dst) pairs may be NULL to skip that tensor. */
+int rpe_warp8_mask(const float *pcl2, const float *img2, const float *sflow2, const uint8_t *mask2,
+                   const float *flow, float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w,
+                   int n, int H, int W, void *stream);
+
+/* Replaces F.interpolate(cat(stereo_flow, image, pcl), scale_factor=0.125, mode='bilinear')
+ * (/root/reference/core/pose/pose_net.py:110-113): out[c, i, j] = mean of the 2x2 pixels
+ * (8i+3..8i+4, 8j+3..8j+4).  Up to three sources concatenated along channels:
+ * src_k (n,c_k,H,W) -> out (n, c_0+c_1+c_2, H/8, W/8) written at channel offset `out_ch_offset` of
+ * a tensor with `out_ch_total` channels. */
+int rpe_downsample8_cat(const float *src0, int c0, const float *src1, int c1, const float *src2, int c2,
+                        float *out, int out_ch_offset, int out_ch_total, int n, int H, int W, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stages 3 + 4 -- fused residual / Jacobian reduction and the on-device SE(3) solver.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef enum rpe_solver_mode {
+    RPE_SOLVER_LBFGS_REF = 0,  /* exact replica of torch.optim.LBFGS as driven by DPoseSE3Head.solve */
+    RPE_SOLVER_GN = 1,         /* Gauss-Newton: in-kernel 6x6 Cholesky + left exp-map update         */
+    RPE_SOLVER_EVAL_ONLY = 2   /* one evaluation of f, grad (and GN Hessian) at the given poses       */
+} rpe_solver_mode;
+
+/* Per-pair result record written by rpe_pose_solve (doubles). */
+#define RPE_POSE_OUT_STRIDE 64
+/*  [0..6]   pose  tx ty tz qx qy qz qw            (LieGroupParameter.group.vec())
+ *  [7..12]  log   tau(3) phi(3)                   (LieGroupParameter.log())
+ *  [13]     f at the last evaluation   [14] L2d   [15] L3d
+ *  [16]     number of objective evaluations       [17] number of solver iterations
+ *  [18]     status: 0 ok, 1 Cholesky failed (GN)
+ *  [19..24] gradient (unclipped) at the last evaluation
+ *  [25..45] GN Hessian upper triangle, row-major (GN / EVAL_ONLY with hessian)
+ */
+
+typedef struct rpe_pose_problem {
+    const float *flow;      /* (n,2,H,W)  time flow                                                */
+    const float *pcl1;      /* (n,3,H,W)                                                           */
+    const float *pcl2;      /* (n,3,H,W)  warped target cloud                                      */
+    const float *w1;        /* (n,1,H,W)  2D confidence, or NULL for ones                          */
+    const float *w2;        /* (n,1,H,W)  3D confidence, or NULL for ones                          */
+    const uint8_t *m1;      /* (n,1,H,W)  bool                                                     */
+    const uint8_t *m2;      /* (n,1,H,W)  bool                                                     */
+    const float *K;         /* (n,3,3)                                                             */
+    const float *lw;        /* (n,2) [w3d, w2d]                                                    */
+    const double *init_pose;/* (n,7) starting poses or NULL for identity                           */
+    int n, H, W;
+} rpe_pose_problem;
+
+/* Replaces DPoseSE3Head.solve + objective (/root/reference/core/pose/pose_head.py:12-79),
+ * project/transform (core/geometry/pinhole_transforms.py:28-30,90-99), lietorch SE3 exp/mul/act/log,
+ * torch.optim.LBFGS.step, clip_grad_norm_(y, 10) and DeclarativeFunctionLie.forward
+ * (core/optimization/declerative_node_lie.py:224-247).  Pairs are solved INDEPENDENTLY
+ * (the reference is batch-1).  One persistent cooperative kernel: per evaluation every
+ * pixel's 2D/3D residuals, Jacobians and weights are fused and reduced in fp64; the 6-dim solver state
+ * lives on the device -- no host synchronisation.
+ *   out      (n, RPE_POSE_OUT_STRIDE) f64
+ *   pose_f32 (n,7) f32 and log_f32 (n,6) f32: the `.float()` outputs of the declarative layer (may be NULL)
+ *   trace    (n, trace_cap, 16) f64 or NULL: per evaluation [pose7 | grad6 | f | L2d | L3d]
+ *   max_iter = lbgfs_iters (LBFGS) or GN iterations. */
+size_t rpe_pose_workspace_bytes(int n_pairs);
+/* Tuning: number of pairs solved concurrently by disjoint CTA groups (default 8, 1..256). */
+int rpe_pose_set_groups(int groups);
+int rpe_pose_solve(const rpe_pose_problem *problem_host, int mode, int max_iter, int with_hessian,
+                   double *out, float *pose_f32, float *log_f32, double *trace, int trace_cap,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage 1 -- RAFT CorrBlock: all-pairs correlation GEMM (tcgen05 + TMA), pyramid, radius lookup.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef enum rpe_corr_precision {
+    RPE_CORR_TF32 = 0,     /* one tcgen05 kind::tf32 pass (inputs rounded to tf32)                  */
+    RPE_CORR_TF32X3 = 1    /* split hi/lo: hi*hi + lo*hi + hi*lo, fp32-class accuracy               */
+} rpe_corr_precision;
+
+/* Replaces CorrBlock.__init__ / CorrBlock.corr (/root/reference/core/RAFT/core/corr.py:13-27, 52-60):
+ * level0[b, q, t] = <fmap1[b,:,q], fmap2[b,:,t]> / sqrt(C) and 3 further 2x2 average-pooled levels.
+ *   fmap1, fmap2 (B,C,h,w) f32 (C % 32 == 0)
+ *   pyramid      level l at byte offset given by rpe_corr_level_offset: (B*h*w, h>>l, w>>l) f32
+ *   workspace    rpe_corr_workspace_bytes: K-major tf32 operand copies */
+size_t rpe_corr_pyramid_bytes(int B, int h, int w, int num_levels);
+size_t rpe_corr_level_offset(int B, int h, int w, int level);
+size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision);
+int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B, int C, int h, int w,
+                   int num_levels, int precision, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Replaces CorrBlock.__call__ + bilinear_sampler (/root/reference/core/RAFT/core/corr.py:29-50,
+ * core/RAFT/core/utils/utils.py:57-71): coords (B,2,h,w) f32 (channel 0 = x) ->
+ * out (B, num_levels*(2r+1)^2, h, w) f32, channel = level*(2r+1)^2 + i*(2r+1) + j with i the
+ * X-offset index, bilinear, zeros outside. */
+int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B, int h, int w,
+                    int num_levels, int radius, void *stream);
+
+/* Replaces RAFT.upsample_flow (/root/reference/core/RAFT/core/raft.py:66-77): convex 8x upsampling
+ * with a softmax over the 9 neighbours.  flow (B,2,h,w), mask (B,576,h,w) -> out (B,2,8h,8w). */
+int rpe_convex_upsample8(const float *flow, const float *mask, float *out, int B, int h, int w, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPE_B200_H */

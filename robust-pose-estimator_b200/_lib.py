@@ -1,0 +1,68 @@
+"""ctypes binding of librpe_b200.so (the C ABI in include/rpe_b200.h).  Fails loudly: a missing
+library or a failing call raises -- there is no CPU / PyTorch fallback behind these entry points."""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librpe_b200.so")
+_lib = None
+
+POSE_OUT_STRIDE = 64
+SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = 0, 1, 2
+CORR_TF32, CORR_TF32X3 = 0, 1
+
+
+class RpeError(RuntimeError):
+    pass
+
+
+class PoseProblem(C.Structure):
+    _fields_ = [("flow", C.c_void_p), ("pcl1", C.c_void_p), ("pcl2", C.c_void_p), ("w1", C.c_void_p),
+                ("w2", C.c_void_p), ("m1", C.c_void_p), ("m2", C.c_void_p), ("K", C.c_void_p),
+                ("lw", C.c_void_p), ("init_pose", C.c_void_p), ("n", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+_P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+SIGNATURES = {
+    # name: (restype, argtypes)
+    "rpe_version": (_I, []),
+    "rpe_status_string": (C.c_char_p, [_I]),
+    "rpe_last_cuda_error": (_I, []),
+    "rpe_device_sm_count": (_I, []),
+    "rpe_depth_proj": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "rpe_proj": (_I, [_P, _P, _P, _I, _F, _I, _I, _I, _P]),
+    "rpe_warp8_mask": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "rpe_downsample8_cat": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_pose_workspace_bytes": (_Z, [_I]),
+    "rpe_pose_set_groups": (_I, [_I]),
+    "rpe_pose_solve": (_I, [C.POINTER(PoseProblem), _I, _I, _I, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "rpe_corr_pyramid_bytes": (_Z, [_I, _I, _I, _I]),
+    "rpe_corr_level_offset": (_Z, [_I, _I, _I, _I]),
+    "rpe_corr_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
+    "rpe_corr_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "rpe_corr_lookup": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_convex_upsample8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+}
+
+
+def lib():
+    """The loaded shared library (loads on first use)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RpeError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                           "(rpe_b200 has no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        l = lib()
+        msg = l.rpe_status_string(status).decode()
+        extra = f" (cudaError {l.rpe_last_cuda_error()})" if status == -4 else ""
+        raise RpeError(f"{what} failed: {msg}{extra}")

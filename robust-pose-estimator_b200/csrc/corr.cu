@@ -1,0 +1,608 @@
+// Stage 1: RAFT CorrBlock on sm_100a.
+//
+//   corr_prep_kernel     fmap (B,C,Q) fp32  ->  K-major tf32 operand (B,Q,Kp)   [transpose + cvt.rna.tf32,
+//                        optional hi/lo split for the 3xTF32 mode]
+//   corr_gemm_kernel     level0[b,q,t] = <f1[b,:,q], f2[b,:,t]> / sqrt(C): persistent, warp-specialised
+//                        tcgen05.mma (kind::tf32, M=128, N=256, accumulators in TMEM), operands staged by
+//                        TMA (SWIZZLE_128B, 4-stage mbarrier ring), double-buffered TMEM accumulators,
+//                        epilogue TMEM -> registers -> swizzled smem -> TMA store.
+//   corr_pool_kernel     levels 1..3 (2x2 means) from level 0 in one pass per query slab.
+//   corr_lookup_kernel   radius-r bilinear window lookup: warp-cooperative patch loads, smem transposition
+//                        so that both the gather and the (B, L*(2r+1)^2, h, w) output are coalesced.
+//
+// Reference semantics: /root/reference/core/RAFT/core/corr.py:12-60, utils/utils.py:57-71.
+#include <cstdio>
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include "common.cuh"
+
+namespace rpe {
+
+// ================================================================================================
+// PTX wrappers
+// ================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("rpe_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// tcgen05: TMEM allocation, MMA, commit, load
+__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t *v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ================================================================================================
+// Operand preparation: (B, C, Q) fp32 -> (B, Q, Kp) tf32-rounded, K contiguous.
+//   which = 0 (A side, fmap1): [hi | lo | hi]      which = 1 (B side, fmap2): [hi | hi | lo]
+// so that the K = 3C contraction yields hi*hi + lo*hi + hi*lo.  Single-pass mode writes [hi] only.
+// ================================================================================================
+__device__ __forceinline__ float to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) corr_prep_kernel(const float *__restrict__ fmap, float *__restrict__ out, int C, int Q,
+                                                        int split, int which) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int Kp = split ? 3 * C : C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, q = q0 + tx;
+        tile[ty + 8 * j][tx] = (c < C && q < Q) ? __ldg(fmap + ((size_t)b * C + c) * Q + q) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int q = q0 + ty + 8 * j, c = c0 + tx;
+        if (q < Q && c < C) {
+            const float x = tile[tx][ty + 8 * j];
+            const float hi = to_tf32(x);
+            float *o = out + ((size_t)b * Q + q) * Kp;
+            o[c] = hi;
+            if (split) {
+                const float lo = to_tf32(x - hi);
+                o[C + c] = which == 0 ? lo : hi;
+                o[2 * C + c] = which == 0 ? hi : lo;
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// tcgen05 / TMA GEMM
+// ================================================================================================
+constexpr int kBM = 128, kBN = 256, kBK = 32;          // tile (elements); kBK * 4 B = one 128-byte swizzle row
+constexpr int kStages = 4, kAccStages = 2;
+constexpr int kEpiCols = 32;                            // columns per epilogue chunk / TMA store box
+constexpr int kGemmThreads = 256;                       // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue
+constexpr int kABytes = kBM * kBK * 4, kBBytes = kBN * kBK * 4;
+constexpr int kStgBytes = kBM * kEpiCols * 4;
+constexpr int kGemmSmem = kStages * (kABytes + kBBytes) + 2 * kStgBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kTmemCols = kAccStages * kBN;        // 512
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13),
+// a/b K-major (0), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+
+struct GemmShape {
+    int B, Q, Kp;      // batch, queries (= targets), padded contraction length
+    int m_tiles, n_tiles;
+    float scale;       // 1 / sqrt(C)
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+    corr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const __grid_constant__ CUtensorMap tmap_c, GemmShape s) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *sA = smem;
+    uint8_t *sB = sA + kStages * kABytes;
+    uint8_t *sStg = sB + kStages * kBBytes;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(sStg + 2 * kStgBytes);
+    uint64_t *empty_bar = full_bar + kStages;
+    uint64_t *tmem_full = empty_bar + kStages;
+    uint64_t *tmem_empty = tmem_full + kAccStages;
+    uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + kAccStages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = s.B * s.m_tiles * s.n_tiles;
+    const int num_kb = s.Kp / kBK;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        prefetch_tmap(&tmap_c);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], 4);      // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr, kTmemCols);
+        tmem_relinquish();
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int b = tile / (s.m_tiles * s.n_tiles);
+                const int r = tile - b * (s.m_tiles * s.n_tiles);
+                const int n_blk = r / s.m_tiles, m_blk = r - n_blk * s.m_tiles;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
+                    tma_load_3d(sA + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM, b);
+                    tma_load_3d(sB + stage * kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * kBN, b);
+                    if (++stage == kStages) stage = 0, phase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one elected lane) =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kBN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tcgen05_fence_after();
+                    const uint64_t da = make_sw128_desc(smem_u32(sA + stage * kABytes));
+                    const uint64_t db = make_sw128_desc(smem_u32(sB + stage * kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBK / 8; ++k) {
+                        // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) start address
+                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
+                    if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
+                    if (++stage == kStages) stage = 0, phase ^= 1;
+                }
+                if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== Epilogue: TMEM -> regs -> swizzled smem -> TMA store =====================
+        const int wq = warp - 4;                       // TMEM lane quarter == warp id % 4
+        const int row = wq * 32 + lane;                // row inside the 128-row tile
+        const bool leader = (threadIdx.x == 128);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        uint32_t chunk_no = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int b = tile / (s.m_tiles * s.n_tiles);
+            const int r = tile - b * (s.m_tiles * s.n_tiles);
+            const int n_blk = r / s.m_tiles, m_blk = r - n_blk * s.m_tiles;
+            mbar_wait(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            for (int c = 0; c < kBN / kEpiCols; ++c, ++chunk_no) {
+                uint8_t *stg = sStg + (chunk_no & 1u) * kStgBytes;
+                if (leader) tma_store_wait_read<1>();          // the store that last read this buffer has drained
+                named_bar_sync(1, 128);
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kBN + c * kEpiCols), v);
+                tmem_ld_wait();
+                if (c == kBN / kEpiCols - 1) {
+                    // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                float4 *rowp = reinterpret_cast<float4 *>(stg + row * 128);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 o;
+                    o.x = __uint_as_float(v[4 * j + 0]) * s.scale;
+                    o.y = __uint_as_float(v[4 * j + 1]) * s.scale;
+                    o.z = __uint_as_float(v[4 * j + 2]) * s.scale;
+                    o.w = __uint_as_float(v[4 * j + 3]) * s.scale;
+                    rowp[j ^ (row & 7)] = o;                       // SWIZZLE_128B: 16-byte chunk index XOR (row % 8)
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(2, 128);
+                if (leader) {
+                    tma_store_3d(&tmap_c, stg, n_blk * kBN + c * kEpiCols, m_blk * kBM, b);
+                    tma_store_commit();
+                }
+            }
+            if (++acc == kAccStages) acc = 0, acc_phase ^= 1;
+        }
+        if (leader) tma_store_wait_read<0>();
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ================================================================================================
+// Pyramid pooling: one CTA per query slab; levels 1..3 from level 0 through shared memory.
+// avg_pool2d(2, 2): ((a00 + a01) + a10 + a11) * 0.25, floor on odd sizes.
+// ================================================================================================
+struct PyrDims {
+    int h[4], w[4];
+    size_t off[4];      // element offsets of the levels inside the pyramid buffer
+    int levels;
+};
+
+__global__ void __launch_bounds__(256) corr_pool_kernel(float *__restrict__ pyr, PyrDims d) {
+    extern __shared__ float sm[];
+    const size_t slab = blockIdx.x;                      // b * Q + q
+    const int n0 = d.h[0] * d.w[0];
+    const float *src = pyr + d.off[0] + slab * n0;
+    float *cur = sm;
+    for (int i = threadIdx.x * 4; i < n0; i += blockDim.x * 4) {
+        if (i + 3 < n0 && ((n0 & 3) == 0)) {
+            *reinterpret_cast<float4 *>(cur + i) = __ldg(reinterpret_cast<const float4 *>(src + i));
+        } else {
+            for (int k = i; k < n0 && k < i + 4; ++k) cur[k] = __ldg(src + k);
+        }
+    }
+    __syncthreads();
+    float *nxt = sm + n0;
+    for (int l = 1; l < d.levels; ++l) {
+        const int hp = d.h[l - 1], wp = d.w[l - 1], hl = d.h[l], wl = d.w[l];
+        (void)hp;
+        float *dst = pyr + d.off[l] + slab * (size_t)(hl * wl);
+        for (int i = threadIdx.x; i < hl * wl; i += blockDim.x) {
+            const int y = i / wl, x = i - y * wl;
+            const float *p = cur + (2 * y) * wp + 2 * x;
+            const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[wp]), p[wp + 1]), 0.25f);
+            nxt[i] = v;
+            dst[i] = v;
+        }
+        __syncthreads();
+        cur = nxt;
+        nxt = cur + hl * wl;
+    }
+}
+
+// ================================================================================================
+// Window lookup.  CTA = 8 warps = 32 consecutive queries of one batch element.
+//   phase 1 (per warp, 4 queries): for each level the (2r+2)^2 integer neighbourhood of the sample
+//            centre is fetched with lanes spread over (row, column) -> a handful of 128-byte lines per
+//            request; bilinear weights are shared by the whole window (integer offsets).
+//   phase 2: the (L*(2r+1)^2) x 32 result tile is written channel-major, 128 contiguous bytes per
+//            channel row.
+// ================================================================================================
+constexpr int kLookupQ = 32;
+constexpr int kMaxWin = 10;       // 2r+2 for r = 4
+
+__global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restrict__ pyr, PyrDims d, const float *__restrict__ coords,
+                                                          float *__restrict__ out, int Q, int radius) {
+    extern __shared__ float sm[];
+    const int n = 2 * radius + 1, win = n + 1;
+    const int nch = d.levels * n * n;
+    float *s_out = sm;                                   // [nch][kLookupQ + 1]
+    float *s_patch = sm + nch * (kLookupQ + 1);          // [8 warps][win*win]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y;
+    const int q_base = blockIdx.x * kLookupQ;
+    float *patch = s_patch + warp * (kMaxWin * kMaxWin);
+
+    for (int qi = warp; qi < kLookupQ; qi += 8) {
+        const int q = q_base + qi;
+        if (q >= Q) break;
+        const float cx = __ldg(coords + ((size_t)b * 2 + 0) * Q + q);
+        const float cy = __ldg(coords + ((size_t)b * 2 + 1) * Q + q);
+        for (int l = 0; l < d.levels; ++l) {
+            const int hl = d.h[l], wl = d.w[l];
+            const float inv = 1.0f / (float)(1 << l);
+            // reference: x = cx / 2^l + dx ; g = 2 x / (wl - 1) - 1 ; ix = (g + 1) * (wl - 1) / 2  (fp32 round trip)
+            const float xc = __fmul_rn(cx, inv), yc = __fmul_rn(cy, inv);
+            const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, xc), (float)(wl - 1)), 1.0f);
+            const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, yc), (float)(hl - 1)), 1.0f);
+            const float ix = __fmul_rn(__fadd_rn(gx, 1.0f), (float)(wl - 1) * 0.5f);
+            const float iy = __fmul_rn(__fadd_rn(gy, 1.0f), (float)(hl - 1) * 0.5f);
+            const float x0f = floorf(ix), y0f = floorf(iy);
+            const float fx = ix - x0f, fy = iy - y0f;
+            // clamp the window origin so that int conversion is safe; fully outside windows read zeros
+            const float lim = 1.0e6f;
+            const int x0 = (int)fminf(fmaxf(x0f, -lim), lim) - radius;
+            const int y0 = (int)fminf(fmaxf(y0f, -lim), lim) - radius;
+            const float *slab = pyr + d.off[l] + ((size_t)b * Q + q) * (size_t)(hl * wl);
+            for (int e = lane; e < win * win; e += 32) {
+                const int ry = e / win, rx = e - ry * win;
+                const int yy = y0 + ry, xx = x0 + rx;
+                float v = 0.0f;
+                if (yy >= 0 && yy < hl && xx >= 0 && xx < wl) v = __ldg(slab + yy * wl + xx);
+                patch[e] = v;
+            }
+            __syncwarp();
+            const float w00 = (1.0f - fy) * (1.0f - fx), w01 = (1.0f - fy) * fx, w10 = fy * (1.0f - fx), w11 = fy * fx;
+            for (int e = lane; e < n * n; e += 32) {
+                const int i = e / n, j = e - i * n;          // i: x-offset index (slow), j: y-offset index (fast)
+                const float *p = patch + j * win + i;
+                const float v = p[0] * w00 + p[1] * w01 + p[win] * w10 + p[win + 1] * w11;
+                s_out[(l * n * n + e) * (kLookupQ + 1) + qi] = v;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const int nq = min(kLookupQ, Q - q_base);
+    for (int e = threadIdx.x; e < nch * kLookupQ; e += blockDim.x) {
+        const int c = e / kLookupQ, qi = e - c * kLookupQ;
+        if (qi < nq) out[((size_t)b * nch + c) * Q + q_base + qi] = s_out[c * (kLookupQ + 1) + qi];
+    }
+}
+
+// ================================================================================================
+// Host side
+// ================================================================================================
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static int load_encode() {
+    if (g_encode) return RPE_OK;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return cuda_fail(e == cudaSuccess ? cudaErrorUnknown : e);
+    g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    return RPE_OK;
+}
+
+// 3-D fp32 tensor (inner, rows, batch) with a (box_inner x box_rows x 1) box, SWIZZLE_128B.
+static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint64_t batch, uint32_t box_inner,
+                    uint32_t box_rows) {
+    cuuint64_t dims[3] = {inner, rows, batch};
+    cuuint64_t strides[2] = {inner * 4, inner * rows * 4};
+    cuuint32_t box[3] = {box_inner, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_last_cuda_error = 100000 + (int)r;
+        return RPE_ERR_CUDA;
+    }
+    return RPE_OK;
+}
+
+static PyrDims pyr_dims(int B, int h, int w, int levels) {
+    PyrDims d;
+    size_t off = 0;
+    d.levels = levels;
+    for (int l = 0; l < 4; ++l) {
+        d.h[l] = l < levels ? (h >> l) : 0;
+        d.w[l] = l < levels ? (w >> l) : 0;
+        d.off[l] = off;
+        if (l < levels) {
+            size_t n = (size_t)B * h * w * d.h[l] * d.w[l];
+            off += (n + 63) & ~(size_t)63;      // keep every level 256-byte aligned
+        }
+    }
+    return d;
+}
+
+}  // namespace rpe
+
+extern "C" {
+
+size_t rpe_corr_level_offset(int B, int h, int w, int level) {
+    if (level < 0 || level > 3) return 0;
+    return rpe::pyr_dims(B, h, w, 4).off[level] * sizeof(float);
+}
+
+size_t rpe_corr_pyramid_bytes(int B, int h, int w, int num_levels) {
+    if (num_levels < 1 || num_levels > 4) return 0;
+    rpe::PyrDims d = rpe::pyr_dims(B, h, w, num_levels);
+    const int l = num_levels - 1;
+    size_t n = (size_t)B * h * w * d.h[l] * d.w[l];
+    return (d.off[l] + ((n + 63) & ~(size_t)63)) * sizeof(float);
+}
+
+size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision) {
+    const size_t Kp = precision == RPE_CORR_TF32X3 ? 3 * (size_t)C : (size_t)C;
+    return 2 * (((size_t)B * h * w * Kp * sizeof(float) + 1023) & ~(size_t)1023);
+}
+
+int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B, int C, int h, int w, int num_levels,
+                   int precision, void *workspace, size_t workspace_bytes, void *stream) {
+    using namespace rpe;
+    if (!fmap1 || !fmap2 || !pyramid || !workspace) return RPE_ERR_INVALID_ARG;
+    if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4) return RPE_ERR_INVALID_ARG;
+    if (C % 32 != 0) return RPE_ERR_INVALID_ARG;
+    if (precision != RPE_CORR_TF32 && precision != RPE_CORR_TF32X3) return RPE_ERR_INVALID_ARG;
+    if ((h >> (num_levels - 1)) < 1 || (w >> (num_levels - 1)) < 1) return RPE_ERR_INVALID_ARG;
+    const int Q = h * w;
+    if (Q % 4 != 0) return RPE_ERR_INVALID_ARG;     // TMA global strides must be multiples of 16 bytes
+    if (workspace_bytes < rpe_corr_workspace_bytes(B, C, h, w, precision)) return RPE_ERR_WORKSPACE;
+    if (!aligned16(pyramid) || (reinterpret_cast<uintptr_t>(workspace) & 1023u)) return RPE_ERR_ALIGNMENT;
+    int rc = load_encode();
+    if (rc != RPE_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int split = precision == RPE_CORR_TF32X3;
+    const int Kp = split ? 3 * C : C;
+    float *opA = reinterpret_cast<float *>(workspace);
+    float *opB = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + rpe_corr_workspace_bytes(B, C, h, w, precision) / 2);
+
+    dim3 pgrid((Q + 31) / 32, C / 32, B);
+    corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap1, opA, C, Q, split, 0);
+    RPE_LAUNCH_CHECK();
+    corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap2, opB, C, Q, split, 1);
+    RPE_LAUNCH_CHECK();
+
+    PyrDims d = pyr_dims(B, h, w, num_levels);
+    CUtensorMap ma, mb, mc;
+    if ((rc = make_map(&ma, opA, Kp, Q, B, kBK, kBM)) != RPE_OK) return rc;
+    if ((rc = make_map(&mb, opB, Kp, Q, B, kBK, kBN)) != RPE_OK) return rc;
+    if ((rc = make_map(&mc, pyramid + d.off[0], Q, Q, B, kEpiCols, kBM)) != RPE_OK) return rc;
+
+    GemmShape s;
+    s.B = B, s.Q = Q, s.Kp = Kp;
+    s.m_tiles = (Q + kBM - 1) / kBM;
+    s.n_tiles = (Q + kBN - 1) / kBN;
+    s.scale = 1.0f / sqrtf((float)C);
+    static bool attr_set = false;
+    if (!attr_set) {
+        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        attr_set = true;
+    }
+    int grid = sm_count();
+    const int tiles = s.B * s.m_tiles * s.n_tiles;
+    if (grid > tiles) grid = tiles;
+    corr_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
+    RPE_LAUNCH_CHECK();
+
+    if (num_levels > 1) {
+        size_t smem = 0;
+        for (int l = 0; l < num_levels; ++l) smem += (size_t)d.h[l] * d.w[l] * sizeof(float);
+        if (smem > 200 * 1024) return RPE_ERR_INVALID_ARG;
+        static size_t pool_attr = 0;
+        if (smem > 48 * 1024 && smem > pool_attr) {
+            RPE_CUDA_TRY(cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            pool_attr = smem;
+        }
+        corr_pool_kernel<<<B * Q, 256, smem, st>>>(pyramid, d);
+        RPE_LAUNCH_CHECK();
+    }
+    return RPE_OK;
+}
+
+int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B, int h, int w, int num_levels, int radius,
+                    void *stream) {
+    using namespace rpe;
+    if (!pyramid || !coords || !out) return RPE_ERR_INVALID_ARG;
+    if (B <= 0 || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4 || radius < 1 || 2 * radius + 2 > kMaxWin)
+        return RPE_ERR_INVALID_ARG;
+    const int Q = h * w;
+    PyrDims d = pyr_dims(B, h, w, num_levels);
+    const int n = 2 * radius + 1;
+    const int nch = num_levels * n * n;
+    const size_t smem = ((size_t)nch * (kLookupQ + 1) + 8 * kMaxWin * kMaxWin) * sizeof(float);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    dim3 grid((Q + kLookupQ - 1) / kLookupQ, B);
+    corr_lookup_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pyramid, d, coords, out, Q, radius);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,251 @@
+"""torch-tensor front end of the C ABI (include/rpe_b200.h).  Pure plumbing: argument checks, output
+allocation, raw pointers + the current CUDA stream.  Every function raises ``RpeError`` when the
+library is missing or a tensor is not a contiguous CUDA tensor -- there is no fallback path."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import RpeError, check
+
+__all__ = ["depth_proj", "proj", "warp8_mask", "downsample8_cat", "pose_solve", "PoseSolution", "CorrPyramid",
+           "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3"]
+
+SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = _lib.SOLVER_LBFGS_REF, _lib.SOLVER_GN, _lib.SOLVER_EVAL_ONLY
+CORR_TF32, CORR_TF32X3 = _lib.CORR_TF32, _lib.CORR_TF32X3
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name, shape=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RpeError(f"{name}: expected a CUDA tensor (rpe_b200 has no CPU path), got "
+                       f"{type(t).__name__}{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.dtype != dtype:
+        raise RpeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RpeError(f"{name}: tensor must be contiguous")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RpeError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 2
+# ---------------------------------------------------------------------------------------------
+def depth_proj(stereo_flow, bf, K, mask=None, want_pcl=True):
+    """rpe_depth_proj: (depth (n,1,H,W), valid bool (n,1,H,W), pcl (n,3,H,W)); ``mask &= valid`` in place."""
+    n, _, H, W = stereo_flow.shape
+    _chk(stereo_flow, torch.float32, "stereo_flow", (n, 2, H, W))
+    _chk(bf, torch.float32, "baseline", (n,))
+    _chk(K, torch.float32, "intrinsics", (n, 3, 3))
+    if mask is not None:
+        _chk(mask, torch.bool, "mask", (n, 1, H, W))
+    depth = torch.empty((n, 1, H, W), device=stereo_flow.device, dtype=torch.float32)
+    valid = torch.empty((n, 1, H, W), device=stereo_flow.device, dtype=torch.bool)
+    pcl = torch.empty((n, 3, H, W), device=stereo_flow.device, dtype=torch.float32) if want_pcl else None
+    check(_lib.lib().rpe_depth_proj(_p(stereo_flow), _p(bf), _p(K), _p(mask), _p(depth), _p(valid), _p(pcl),
+                                    n, H, W, _stream()), "rpe_depth_proj")
+    return depth, valid, pcl
+
+
+def proj(depth, K, rescale=None):
+    """rpe_proj: pcl (n,3,H,W) = depth * K^-1 [u+.5, v+.5, 1]; ``rescale`` = tracker scale for the fp32 round trip."""
+    n, _, H, W = depth.shape
+    _chk(depth, torch.float32, "depth", (n, 1, H, W))
+    _chk(K, torch.float32, "intrinsics", (n, 3, 3))
+    pcl = torch.empty((n, 3, H, W), device=depth.device, dtype=torch.float32)
+    check(_lib.lib().rpe_proj(_p(depth), _p(K), _p(pcl), 0 if rescale is None else 1,
+                              1.0 if rescale is None else float(rescale), n, H, W, _stream()), "rpe_proj")
+    return pcl
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 5
+# ---------------------------------------------------------------------------------------------
+def warp8_mask(pcl2, img2, sflow2, mask2, flow):
+    """rpe_warp8_mask: returns (pcl2w, img2w, sflow2w, mask2w); any source may be None."""
+    n, _, H, W = flow.shape
+    _chk(flow, torch.float32, "flow", (n, 2, H, W))
+    outs = []
+    for t, c, name in ((pcl2, 3, "pcl2"), (img2, 3, "img2"), (sflow2, 2, "sflow2")):
+        if t is None:
+            outs.append(None)
+        else:
+            _chk(t, torch.float32, name, (n, c, H, W))
+            outs.append(torch.empty_like(t))
+    m_out = None
+    if mask2 is not None:
+        _chk(mask2, torch.bool, "mask2", (n, 1, H, W))
+        m_out = torch.empty_like(mask2)
+    check(_lib.lib().rpe_warp8_mask(_p(pcl2), _p(img2), _p(sflow2), _p(mask2), _p(flow), _p(outs[0]), _p(outs[1]),
+                                    _p(outs[2]), _p(m_out), n, H, W, _stream()), "rpe_warp8_mask")
+    return outs[0], outs[1], outs[2], m_out
+
+
+def downsample8_cat(srcs, out=None, ch_offset=0):
+    """rpe_downsample8_cat: 1/8 bilinear down-sampling of up to 3 NCHW tensors, concatenated on channels."""
+    srcs = [s for s in srcs if s is not None]
+    if not 1 <= len(srcs) <= 3:
+        raise RpeError("downsample8_cat takes 1..3 sources")
+    n, _, H, W = srcs[0].shape
+    for i, s in enumerate(srcs):
+        _chk(s, torch.float32, f"src{i}", (n, s.shape[1], H, W))
+    ctot = sum(s.shape[1] for s in srcs)
+    if out is None:
+        out = torch.empty((n, ctot, H // 8, W // 8), device=srcs[0].device, dtype=torch.float32)
+        ch_offset = 0
+    _chk(out, torch.float32, "out")
+    a = srcs + [None] * (3 - len(srcs))
+    ch = [0 if s is None else s.shape[1] for s in a]
+    check(_lib.lib().rpe_downsample8_cat(_p(a[0]), ch[0], _p(a[1]), ch[1], _p(a[2]), ch[2], _p(out), ch_offset,
+                                         out.shape[1], n, H, W, _stream()), "rpe_downsample8_cat")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# stages 3 + 4
+# ---------------------------------------------------------------------------------------------
+class PoseSolution:
+    """Device-resident result of rpe_pose_solve; nothing is copied to the host until asked."""
+
+    def __init__(self, out, pose_f32, log_f32, trace):
+        self.out, self.pose, self.log, self.trace = out, pose_f32, log_f32, trace
+
+    @property
+    def pose64(self):
+        return self.out[:, 0:7]
+
+    @property
+    def log64(self):
+        return self.out[:, 7:13]
+
+    @property
+    def loss(self):
+        return self.out[:, 13]
+
+    @property
+    def n_evals(self):
+        return self.out[:, 16]
+
+    @property
+    def status(self):
+        return self.out[:, 18]
+
+    @property
+    def grad(self):
+        return self.out[:, 19:25]
+
+    def hessian(self):
+        """(n,6,6) symmetric GN Hessian assembled from the stored upper triangle."""
+        n = self.out.shape[0]
+        H = torch.zeros((n, 6, 6), dtype=torch.float64, device=self.out.device)
+        iu = torch.triu_indices(6, 6, device=self.out.device)
+        H[:, iu[0], iu[1]] = self.out[:, 25:46]
+        return H + H.transpose(1, 2) - torch.diag_embed(torch.diagonal(H, dim1=1, dim2=2))
+
+
+_pose_ws = {}
+
+
+def _pose_workspace(device, n):
+    key = (device.index, )
+    need = _lib.lib().rpe_pose_workspace_bytes(n)
+    ws = _pose_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _pose_ws[key] = ws
+    return ws
+
+
+def pose_solve(flow, pcl1, pcl2, w1, w2, m1, m2, K, lw, mode=SOLVER_LBFGS_REF, max_iter=20, init_pose=None,
+               with_hessian=False, trace_cap=0):
+    """rpe_pose_solve on n independent pairs.  w1 / w2 may be None (unit confidence)."""
+    n, _, H, W = flow.shape
+    _chk(flow, torch.float32, "flow", (n, 2, H, W))
+    _chk(pcl1, torch.float32, "pcl1", (n, 3, H, W))
+    _chk(pcl2, torch.float32, "pcl2", (n, 3, H, W))
+    if w1 is not None:
+        _chk(w1, torch.float32, "weights1", (n, 1, H, W))
+    if w2 is not None:
+        _chk(w2, torch.float32, "weights2", (n, 1, H, W))
+    _chk(m1, torch.bool, "mask1", (n, 1, H, W))
+    _chk(m2, torch.bool, "mask2", (n, 1, H, W))
+    _chk(K, torch.float32, "intrinsics", (n, 3, 3))
+    _chk(lw, torch.float32, "loss_weight", (n, 2))
+    if init_pose is not None:
+        _chk(init_pose, torch.float64, "init_pose", (n, 7))
+    dev = flow.device
+    out = torch.zeros((n, _lib.POSE_OUT_STRIDE), dtype=torch.float64, device=dev)
+    pose32 = torch.empty((n, 7), dtype=torch.float32, device=dev)
+    log32 = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    trace = torch.zeros((n, trace_cap, 16), dtype=torch.float64, device=dev) if trace_cap > 0 else None
+    ws = _pose_workspace(dev, n)
+    pb = _lib.PoseProblem(flow.data_ptr(), pcl1.data_ptr(), pcl2.data_ptr(), 0 if w1 is None else w1.data_ptr(),
+                          0 if w2 is None else w2.data_ptr(), m1.data_ptr(), m2.data_ptr(), K.data_ptr(),
+                          lw.data_ptr(), 0 if init_pose is None else init_pose.data_ptr(), n, H, W)
+    check(_lib.lib().rpe_pose_solve(C.byref(pb), int(mode), int(max_iter), 1 if with_hessian else 0, _p(out),
+                                    _p(pose32), _p(log32), _p(trace), int(trace_cap), _p(ws), ws.numel(), _stream()),
+          "rpe_pose_solve")
+    return PoseSolution(out, pose32, log32, trace)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage 1
+# ---------------------------------------------------------------------------------------------
+class CorrPyramid:
+    """Device-resident 4-level all-pairs correlation pyramid (rpe_corr_build) + window lookup
+    (rpe_corr_lookup).  Buffers are cached per shape and reused across frames."""
+
+    _cache = {}
+
+    def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=CORR_TF32):
+        B, Cc, h, w = fmap1.shape
+        _chk(fmap1, torch.float32, "fmap1", (B, Cc, h, w))
+        _chk(fmap2, torch.float32, "fmap2", (B, Cc, h, w))
+        self.B, self.C, self.h, self.w = B, Cc, h, w
+        self.num_levels, self.radius = num_levels, radius
+        l = _lib.lib()
+        key = (fmap1.device.index, B, Cc, h, w, num_levels, precision)
+        bufs = CorrPyramid._cache.get(key)
+        if bufs is None:
+            pyr = torch.empty(l.rpe_corr_pyramid_bytes(B, h, w, num_levels) // 4, dtype=torch.float32, device=fmap1.device)
+            ws = torch.empty(l.rpe_corr_workspace_bytes(B, Cc, h, w, precision) + 1024, dtype=torch.uint8, device=fmap1.device)
+            bufs = (pyr, ws)
+            CorrPyramid._cache[key] = bufs
+        self.pyramid, self._ws = bufs
+        ws_ptr = (self._ws.data_ptr() + 1023) & ~1023
+        check(l.rpe_corr_build(_p(fmap1), _p(fmap2), _p(self.pyramid), B, Cc, h, w, num_levels, int(precision),
+                               C.c_void_p(ws_ptr), self._ws.numel() - (ws_ptr - self._ws.data_ptr()), _stream()),
+              "rpe_corr_build")
+
+    def level(self, l):
+        """View of pyramid level l as (B*h*w, 1, h>>l, w>>l) like the reference's corr_pyramid[l]."""
+        off = _lib.lib().rpe_corr_level_offset(self.B, self.h, self.w, l) // 4
+        hl, wl = self.h >> l, self.w >> l
+        n = self.B * self.h * self.w
+        return self.pyramid[off:off + n * hl * wl].view(n, 1, hl, wl)
+
+    def __call__(self, coords):
+        _chk(coords, torch.float32, "coords", (self.B, 2, self.h, self.w))
+        n = 2 * self.radius + 1
+        out = torch.empty((self.B, self.num_levels * n * n, self.h, self.w), dtype=torch.float32, device=coords.device)
+        check(_lib.lib().rpe_corr_lookup(_p(self.pyramid), _p(coords), _p(out), self.B, self.h, self.w,
+                                         self.num_levels, self.radius, _stream()), "rpe_corr_lookup")
+        return out
+
+
+def convex_upsample8(flow, mask):
+    """rpe_convex_upsample8: flow (B,2,h,w), mask (B,576,h,w) -> (B,2,8h,8w)."""
+    B, _, h, w = flow.shape
+    _chk(flow, torch.float32, "flow", (B, 2, h, w))
+    _chk(mask, torch.float32, "mask", (B, 576, h, w))
+    out = torch.empty((B, 2, 8 * h, 8 * w), dtype=torch.float32, device=flow.device)
+    check(_lib.lib().rpe_convex_upsample8(_p(flow), _p(mask), _p(out), B, h, w, _stream()), "rpe_convex_upsample8")
+    return out

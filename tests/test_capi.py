@@ -1,0 +1,57 @@
+"""CPU: the C-ABI shared library loads and exports every symbol declared in include/rpe_b200.h
+(no compute calls -- there is no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rpe_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rpe_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported():
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib, build
+    build.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(handle, n), f"{n} declared in include/rpe_b200.h but not exported"
+
+
+def test_ctypes_binding_covers_header():
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib
+    assert set(_declared_symbols()) == set(_lib.SIGNATURES)
+
+
+def test_host_only_entry_points():
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib
+    l = _lib.lib()
+    assert l.rpe_version() >= 100
+    assert l.rpe_status_string(0) == b"ok"
+    assert l.rpe_status_string(-3) == b"workspace too small"
+    # pyramid layout arithmetic is host side: 4 levels of a 64x80 grid, batch 2
+    q = 64 * 80
+    assert l.rpe_corr_level_offset(2, 64, 80, 0) == 0
+    assert l.rpe_corr_level_offset(2, 64, 80, 1) == 2 * q * q * 4
+    assert l.rpe_corr_pyramid_bytes(2, 64, 80, 4) >= 2 * q * (q + q // 4 + q // 16 + q // 64) * 4
+    assert l.rpe_pose_workspace_bytes(64) > 0
+    assert l.rpe_pose_set_groups(0) == -1 and l.rpe_pose_set_groups(8) == 0
+
+
+def test_ops_refuse_cpu_tensors():
+    import torch
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import ops
+    from rpe_b200._lib import RpeError
+    with pytest.raises(RpeError):
+        ops.proj(torch.ones(1, 1, 8, 8), torch.eye(3)[None])
