@@ -77,6 +77,12 @@ int rpe_warp8_mask(const float *pcl2, const float *img2, const float *sflow2, co
                    const float *flow, float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w,
                    int n, int H, int W, void *stream);
 
+/* Operator-level seams with the reference's generic signatures
+ * (/root/reference/core/interpol/flow_utils.py:4-14 remap_from_flow, :17-26 remap_from_flow_nearest):
+ * x (n,C,H,W) f32 warped by flow (n,2,H,W) -> out (n,C,H,W); zeros outside the image. */
+int rpe_remap_bilinear(const float *x, int C, const float *flow, float *out, int n, int H, int W, void *stream);
+int rpe_remap_nearest(const float *x, int C, const float *flow, float *out, int n, int H, int W, void *stream);
+
 /* Replaces F.interpolate(cat(stereo_flow, image, pcl), scale_factor=0.125, mode='bilinear')
  * (/root/reference/core/pose/pose_net.py:110-113): out[c, i, j] = mean of the 2x2 pixels
  * (8i+3..8i+4, 8j+3..8j+4).  Up to three sources concatenated along channels:

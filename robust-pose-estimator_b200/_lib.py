@@ -32,6 +32,8 @@ SIGNATURES = {
     "rpe_depth_proj": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "rpe_proj": (_I, [_P, _P, _P, _I, _F, _I, _I, _I, _P]),
     "rpe_warp8_mask": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "rpe_remap_bilinear": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
+    "rpe_remap_nearest": (_I, [_P, _I, _P, _P, _I, _I, _I, _P]),
     "rpe_downsample8_cat": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_pose_workspace_bytes": (_Z, [_I]),
     "rpe_pose_set_groups": (_I, [_I]),

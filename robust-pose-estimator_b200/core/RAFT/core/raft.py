@@ -1,0 +1,120 @@
+"""RAFT optical flow with the reference's interface (/root/reference/core/RAFT/core/raft.py:24-137).
+
+The convolutional trunk runs through torch (cuDNN) from a functional weight table; the correlation
+volume, its lookup and the convex up-sampling are the hand-written sm_100a kernels.  Deviations that
+do not change the consumed result:
+  * only the final flow prediction is up-sampled unless ``all_predictions=True`` (the pose path
+    reads ``flow_predictions[-1]`` only, pose_net.py:66-67);
+  * ``precision``: "fp32" (parity mode: cuDNN fp32, TF32 off, correlation TF32x3 split) |
+    "tf32" | "bf16" / "fp16" (autocast like the reference's CUDA run, raft.py:92,100,117)."""
+import contextlib
+
+import torch
+from torch import nn
+
+from .... import ops
+from ...utils.param_tree import build_tree
+from .corr import CorrBlock
+from .extractor import encoder_entries, encoder_forward
+from .update import prepare_update_weights, update_entries, update_forward
+
+_AUTOCAST = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def coords_grid(batch, ht, wd, device):
+    ys, xs = torch.meshgrid(torch.arange(ht, device=device), torch.arange(wd, device=device), indexing="ij")
+    return torch.stack((xs, ys), 0).float()[None].repeat(batch, 1, 1, 1)
+
+
+class RAFT(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        if config.get("small", False):
+            raise NotImplementedError("only the 'basic' RAFT of the shipped checkpoints is on the f2f path")
+        self.config = config
+        config["corr_levels"], config["corr_radius"] = 4, 4          # raft.py:37-38
+        self.hidden_dim = self.context_dim = 128
+        self.precision = config.get("precision", "fp32")
+        entries = (encoder_entries("fnet.", "instance", 256) + encoder_entries("cnet.", "batch", 256)
+                   + update_entries("update_block."))
+        tree = build_tree(entries)
+        self.fnet, self.cnet, self.update_block = tree.fnet, tree.cnet, tree.update_block
+        self._W = None
+
+    # ---- weight table ------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        self._W = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._W = None
+        return super().load_state_dict(*a, **k)
+
+    def weights(self):
+        if self._W is None:
+            W = {}
+            for name in ("fnet", "cnet", "update_block"):
+                W.update(getattr(self, name).table(name + "."))
+            self._W = prepare_update_weights(W, "update_block.")
+        return self._W
+
+    def freeze_bn(self):
+        return self                                               # BatchNorm is always evaluated in eval mode here
+
+    # ---- building blocks reused by the batched tracker -----------------------------------------
+    def _ctx(self):
+        """Precision context of the convolutional trunk: fp32 = cuDNN fp32 with TF32 off (parity mode)."""
+        stack = contextlib.ExitStack()
+        dt = _AUTOCAST.get(self.precision)
+        stack.enter_context(torch.backends.cudnn.flags(enabled=True, benchmark=self.precision != "fp32",
+                                                       deterministic=False, allow_tf32=self.precision != "fp32"))
+        stack.enter_context(torch.autocast("cuda", dtype=dt) if dt is not None else torch.autocast("cuda", enabled=False))
+        return stack
+
+    def features(self, images):
+        """fnet over (N,3,H,W) images in 0..255 -> (N,256,H/8,W/8) float32."""
+        x = (2 * (images / 255.0) - 1.0).contiguous()
+        with self._ctx():
+            return encoder_forward(x, self.weights(), "fnet.", "instance").float()
+
+    def context(self, images):
+        """cnet -> (net, inp) = (tanh, relu) halves, each (N,128,H/8,W/8)."""
+        x = (2 * (images / 255.0) - 1.0).contiguous()
+        with self._ctx():
+            c = encoder_forward(x, self.weights(), "cnet.", "batch")
+            net, inp = torch.split(c, [self.hidden_dim, self.context_dim], dim=1)
+            return torch.tanh(net), torch.relu(inp)
+
+    def refine(self, fmap1, fmap2, net, inp, iters=12, flow_init=None, upsample=True, all_predictions=False):
+        """Correlation pyramid + `iters` GRU updates + convex up-sampling."""
+        B, _, h, w = fmap1.shape
+        corr_prec = ops.CORR_TF32X3 if self.precision == "fp32" else ops.CORR_TF32
+        corr_fn = CorrBlock(fmap1, fmap2, radius=self.config["corr_radius"], precision=corr_prec)
+        coords0 = coords_grid(B, h, w, fmap1.device)
+        coords1 = coords0.clone() if flow_init is None else coords0 + flow_init
+        W = self.weights()
+        preds = []
+        for itr in range(iters):
+            corr = corr_fn(coords1)
+            flow = coords1 - coords0
+            last = itr == iters - 1
+            with self._ctx():
+                net, up_mask, delta = update_forward(net, inp, corr, flow, W, "update_block.",
+                                                     want_mask=upsample and (last or all_predictions))
+            coords1 = coords1 + delta.float()
+            if last or all_predictions:
+                lo = (coords1 - coords0).contiguous()
+                preds.append(ops.convex_upsample8(lo, up_mask.float().contiguous()) if upsample else lo)
+        return preds, net, inp, coords1 - coords0
+
+    # ---- reference interface -------------------------------------------------------------------
+    def forward(self, image1, image2, iters=12, flow_init=None, test_mode=False, upsample=True, all_predictions=False):
+        with torch.no_grad():
+            B = image1.shape[0]
+            fmaps = self.features(torch.cat((image1, image2), 0))
+            net, inp = self.context(image1)
+            preds, net, inp, flow_lo = self.refine(fmaps[:B].contiguous(), fmaps[B:].contiguous(), net, inp, iters,
+                                                   flow_init, upsample, all_predictions)
+        if test_mode:
+            return flow_lo, preds[-1]
+        return preds, net, inp

@@ -1,0 +1,121 @@
+"""Frame-to-frame tracker with the reference's interface
+(/root/reference/core/pose/pose_estimator.py:11-160).  Only the f2f branch exists here: the
+frame-to-model branch (SurfelMap) is out of scope.
+
+Differences that do not change results:
+  * the failure guard (NaN or |log| > 0.1 -> identity, pose_estimator.py:81-85) is evaluated on the
+    device without a host synchronisation; the flags are kept in ``failure_flags`` and the reference's
+    RuntimeWarning is raised lazily by ``check_failures()`` (or immediately with config['sync_guard']).
+"""
+import warnings
+from collections import OrderedDict
+
+import torch
+
+from ...lie import SE3
+from ..utils.frame_class import Frame
+from .pose_net import PoseNet
+
+
+class PoseEstimator(torch.nn.Module):
+    def __init__(self, config, intrinsics, baseline, checkpoint, img_shape, init_pose=None):
+        """
+        :param config: the ``slam`` section of configuration/infer_f2f.yaml (+ optional keys
+                       ``precision`` fp32|tf32|bf16|fp16, ``solver`` lbfgs_ref|gn, ``sync_guard``)
+        :param intrinsics: rectified camera intrinsics (3,3)
+        :param baseline: stereo baseline x focal length in pixel * mm ("bf")
+        :param checkpoint: path of a reference checkpoint (trained/*.pth), or a dict {state_dict, config},
+                           or None for random initialisation of the same architecture
+        :param img_shape: (W, H) like the reference's ``img_size``
+        :param init_pose: SE3 of shape (1,), defaults to identity
+        """
+        super().__init__()
+        if not config.get("frame2frame", True):
+            raise NotImplementedError("only the frame-to-frame configuration is implemented on this path")
+        if checkpoint is None:
+            checkp = {"config": {"model": {"iters": 12, "dropout": 0.0, "small": False}}, "state_dict": None}
+        elif isinstance(checkpoint, dict):
+            checkp = checkpoint
+        else:
+            checkp = torch.load(checkpoint, map_location="cpu", weights_only=False)
+        mcfg = dict(checkp["config"]["model"])
+        mcfg["image_shape"] = (img_shape[1], img_shape[0])
+        mcfg["lbgfs_iters"] = config["lbgfs_iters"]
+        mcfg["use_weights"] = config["conf_weighing"]
+        mcfg["precision"] = config.get("precision", "fp32")
+        mcfg["solver"] = config.get("solver", "lbfgs_ref")
+        model = PoseNet(mcfg)
+        if checkp["state_dict"] is not None:
+            model.load_state_dict(OrderedDict((k.replace("module.", ""), v) for k, v in checkp["state_dict"].items()))
+        model.eval()
+        self.model = model
+        self.intrinsics = intrinsics.unsqueeze(0).float()
+        self.register_buffer("scale", torch.tensor(1 / config["depth_clipping"][1]), persistent=False)
+        self.register_buffer("baseline", torch.tensor(baseline).unsqueeze(0).float(), persistent=False)
+        self.last_pose = (SE3.Identity(1) if init_pose is None else init_pose).float()
+        self.last_frame = None
+        self.frame = None
+        self.frame2frame = True
+        self.scene = None
+        self.config = config
+        self.failure_flags = []
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self.intrinsics = fn(self.intrinsics)
+        self.last_pose = SE3(fn(self.last_pose.data))
+        return out
+
+    def forward(self, limg, rimg, mask):
+        """limg, rimg (1,3,H,W) float 0..255, mask (1,1,H,W) bool -> (pose SE3 in mm, None, flow, weights)."""
+        self.last_pose = self.last_pose.to(limg.device)
+        self.last_frame = self.frame
+        self.frame = Frame(limg, rimg, mask=mask)
+        rel_pose, ret_frame, flow, weights = self.get_pose_f2f()
+
+        # pose_estimator.py:81-87, evaluated on the device
+        bad = torch.isnan(rel_pose.vec()).any() | (torch.abs(rel_pose.log()) > 1.0e-1).any()
+        ident = SE3.IdentityLike(self.last_pose)
+        rel_pose = SE3(torch.where(bad, ident.data, rel_pose.vec().to(ident.dtype)))
+        self.failure_flags.append(bad)
+        if self.config.get("sync_guard", False) and bool(bad):
+            warnings.warn("pose estimation not converged, skip.", RuntimeWarning)
+        self.last_frame = ret_frame
+        rel_pose = rel_pose.scale(1 / self.scale)                  # de-normalise depth scaling
+        self.last_pose = self.last_pose * rel_pose.inv()           # chain transforms
+        return self.last_pose, self.scene, flow, weights
+
+    def get_pose_f2f(self):
+        flow = None
+        if self.last_frame is None:
+            rel = SE3.IdentityLike(self.last_pose)
+            depth, stereo_flow, valid = self.model.flow2depth(self.frame.img, self.frame.rimg, self.baseline * self.scale)
+            self.frame.depth = depth / self.scale
+            self.frame.flow = stereo_flow                            # `valid` is discarded
+            return rel, None, None, None
+        rel, depth1, depth2, weights, flow, stereo_flow = self.model.infer(
+            self.last_frame.img, self.frame.img, self.intrinsics, self.baseline * self.scale,
+            depth1=self.last_frame.depth * self.scale, image2r=self.frame.rimg, mask1=self.last_frame.mask,
+            mask2=self.frame.mask, stereo_flow1=self.last_frame.flow, ret_details=True)
+        self.frame.depth = depth2 / self.scale
+        self.frame.flow = stereo_flow
+        return rel, self.last_frame, flow, weights
+
+    def check_failures(self):
+        """Synchronise and raise the reference's warning for every failed pair; returns their indices."""
+        if not self.failure_flags:
+            return []
+        idx = torch.stack(self.failure_flags).nonzero().flatten().tolist()
+        for _ in idx:
+            warnings.warn("pose estimation not converged, skip.", RuntimeWarning)
+        return idx
+
+    @property
+    def device(self):
+        return self.last_pose.device
+
+    def get_last_frame(self):
+        return self.last_frame
+
+    def get_frame(self):
+        return self.frame

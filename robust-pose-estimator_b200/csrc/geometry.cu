@@ -165,6 +165,21 @@ __global__ void __launch_bounds__(256) warp8_mask_kernel(WarpSrc t, const uint8_
     }
 }
 
+// Nearest-neighbour warp of a float tensor (remap_from_flow_nearest on arbitrary inputs).
+__global__ void __launch_bounds__(256) remap_nearest_kernel(const float *__restrict__ x, const float *__restrict__ flow,
+                                                            float *__restrict__ out, int C, int H, int W) {
+    const int HW = H * W;
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= HW) return;
+    const int row = i / W, col = i - row * W;
+    const float xs = rintf(sample_coord(__ldg(flow + (size_t)b * 2 * HW + i), col, W));
+    const float ys = rintf(sample_coord(__ldg(flow + (size_t)b * 2 * HW + HW + i), row, H));
+    const bool ok = xs > -1.0f && xs < (float)W && ys > -1.0f && ys < (float)H;
+    const int o = ok ? (int)ys * W + (int)xs : 0;
+    for (int c = 0; c < C; ++c) out[((size_t)b * C + c) * HW + i] = ok ? __ldg(x + ((size_t)b * C + c) * HW + o) : 0.0f;
+}
+
 struct CatSrc {
     const float *src[3];
     int ch[3];
@@ -244,6 +259,26 @@ int rpe_warp8_mask(const float *pcl2, const float *img2, const float *sflow2, co
     t.src[2] = sflow2, t.dst[2] = sflow2w, t.ch[2] = 2;
     dim3 grid((H * W + 255) / 256, n);
     rpe::warp8_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, mask2, flow, mask2w, H, W);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_remap_bilinear(const float *x, int C, const float *flow, float *out, int n, int H, int W, void *stream) {
+    if (!x || !flow || !out || C <= 0 || n <= 0 || H <= 1 || W <= 1) return RPE_ERR_INVALID_ARG;
+    rpe::WarpSrc t;
+    t.src[0] = x, t.dst[0] = out, t.ch[0] = C;
+    t.src[1] = nullptr, t.dst[1] = nullptr, t.ch[1] = 0;
+    t.src[2] = nullptr, t.dst[2] = nullptr, t.ch[2] = 0;
+    dim3 grid((H * W + 255) / 256, n);
+    rpe::warp8_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, nullptr, flow, nullptr, H, W);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_remap_nearest(const float *x, int C, const float *flow, float *out, int n, int H, int W, void *stream) {
+    if (!x || !flow || !out || C <= 0 || n <= 0 || H <= 1 || W <= 1) return RPE_ERR_INVALID_ARG;
+    dim3 grid((H * W + 255) / 256, n);
+    rpe::remap_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, flow, out, C, H, W);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

@@ -89,6 +89,26 @@ def warp8_mask(pcl2, img2, sflow2, mask2, flow):
     return outs[0], outs[1], outs[2], m_out
 
 
+def remap_bilinear(x, flow):
+    """rpe_remap_bilinear: generic remap_from_flow (any channel count)."""
+    n, Cc, H, W = x.shape
+    _chk(x, torch.float32, "x")
+    _chk(flow, torch.float32, "flow", (n, 2, H, W))
+    out = torch.empty_like(x)
+    check(_lib.lib().rpe_remap_bilinear(_p(x), Cc, _p(flow), _p(out), n, H, W, _stream()), "rpe_remap_bilinear")
+    return out
+
+
+def remap_nearest(x, flow):
+    """rpe_remap_nearest: generic remap_from_flow_nearest (float in / float out)."""
+    n, Cc, H, W = x.shape
+    _chk(x, torch.float32, "x")
+    _chk(flow, torch.float32, "flow", (n, 2, H, W))
+    out = torch.empty_like(x)
+    check(_lib.lib().rpe_remap_nearest(_p(x), Cc, _p(flow), _p(out), n, H, W, _stream()), "rpe_remap_nearest")
+    return out
+
+
 def downsample8_cat(srcs, out=None, ch_offset=0):
     """rpe_downsample8_cat: 1/8 bilinear down-sampling of up to 3 NCHW tensors, concatenated on channels."""
     srcs = [s for s in srcs if s is not None]

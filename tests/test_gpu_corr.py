@@ -95,7 +95,7 @@ def test_lookup_full_size_vs_oracle_sample(ops):
         q = y * w + x
         sub = [p[b:b + 1, q:q + 1] for p in pyr]
         ref = corr_np.lookup(sub, coords[b:b + 1, :, y:y + 1, x:x + 1])
-        np.testing.assert_allclose(out[b, :, y, x], ref[0, :, 0, 0], atol=3e-6)
+        np.testing.assert_allclose(out[b, :, y, x], ref[0, :, 0, 0], atol=1e-5)   # shared sub-pixel fraction per window
     # linearity in the volume: lookup(2 * pyramid) == 2 * lookup(pyramid)
     cp.pyramid.mul_(2.0)
     out2 = cp(dev(coords)).cpu().numpy()
