@@ -144,6 +144,14 @@ int rpe_pose_solve(const rpe_pose_problem *problem_host, int mode, int max_iter,
                    double *out, float *pose_f32, float *log_f32, double *trace, int trace_cap,
                    void *workspace, size_t workspace_bytes, void *stream);
 
+/* Host-side (CPU pointers) trajectory composition -- replaces the per-frame tail of PoseEstimator.forward
+ * (/root/reference/core/pose/pose_estimator.py:81-91): failure guard (NaN or |log| > 0.1 -> identity),
+ * rel.scale(1/scale), last_pose <- last_pose * rel^-1, in fp32.
+ *   rel_host (n,7), log_host (n,6): per-pair solver outputs; init_pose_host (7);
+ *   abs_out_host (n+1,7): init pose followed by the pose after every pair; failed_out_host (n) or NULL. */
+int rpe_compose_trajectory_host(const float *rel_host, const float *log_host, int n, const float *init_pose_host,
+                                float inv_scale, float *abs_out_host, unsigned char *failed_out_host);
+
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- RAFT CorrBlock: all-pairs correlation GEMM (tcgen05 + TMA), pyramid, radius lookup.
  * ---------------------------------------------------------------------------------------------- */

@@ -38,6 +38,7 @@ SIGNATURES = {
     "rpe_pose_workspace_bytes": (_Z, [_I]),
     "rpe_pose_set_groups": (_I, [_I]),
     "rpe_pose_solve": (_I, [C.POINTER(PoseProblem), _I, _I, _I, _P, _P, _P, _P, _I, _P, _Z, _P]),
+    "rpe_compose_trajectory_host": (_I, [_P, _P, _I, _P, _F, _P, _P]),
     "rpe_corr_pyramid_bytes": (_Z, [_I, _I, _I, _I]),
     "rpe_corr_level_offset": (_Z, [_I, _I, _I, _I]),
     "rpe_corr_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),

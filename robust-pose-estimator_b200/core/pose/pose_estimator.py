@@ -101,6 +101,35 @@ class PoseEstimator(torch.nn.Module):
         self.frame.flow = stereo_flow
         return rel, self.last_frame, flow, weights
 
+    def infer_sequence(self, limgs, rimgs, masks, chunk=8, use_graphs=False):
+        """Throughput path: a whole sequence (T,3,H,W) / (T,1,H,W) on the device -> absolute poses
+        (T,7) float32 on the HOST (mm; row 0 = initial pose, like the reference's trajectory list) and the
+        per-pair failure flags (T-1,).  Pairs are solved in chunks by ``F2FEngine``; the trajectory is composed
+        on the host with rpe_compose_trajectory_host (one device->host copy of (T-1) x 13 floats)."""
+        import ctypes as C
+
+        from ... import _lib
+        from ...engine import F2FEngine
+        key = (chunk, use_graphs)
+        if getattr(self, "_engine_key", None) != key:
+            self._engine, self._engine_key = F2FEngine(self, chunk, use_graphs), key
+        self._engine.reset()
+        rel, log, evals = self._engine.infer_sequence(limgs, rimgs, masks)
+        n = rel.shape[0]
+        host = torch.cat((rel, log), 1).cpu().contiguous()                      # the only device->host transfer
+        rel_h, log_h = host[:, :7].contiguous(), host[:, 7:].contiguous()
+        init = self.last_pose.data.reshape(7).float().cpu().contiguous()
+        out = torch.empty((n + 1, 7), dtype=torch.float32)
+        failed = torch.zeros((max(n, 1),), dtype=torch.uint8)
+        inv_scale = float((1 / self.scale).float().cpu())
+        _lib.check(_lib.lib().rpe_compose_trajectory_host(C.c_void_p(rel_h.data_ptr()), C.c_void_p(log_h.data_ptr()), n,
+                                                          C.c_void_p(init.data_ptr()), inv_scale,
+                                                          C.c_void_p(out.data_ptr()), C.c_void_p(failed.data_ptr())),
+                   "rpe_compose_trajectory_host")
+        self.last_pose = SE3(out[-1:].clone().to(self.last_pose.device))
+        self.last_evals = evals
+        return out, failed[:n].bool()
+
     def check_failures(self):
         """Synchronise and raise the reference's warning for every failed pair; returns their indices."""
         if not self.failure_flags:

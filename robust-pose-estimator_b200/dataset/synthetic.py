@@ -8,7 +8,7 @@ ground truth is known.  numpy only (host side); images are quantised to uint8 li
 
 Geometry (mm): world = camera-1 frame.  Surface z = Z(x, y) (plane + smooth bumps), texture
 T(x, y) a sum of sine octaves.  A camera with extrinsics (R, t) (p_cam = R p_world + t) is rendered
-by fixed-point ray/height-field intersection.  Pixel centres at +0.5 (pinhole_transforms.py:15-17).
+by Newton ray/height-field intersection.  Pixel centres at +0.5 (pinhole_transforms.py:15-17).
 """
 import numpy as np
 
@@ -99,18 +99,26 @@ class SyntheticStereoSequence:
         self._rays = Kinv @ self._rays                                    # (3, HW), z = 1
 
     # ---- scene functions ------------------------------------------------------------------
-    def _Z(self, x, y):
+    def _Z(self, x, y, grad=False):
         z = self._z0 + self._slope[0] * x + self._slope[1] * y
+        zx = np.full_like(x, self._slope[0]) if grad else None
+        zy = np.full_like(x, self._slope[1]) if grad else None
         for a, w, p in zip(self._bump_amp, self._bump_w, self._bump_p):
-            z = z + a * np.sin(w[0] * x + w[1] * y + p)
-        return z
+            ph = w[0] * x + w[1] * y + p
+            z = z + a * np.sin(ph)
+            if grad:
+                c = a * np.cos(ph)
+                zx += c * w[0]
+                zy += c * w[1]
+        return (z, zx, zy) if grad else z
 
     def _tex(self, x, y):
         out = np.full((3,) + x.shape, 127.5)
         for a, w, p in zip(self._tex_a, self._tex_w, self._tex_p):
             ph = w[0] * x + w[1] * y
-            for c in range(3):
-                out[c] += a * np.sin(ph + p[c])
+            s, c = np.sin(ph), np.cos(ph)
+            for ch in range(3):                                   # sin(ph + p) = sin ph cos p + cos ph sin p
+                out[ch] += (a * np.cos(p[ch])) * s + (a * np.sin(p[ch])) * c
         return out
 
     def _render(self, R, t):
@@ -118,10 +126,11 @@ class SyntheticStereoSequence:
         o = -R.T @ t
         d = R.T @ self._rays                                               # world ray dirs, (3, HW)
         s = np.full(d.shape[1], self._z0)
-        for _ in range(25):                                                # fixed point on o.z + s d.z = Z(x, y)
+        for _ in range(8):                                                 # Newton on o.z + s d.z = Z(x(s), y(s))
             x = o[0] + s * d[0]
             y = o[1] + s * d[1]
-            s = (self._Z(x, y) - o[2]) / d[2]
+            z, zx, zy = self._Z(x, y, grad=True)
+            s = s - (o[2] + s * d[2] - z) / (d[2] - zx * d[0] - zy * d[1])
         x = o[0] + s * d[0]
         y = o[1] + s * d[1]
         rgb = np.clip(np.rint(self._tex(x, y)), 0, 255).astype(np.uint8).reshape(3, self.H, self.W)

@@ -1,0 +1,147 @@
+"""Batched frame-to-frame engine: the throughput path behind ``PoseEstimator.infer_sequence``.
+
+Frame pairs are independent in the f2f configuration, so a sequence is processed in
+chunks of C consecutive frames.  Per chunk (all on one CUDA stream, optionally replayed as one CUDA graph):
+
+  fnet over the 2C left/right images, cnet over the C left images          (cuDNN, once per image:
+                                                                             the reference recomputes the
+                                                                             features of frame k twice)
+  one RAFT refinement over 2C samples: C temporal pairs (k-1 -> k) + C stereo pairs (left k -> right k)
+      rpe_corr_build / 12 x rpe_corr_lookup / rpe_convex_upsample8          (sm_100a kernels)
+  rpe_depth_proj, rpe_proj, rpe_warp8_mask, rpe_downsample8_cat, confidence heads, rpe_pose_solve (n = C)
+
+State carried between chunks = the last frame's features, context, normalised depth, stereo flow, mask and
+image, exactly what the reference keeps in ``Frame`` (pose_estimator.py:62-63,115-122).  The arithmetic per
+pair is the same as the per-frame tracker; only batch composition differs (eval-mode BatchNorm and
+InstanceNorm are per-sample, so this is exact up to cuDNN algorithm selection)."""
+import torch
+
+from . import ops
+from .core.unet.unet import tiny_unet_forward
+
+
+class _FrameState:
+    __slots__ = ("img", "fmap", "net", "inp", "depth", "sflow", "mask")
+
+
+class F2FEngine:
+    def __init__(self, estimator, chunk=8, use_graphs=False):
+        self.est = estimator
+        self.model = estimator.model
+        self.chunk = int(chunk)
+        self.use_graphs = use_graphs
+        self._graphs = {}
+        self.reset()
+
+    def reset(self):
+        self.prev = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _first_frame(self, limg, rimg, mask):
+        """Frame 0 of a sequence: stereo depth only; its validity is NOT and-ed into the mask."""
+        raft = self.model.flow
+        f = raft.features(torch.cat((limg, rimg), 0))
+        net, inp = raft.context(limg)
+        preds, _, _, _ = raft.refine(f[0:1].contiguous(), f[1:2].contiguous(), net, inp)
+        bl = (self.est.baseline * self.est.scale).float().reshape(1)
+        eye = torch.eye(3, device=limg.device)[None]
+        depth, _, _ = ops.depth_proj(preds[-1], bl, eye, None, want_pcl=False)
+        st = _FrameState()
+        st.img, st.fmap, st.net, st.inp = limg, f[0:1].contiguous(), net, inp
+        st.depth, st.sflow, st.mask = depth, preds[-1], mask.clone()
+        return st
+
+    def _chunk_body(self, prev, limg, rimg, mask):
+        """C new frames given the state of the frame before them -> (pose (C,7), log (C,6), evals (C,), new state)."""
+        C = limg.shape[0]
+        raft, model, est = self.model.flow, self.model, self.est
+        H, W = limg.shape[-2:]
+        f = raft.features(torch.cat((limg, rimg), 0))
+        fL, fR = f[:C], f[C:]
+        net0, inp = raft.context(limg)
+        fL_prev = torch.cat((prev.fmap, fL[:-1]), 0)
+        net_prev = torch.cat((prev.net, net0[:-1]), 0)
+        inp_prev = torch.cat((prev.inp, inp[:-1]), 0)
+        # samples [0, C): temporal pairs (k-1 -> k); samples [C, 2C): stereo pairs of the new frames
+        preds, gru, ctx, _ = raft.refine(torch.cat((fL_prev, fL), 0).contiguous(), torch.cat((fL, fR), 0).contiguous(),
+                                         torch.cat((net_prev, net0), 0), torch.cat((inp_prev, inp), 0))
+        time_flow = preds[-1][:C].contiguous()
+        sflow = preds[-1][C:].contiguous()
+        K = est.intrinsics.float().expand(C, 3, 3).contiguous()
+        bl = (est.baseline * est.scale).float().reshape(1).expand(C).contiguous()
+        mask2 = mask.clone()
+        depth2, _, pcl2 = ops.depth_proj(sflow, bl, K, mask2)                       # mask2 &= stereo validity
+        depth_prev = torch.cat((prev.depth, depth2[:-1]), 0).contiguous()
+        pcl1 = ops.proj(depth_prev, K, rescale=float(est.scale))                  # (d / scale) * scale round trip
+        img_prev = torch.cat((prev.img, limg[:-1]), 0).contiguous()
+        sflow_prev = torch.cat((prev.sflow, sflow[:-1]), 0).contiguous()
+        mask1 = torch.cat((prev.mask, mask2[:-1]), 0).contiguous()
+        conf1, conf2, pcl2w, mask2w = model.get_weight_maps(pcl1, pcl2, img_prev, limg, mask2, time_flow, sflow_prev,
+                                                            sflow, gru[:C], ctx[:C])
+        lw = model.loss_weight[None, :].float().expand(C, 2).contiguous()
+        head = model.pose_head.problem
+        mode = ops.SOLVER_GN if head.solver == "gn" else ops.SOLVER_LBFGS_REF
+        iters = head.gn_iters if head.solver == "gn" else head.lbgfs_iters
+        sol = ops.pose_solve(time_flow, pcl1, pcl2w, conf1, conf2, mask1, mask2w, K, lw, mode=mode, max_iter=iters)
+        st = _FrameState()
+        st.img, st.fmap, st.net, st.inp = limg[-1:], fL[-1:].contiguous(), net0[-1:], inp[-1:]
+        st.depth, st.sflow, st.mask = depth2[-1:], sflow[-1:], mask2[-1:]
+        return sol.pose, sol.log, sol.n_evals, st
+
+    # ------------------------------------------------------------------------------------------------
+    def _graphed_chunk(self, prev, limg, rimg, mask):
+        """Replay a captured CUDA graph of ``_chunk_body`` (static input / state / output buffers per shape)."""
+        key = (tuple(limg.shape), limg.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            static = {"limg": limg.clone(), "rimg": rimg.clone(), "mask": mask.clone(), "prev": _FrameState()}
+            for k in _FrameState.__slots__:
+                setattr(static["prev"], k, getattr(prev, k).clone())
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                                    # warm-up outside capture
+                for _ in range(2):
+                    self._chunk_body(static["prev"], static["limg"], static["rimg"], static["mask"])
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static["out"] = self._chunk_body(static["prev"], static["limg"], static["rimg"], static["mask"])
+            g = (graph, static)
+            self._graphs[key] = g
+        graph, static = g
+        static["limg"].copy_(limg)
+        static["rimg"].copy_(rimg)
+        static["mask"].copy_(mask)
+        for k in _FrameState.__slots__:
+            getattr(static["prev"], k).copy_(getattr(prev, k))
+        graph.replay()
+        pose, log, evals, st = static["out"]
+        new = _FrameState()
+        for k in _FrameState.__slots__:
+            setattr(new, k, getattr(st, k).clone())
+        return pose.clone(), log.clone(), evals.clone(), new
+
+    # ------------------------------------------------------------------------------------------------
+    def infer_sequence(self, limgs, rimgs, masks):
+        """limgs, rimgs (T,3,H,W) float 0..255 on the device, masks (T,1,H,W) bool.
+        -> relative poses (T-1,7) f32 (normalised units, frame k-1 -> k), tangents (T-1,6), evals (T-1,).
+        Continues from the previous call's last frame if ``reset()`` was not called."""
+        T = limgs.shape[0]
+        poses, logs, evals = [], [], []
+        with torch.no_grad():
+            start = 0
+            if self.prev is None:
+                self.prev = self._first_frame(limgs[0:1], rimgs[0:1], masks[0:1])
+                start = 1
+            for a in range(start, T, self.chunk):
+                b = min(a + self.chunk, T)
+                args = (self.prev, limgs[a:b], rimgs[a:b], masks[a:b])
+                if self.use_graphs and (b - a) == self.chunk:
+                    p, l, e, self.prev = self._graphed_chunk(*args)
+                else:
+                    p, l, e, self.prev = self._chunk_body(*args)
+                poses.append(p), logs.append(l), evals.append(e)
+        if not poses:
+            dev = limgs.device
+            return torch.zeros((0, 7), device=dev), torch.zeros((0, 6), device=dev), torch.zeros((0,), device=dev)
+        return torch.cat(poses), torch.cat(logs), torch.cat(evals)
