@@ -38,6 +38,7 @@ int rpe_version(void);
 const char *rpe_status_string(int status);
 int rpe_last_cuda_error(void);                 /* cudaError_t of the last failing CUDA call      */
 int rpe_device_sm_count(void);
+long long rpe_launch_count(void);               /* kernels launched by this library so far        */
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 2 -- stereo depth lifting and pinhole back-projection (coalesced per-pixel kernels).

@@ -7,6 +7,7 @@
 namespace rpe {
 
 extern int g_last_cuda_error;
+extern long long g_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
 
 inline int cuda_fail(cudaError_t e) {
     g_last_cuda_error = (int)e;
@@ -23,6 +24,7 @@ inline int cuda_fail(cudaError_t e) {
     do {                                                     \
         cudaError_t _e = cudaGetLastError();                 \
         if (_e != cudaSuccess) return ::rpe::cuda_fail(_e);  \
+        ++::rpe::g_launch_count;                             \
     } while (0)
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

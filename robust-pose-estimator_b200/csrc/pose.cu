@@ -660,6 +660,7 @@ int rpe_pose_solve(const rpe_pose_problem *pb, int mode, int max_iter, int with_
     RPE_CUDA_TRY(cudaMemsetAsync(P.counters, 0, 256 * 128, st));
     void *args[] = {&P};
     RPE_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(bpg * n_groups), dim3(kPoseThreads), args, 0, st));
+    ++g_launch_count;
     return RPE_OK;
 }
 

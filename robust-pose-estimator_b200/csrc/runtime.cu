@@ -4,6 +4,7 @@
 
 namespace rpe {
 int g_last_cuda_error = 0;
+long long g_launch_count = 0;
 
 int sm_count() {
     static int cached = 0;
@@ -36,6 +37,8 @@ const char *rpe_status_string(int status) {
 int rpe_last_cuda_error(void) { return rpe::g_last_cuda_error; }
 
 int rpe_device_sm_count(void) { return rpe::sm_count(); }
+
+long long rpe_launch_count(void) { return rpe::g_launch_count; }
 
 // ---- host-side trajectory composition (fp32, same operation order as the reference's lietorch calls) ----
 namespace {

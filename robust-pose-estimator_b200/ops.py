@@ -19,6 +19,36 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional per-stage CUDA-event timing (bench.py): {stage: [(start_event, end_event, units), ...]}.
+_timers = None
+
+
+def enable_timers(on=True):
+    global _timers
+    _timers = {} if on else None
+    return _timers
+
+
+class _timed:
+    """Brackets one C-ABI call with CUDA events on the launching stream when timers are enabled."""
+
+    def __init__(self, stage, units=1):
+        self.stage, self.units = stage, units
+
+    def __enter__(self):
+        if _timers is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _timers is not None:
+            self.e1.record()
+            _timers.setdefault(self.stage, []).append((self.e0, self.e1, self.units))
+        return False
+
+
 def _chk(t, dtype, name, shape=None):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RpeError(f"{name}: expected a CUDA tensor (rpe_b200 has no CPU path), got "
@@ -50,8 +80,9 @@ def depth_proj(stereo_flow, bf, K, mask=None, want_pcl=True):
     depth = torch.empty((n, 1, H, W), device=stereo_flow.device, dtype=torch.float32)
     valid = torch.empty((n, 1, H, W), device=stereo_flow.device, dtype=torch.bool)
     pcl = torch.empty((n, 3, H, W), device=stereo_flow.device, dtype=torch.float32) if want_pcl else None
-    check(_lib.lib().rpe_depth_proj(_p(stereo_flow), _p(bf), _p(K), _p(mask), _p(depth), _p(valid), _p(pcl),
-                                    n, H, W, _stream()), "rpe_depth_proj")
+    with _timed("depth_proj", n):
+        check(_lib.lib().rpe_depth_proj(_p(stereo_flow), _p(bf), _p(K), _p(mask), _p(depth), _p(valid), _p(pcl),
+                                        n, H, W, _stream()), "rpe_depth_proj")
     return depth, valid, pcl
 
 
@@ -61,8 +92,9 @@ def proj(depth, K, rescale=None):
     _chk(depth, torch.float32, "depth", (n, 1, H, W))
     _chk(K, torch.float32, "intrinsics", (n, 3, 3))
     pcl = torch.empty((n, 3, H, W), device=depth.device, dtype=torch.float32)
-    check(_lib.lib().rpe_proj(_p(depth), _p(K), _p(pcl), 0 if rescale is None else 1,
-                              1.0 if rescale is None else float(rescale), n, H, W, _stream()), "rpe_proj")
+    with _timed("proj", n):
+        check(_lib.lib().rpe_proj(_p(depth), _p(K), _p(pcl), 0 if rescale is None else 1,
+                                  1.0 if rescale is None else float(rescale), n, H, W, _stream()), "rpe_proj")
     return pcl
 
 
@@ -84,8 +116,9 @@ def warp8_mask(pcl2, img2, sflow2, mask2, flow):
     if mask2 is not None:
         _chk(mask2, torch.bool, "mask2", (n, 1, H, W))
         m_out = torch.empty_like(mask2)
-    check(_lib.lib().rpe_warp8_mask(_p(pcl2), _p(img2), _p(sflow2), _p(mask2), _p(flow), _p(outs[0]), _p(outs[1]),
-                                    _p(outs[2]), _p(m_out), n, H, W, _stream()), "rpe_warp8_mask")
+    with _timed("warp8_mask", n):
+        check(_lib.lib().rpe_warp8_mask(_p(pcl2), _p(img2), _p(sflow2), _p(mask2), _p(flow), _p(outs[0]), _p(outs[1]),
+                                        _p(outs[2]), _p(m_out), n, H, W, _stream()), "rpe_warp8_mask")
     return outs[0], outs[1], outs[2], m_out
 
 
@@ -210,9 +243,10 @@ def pose_solve(flow, pcl1, pcl2, w1, w2, m1, m2, K, lw, mode=SOLVER_LBFGS_REF, m
     pb = _lib.PoseProblem(flow.data_ptr(), pcl1.data_ptr(), pcl2.data_ptr(), 0 if w1 is None else w1.data_ptr(),
                           0 if w2 is None else w2.data_ptr(), m1.data_ptr(), m2.data_ptr(), K.data_ptr(),
                           lw.data_ptr(), 0 if init_pose is None else init_pose.data_ptr(), n, H, W)
-    check(_lib.lib().rpe_pose_solve(C.byref(pb), int(mode), int(max_iter), 1 if with_hessian else 0, _p(out),
-                                    _p(pose32), _p(log32), _p(trace), int(trace_cap), _p(ws), ws.numel(), _stream()),
-          "rpe_pose_solve")
+    with _timed("pose_solve", n):
+        check(_lib.lib().rpe_pose_solve(C.byref(pb), int(mode), int(max_iter), 1 if with_hessian else 0, _p(out),
+                                        _p(pose32), _p(log32), _p(trace), int(trace_cap), _p(ws), ws.numel(), _stream()),
+              "rpe_pose_solve")
     return PoseSolution(out, pose32, log32, trace)
 
 
@@ -241,9 +275,10 @@ class CorrPyramid:
             CorrPyramid._cache[key] = bufs
         self.pyramid, self._ws = bufs
         ws_ptr = (self._ws.data_ptr() + 1023) & ~1023
-        check(l.rpe_corr_build(_p(fmap1), _p(fmap2), _p(self.pyramid), B, Cc, h, w, num_levels, int(precision),
-                               C.c_void_p(ws_ptr), self._ws.numel() - (ws_ptr - self._ws.data_ptr()), _stream()),
-              "rpe_corr_build")
+        with _timed("corr_build", B):
+            check(l.rpe_corr_build(_p(fmap1), _p(fmap2), _p(self.pyramid), B, Cc, h, w, num_levels, int(precision),
+                                   C.c_void_p(ws_ptr), self._ws.numel() - (ws_ptr - self._ws.data_ptr()), _stream()),
+                  "rpe_corr_build")
 
     def level(self, l):
         """View of pyramid level l as (B*h*w, 1, h>>l, w>>l) like the reference's corr_pyramid[l]."""
@@ -256,8 +291,9 @@ class CorrPyramid:
         _chk(coords, torch.float32, "coords", (self.B, 2, self.h, self.w))
         n = 2 * self.radius + 1
         out = torch.empty((self.B, self.num_levels * n * n, self.h, self.w), dtype=torch.float32, device=coords.device)
-        check(_lib.lib().rpe_corr_lookup(_p(self.pyramid), _p(coords), _p(out), self.B, self.h, self.w,
-                                         self.num_levels, self.radius, _stream()), "rpe_corr_lookup")
+        with _timed("corr_lookup", self.B):
+            check(_lib.lib().rpe_corr_lookup(_p(self.pyramid), _p(coords), _p(out), self.B, self.h, self.w,
+                                             self.num_levels, self.radius, _stream()), "rpe_corr_lookup")
         return out
 
 
@@ -267,5 +303,6 @@ def convex_upsample8(flow, mask):
     _chk(flow, torch.float32, "flow", (B, 2, h, w))
     _chk(mask, torch.float32, "mask", (B, 576, h, w))
     out = torch.empty((B, 2, 8 * h, 8 * w), dtype=torch.float32, device=flow.device)
-    check(_lib.lib().rpe_convex_upsample8(_p(flow), _p(mask), _p(out), B, h, w, _stream()), "rpe_convex_upsample8")
+    with _timed("convex_upsample8", B):
+        check(_lib.lib().rpe_convex_upsample8(_p(flow), _p(mask), _p(out), B, h, w, _stream()), "rpe_convex_upsample8")
     return out
