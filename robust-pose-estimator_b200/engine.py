@@ -31,6 +31,7 @@ class F2FEngine:
         self.chunk = int(chunk)
         self.use_graphs = use_graphs
         self._graphs = {}
+        self._scale = float(estimator.scale)        # host copy: no device sync inside (graph-captured) chunks
         self.reset()
 
     def reset(self):
@@ -72,7 +73,7 @@ class F2FEngine:
         mask2 = mask.clone()
         depth2, _, pcl2 = ops.depth_proj(sflow, bl, K, mask2)                       # mask2 &= stereo validity
         depth_prev = torch.cat((prev.depth, depth2[:-1]), 0).contiguous()
-        pcl1 = ops.proj(depth_prev, K, rescale=float(est.scale))                  # (d / scale) * scale round trip
+        pcl1 = ops.proj(depth_prev, K, rescale=self._scale)                  # (d / scale) * scale round trip
         img_prev = torch.cat((prev.img, limg[:-1]), 0).contiguous()
         sflow_prev = torch.cat((prev.sflow, sflow[:-1]), 0).contiguous()
         mask1 = torch.cat((prev.mask, mask2[:-1]), 0).contiguous()
@@ -136,7 +137,7 @@ class F2FEngine:
             for a in range(start, T, self.chunk):
                 b = min(a + self.chunk, T)
                 args = (self.prev, limgs[a:b], rimgs[a:b], masks[a:b])
-                if self.use_graphs and (b - a) == self.chunk:
+                if self.use_graphs and (b - a) == self.chunk and ops._timers is None:   # events cannot be recorded in a capture
                     p, l, e, self.prev = self._graphed_chunk(*args)
                 else:
                     p, l, e, self.prev = self._chunk_body(*args)

@@ -172,3 +172,26 @@ def test_gauss_newton_solver_mode(golden_dir):
     rot, trans = _pose_err(poses[-1], g["traj"][-1])
     print(f"GN vs reference L-BFGS: rot {rot:.2e} rad, rel. trans {trans:.2e}")
     assert rot < 5e-3 and trans < 5e-2
+
+
+@pytest.mark.parametrize("chunk,graphs", [(1, False), (2, False), (2, True)])
+def test_batched_engine_matches_reference(golden_dir, chunk, graphs):
+    """PoseEstimator.infer_sequence (chunked engine, feature reuse, optional CUDA graph, host composition through
+    rpe_compose_trajectory_host) reproduces the reference trajectory."""
+    _need_ckpt()
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_estimator import PoseEstimator
+    g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
+    W, H = [int(v) for v in g["size"]]
+    est = PoseEstimator(dict(SLAM), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    L = torch.from_numpy(g["imgs_l"].astype(np.float32)).cuda()
+    R = torch.from_numpy(g["imgs_r"].astype(np.float32)).cuda()
+    M = torch.from_numpy(np.stack([unpack(g["masks_in"][i], (1, H, W)) for i in range(3)])).cuda()
+    # 5 frames: 0 1 2 1 0 (exercise more than one chunk); the first three must match the golden trajectory
+    idx = [0, 1, 2, 1, 0]
+    traj, failed = est.infer_sequence(L[idx], R[idx], M[idx], chunk=chunk, use_graphs=graphs)
+    assert traj.shape == (5, 7) and not failed.any()
+    for k in range(1, 3):
+        rot, trans = _pose_err(traj[k].numpy(), g["traj"][k])
+        assert rot < 1e-4 and trans < 1e-4, f"frame {k}: rot {rot:.2e} trans {trans:.2e}"
+    assert est.last_evals[:2].tolist() == [len(g["pair0_eval_pose"]), len(g["pair1_eval_pose"])]
