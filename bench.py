@@ -209,8 +209,11 @@ def main():
         dist.barrier()
     lib = _lib.lib()
 
+    # rank r owns pairs [r*P, (r+1)*P) of one global (N*P + 1)-frame sequence: frames [r*P, (r+1)*P] (one halo frame)
     T = args.pairs + 1
-    L, R, M, seq = synthetic_sequence(T, seed=rank)
+    Lg, Rg, Mg, seq = synthetic_sequence(world * args.pairs + 1, seed=0)
+    L, R, M = (a[rank * args.pairs: rank * args.pairs + T] for a in (Lg, Rg, Mg))
+    del Lg, Rg, Mg
     trained = os.path.isfile(CKPT)
     cfg = dict(SLAM, precision=args.precision)
     est = PoseEstimator(cfg, torch.tensor(seq.calib["intrinsics"]["left"]), seq.calib["bf"], CKPT if trained else None,
@@ -219,22 +222,27 @@ def main():
     hL, hR, hM = (torch.from_numpy(a).pin_memory() for a in (L, R, M))
     dL, dR, dM = hL.to(dev).float(), hR.to(dev).float(), hM.to(dev)
     h2d = hL.numel() + hR.numel() + hM.numel()
+    from rpe_b200 import parallel
     engine = F2FEngine(est, chunk=args.chunk, use_graphs=args.graphs)
-    gathered = [torch.empty((args.pairs, 13), device=dev) for _ in range(world)] if world > 1 else None
+    inv_scale = float((1 / est.scale).float().cpu())
 
-    def device_step():
+    def device_step(l=dL, r=dR, m=dM):
         engine.reset()
-        rel, log, evals = engine.infer_sequence(dL, dR, dM)
-        if world > 1:
-            dist.all_gather(gathered, torch.cat((rel, log), 1).contiguous())     # the path's only exchange step
-        return rel, log, evals
+        rel, log, evals = engine.infer_sequence(l, r, m, sequence_start=(rank == 0))
+        rec = parallel.gather_pair_records(torch.cat((rel, log), 1).contiguous(), world * args.pairs)   # only exchange step
+        return rel, log, evals, rec
 
     def e2e_step():
         l = hL.to(dev, non_blocking=True).float()
         r = hR.to(dev, non_blocking=True).float()
         m = hM.to(dev, non_blocking=True)
-        est.last_pose = est.last_pose.__class__.Identity(1, device=dev)
-        return est.infer_sequence(l, r, m, chunk=args.chunk, use_graphs=args.graphs)
+        if world == 1:                                                            # the public API call a user makes
+            est.last_pose = est.last_pose.__class__.Identity(1, device=dev)
+            return est.infer_sequence(l, r, m, chunk=args.chunk, use_graphs=args.graphs)
+        rec = device_step(l, r, m)[3]
+        if rank == 0:                                                             # host composition of the gathered poses
+            return parallel.compose_trajectory(rec, [0, 0, 0, 0, 0, 0, 1.0], inv_scale)
+        return None, torch.zeros(1)
 
     def sync_all():
         if world > 1:
@@ -315,7 +323,7 @@ def main():
                        "ms_per_pair": ms / args.steps / args.pairs},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": pairs_total / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(args.pairs * 13 * 4), "input": "pinned uint8 frames + bool masks",
+                    "d2h_bytes_per_step": int(world * args.pairs * 13 * 4), "input": "pinned uint8 frames + bool masks",
                     "failed_pairs": int(failed.sum())},
             "roofline": roofline, "stages": stage, "lbfgs_evals_per_pair": evals_total / args.pairs}
     if world == 1 and not args.no_cpu_baseline:

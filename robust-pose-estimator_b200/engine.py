@@ -38,18 +38,20 @@ class F2FEngine:
         self.prev = None
 
     # ------------------------------------------------------------------------------------------------
-    def _first_frame(self, limg, rimg, mask):
-        """Frame 0 of a sequence: stereo depth only; its validity is NOT and-ed into the mask."""
+    def _first_frame(self, limg, rimg, mask, sequence_start=True):
+        """First frame of a (shard of a) sequence: stereo depth only.  For the first frame of the SEQUENCE the
+        stereo validity is NOT and-ed into the mask; for the halo frame of a later shard it is."""
         raft = self.model.flow
         f = raft.features(torch.cat((limg, rimg), 0))
         net, inp = raft.context(limg)
         preds, _, _, _ = raft.refine(f[0:1].contiguous(), f[1:2].contiguous(), net, inp)
         bl = (self.est.baseline * self.est.scale).float().reshape(1)
         eye = torch.eye(3, device=limg.device)[None]
-        depth, _, _ = ops.depth_proj(preds[-1], bl, eye, None, want_pcl=False)
+        m = mask.clone()
+        depth, _, _ = ops.depth_proj(preds[-1], bl, eye, None if sequence_start else m, want_pcl=False)
         st = _FrameState()
         st.img, st.fmap, st.net, st.inp = limg, f[0:1].contiguous(), net, inp
-        st.depth, st.sflow, st.mask = depth, preds[-1], mask.clone()
+        st.depth, st.sflow, st.mask = depth, preds[-1], m
         return st
 
     def _chunk_body(self, prev, limg, rimg, mask):
@@ -123,7 +125,7 @@ class F2FEngine:
         return pose.clone(), log.clone(), evals.clone(), new
 
     # ------------------------------------------------------------------------------------------------
-    def infer_sequence(self, limgs, rimgs, masks):
+    def infer_sequence(self, limgs, rimgs, masks, sequence_start=True):
         """limgs, rimgs (T,3,H,W) float 0..255 on the device, masks (T,1,H,W) bool.
         -> relative poses (T-1,7) f32 (normalised units, frame k-1 -> k), tangents (T-1,6), evals (T-1,).
         Continues from the previous call's last frame if ``reset()`` was not called."""
@@ -132,7 +134,7 @@ class F2FEngine:
         with torch.no_grad():
             start = 0
             if self.prev is None:
-                self.prev = self._first_frame(limgs[0:1], rimgs[0:1], masks[0:1])
+                self.prev = self._first_frame(limgs[0:1], rimgs[0:1], masks[0:1], sequence_start)
                 start = 1
             for a in range(start, T, self.chunk):
                 b = min(a + self.chunk, T)
