@@ -176,7 +176,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32", "fp16", "bf16"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32", "fp16", "bf16"])
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--pairs", type=int, default=64)
     ap.add_argument("--graphs", action="store_true")
@@ -315,7 +315,7 @@ def main():
                 "traffic": None, "peak_source": peak_src, "avg_launch_us": d["avg_us"], "algorithmic_bytes_per_launch": alg}
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "tf32": "tf32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32-equivalent split, fp32 accumulate)", "tf32": "tf32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "f2f_640x512_seq65", "pairs_per_gpu_per_step": args.pairs, "chunk": args.chunk,
                        "precision": args.precision, "solver": "lbfgs_ref", "lbgfs_iters": 20, "conf_weighing": True,
                        "weights": "poseNet_2xf8up4b.pth" if trained else "random-init (checkpoint not shipped)",

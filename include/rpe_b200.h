@@ -184,6 +184,54 @@ int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B
  * with a softmax over the 9 neighbours.  flow (B,2,h,w), mask (B,576,h,w) -> out (B,2,8h,8w). */
 int rpe_convex_upsample8(const float *flow, const float *mask, float *out, int B, int h, int w, void *stream);
 
+int rpe_convex_upsample8_nhwc(const float *flow, const float *mask, int mask_ld, float *out, int B, int h, int w, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row: the RAFT update operator on tcgen05 tensor cores.
+ * Replaces the convolutions of BasicUpdateBlock (/root/reference/core/RAFT/core/update.py:79-136) that the
+ * reference runs through cuDNN.  Activations are NHWC bf16 "split" planes (hi = bf16(v), lo = bf16(v - hi));
+ * a convolution contracts over a list of (activation plane, weight) sources, so concatenated inputs are never
+ * materialised and hi*hi + lo*hi + hi*lo reproduces fp32 convolutions to ~1e-5.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rpe_conv_source {
+    const void *act;     /* bf16 NHWC (N,H,W,c_total)                                  */
+    int c_total;         /* channel stride of `act` (multiple of 8)                    */
+    int c_offset;        /* first channel read (multiple of 8)                         */
+    int c_count;         /* channels read (multiple of 64)                             */
+    const void *weight;  /* bf16 [kh*kw][cout_pad][c_count], K-major                   */
+} rpe_conv_source;
+
+typedef struct rpe_conv_desc {
+    int n_sources;
+    rpe_conv_source src[8];
+    int N, H, W;
+    int kh, kw;          /* odd; stride 1, zero padding (kh/2, kw/2)                   */
+    int cout, cout_pad;  /* real / padded (multiple of 16) output channels             */
+    const float *bias;   /* (cout) or NULL                                             */
+    int activation;      /* 0 none, 1 relu, 2 sigmoid, 3 tanh                          */
+    float out_scale;     /* applied after the activation                               */
+    float *out_f32;      /* NHWC fp32 output (N,H,W,f32_ld) at channel f32_offset, or NULL */
+    int f32_ld, f32_offset;
+    void *out_hi, *out_lo; /* NHWC bf16 split planes (N,H,W,bf_ld) at channel bf_offset, or NULL */
+    int bf_ld, bf_offset;
+} rpe_conv_desc;
+
+int rpe_conv_plan_create(const rpe_conv_desc *desc, void **plan_out);   /* encodes the TMA descriptors once */
+int rpe_conv_plan_run(void *plan, void *stream);
+int rpe_conv_plan_destroy(void *plan);
+
+/* CorrBlock.__call__ writing the NHWC bf16 split planes the first motion-encoder convolution reads (ld >= 324). */
+int rpe_corr_lookup_nhwc_bf16(const float *pyramid, const float *coords, void *out_hi, void *out_lo, int ld, int B, int h, int w,
+                              int num_levels, int radius, void *stream);
+/* Layout / split helpers and the element-wise pieces of the update operator (update.py:45-60, raft.py:112-121). */
+int rpe_nchw_to_nhwc_split(const float *x, void *hi, void *lo, float *f32, int n, int C, int H, int W, int ld, int off,
+                           int f32_ld, int f32_off, void *stream);
+int rpe_nhwc_to_nchw(const float *x, float *out, int n, int C, int H, int W, int ld, int off, void *stream);
+int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi, void *col_lo, int col_ld, void *x_hi,
+                  void *x_lo, int x_ld, int x_off, int n, int h, int w, void *stream);
+int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *out_lo, int out_ld, int out_off,
+                 long long npix, int mode, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,18 @@ class PoseProblem(C.Structure):
                 ("lw", C.c_void_p), ("init_pose", C.c_void_p), ("n", C.c_int), ("H", C.c_int), ("W", C.c_int)]
 
 
+class ConvSource(C.Structure):
+    _fields_ = [("act", C.c_void_p), ("c_total", C.c_int), ("c_offset", C.c_int), ("c_count", C.c_int), ("weight", C.c_void_p)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("n_sources", C.c_int), ("src", ConvSource * 8), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("kh", C.c_int), ("kw", C.c_int), ("cout", C.c_int), ("cout_pad", C.c_int), ("bias", C.c_void_p),
+                ("activation", C.c_int), ("out_scale", C.c_float), ("out_f32", C.c_void_p), ("f32_ld", C.c_int),
+                ("f32_offset", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("bf_ld", C.c_int),
+                ("bf_offset", C.c_int)]
+
+
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     # name: (restype, argtypes)
@@ -46,6 +58,15 @@ SIGNATURES = {
     "rpe_corr_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
     "rpe_corr_lookup": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_convex_upsample8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "rpe_convex_upsample8_nhwc": (_I, [_P, _P, _I, _P, _I, _I, _I, _P]),
+    "rpe_conv_plan_create": (_I, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
+    "rpe_conv_plan_run": (_I, [_P, _P]),
+    "rpe_conv_plan_destroy": (_I, [_P]),
+    "rpe_corr_lookup_nhwc_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "rpe_nchw_to_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rpe_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "rpe_flow_step": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_gru_gate": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_longlong, _I, _P]),
 }
 
 

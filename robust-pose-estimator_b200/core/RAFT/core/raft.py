@@ -5,8 +5,10 @@ volume, its lookup and the convex up-sampling are the hand-written sm_100a kerne
 do not change the consumed result:
   * only the final flow prediction is up-sampled unless ``all_predictions=True`` (the pose path
     reads ``flow_predictions[-1]`` only, pose_net.py:66-67);
-  * ``precision``: "fp32" (parity mode: cuDNN fp32, TF32 off, correlation TF32x3 split) |
-    "tf32" | "bf16" / "fp16" (autocast like the reference's CUDA run, raft.py:92,100,117)."""
+  * ``precision``: "fp32" (cuDNN fp32, TF32 off, correlation TF32x3 split) |
+    "bf16x3" (parity-grade fast mode: encoders cuDNN fp32, the 12-iteration update operator on the tcgen05
+    bf16x3 convolution kernels, update_tc.py) | "tf32" | "bf16" / "fp16" (autocast like the reference's CUDA run,
+    raft.py:92,100,117)."""
 import contextlib
 
 import torch
@@ -17,6 +19,7 @@ from ...utils.param_tree import build_tree
 from .corr import CorrBlock
 from .extractor import encoder_entries, encoder_forward
 from .update import prepare_update_weights, update_entries, update_forward
+from .update_tc import UpdateTC
 
 _AUTOCAST = {"bf16": torch.bfloat16, "fp16": torch.float16}
 
@@ -40,14 +43,15 @@ class RAFT(nn.Module):
         tree = build_tree(entries)
         self.fnet, self.cnet, self.update_block = tree.fnet, tree.cnet, tree.update_block
         self._W = None
+        self._tc = None
 
     # ---- weight table ------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
-        self._W = None
+        self._W = self._tc = None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._W = None
+        self._W = self._tc = None
         return super().load_state_dict(*a, **k)
 
     def weights(self):
@@ -66,8 +70,8 @@ class RAFT(nn.Module):
         """Precision context of the convolutional trunk: fp32 = cuDNN fp32 with TF32 off (parity mode)."""
         stack = contextlib.ExitStack()
         dt = _AUTOCAST.get(self.precision)
-        stack.enter_context(torch.backends.cudnn.flags(enabled=True, benchmark=self.precision != "fp32",
-                                                       deterministic=False, allow_tf32=self.precision != "fp32"))
+        exact = self.precision in ("fp32", "bf16x3")
+        stack.enter_context(torch.backends.cudnn.flags(enabled=True, benchmark=not exact, deterministic=False, allow_tf32=not exact))
         stack.enter_context(torch.autocast("cuda", dtype=dt) if dt is not None else torch.autocast("cuda", enabled=False))
         return stack
 
@@ -88,8 +92,13 @@ class RAFT(nn.Module):
     def refine(self, fmap1, fmap2, net, inp, iters=12, flow_init=None, upsample=True, all_predictions=False):
         """Correlation pyramid + `iters` GRU updates + convex up-sampling."""
         B, _, h, w = fmap1.shape
-        corr_prec = ops.CORR_TF32X3 if self.precision == "fp32" else ops.CORR_TF32
+        corr_prec = ops.CORR_TF32X3 if self.precision in ("fp32", "bf16x3") else ops.CORR_TF32
         corr_fn = CorrBlock(fmap1, fmap2, radius=self.config["corr_radius"], precision=corr_prec)
+        if self.precision == "bf16x3" and not all_predictions:
+            if self._tc is None:
+                self._tc = UpdateTC(self.weights())
+            flow_up, net, flow_lo = self._tc.refine(corr_fn._pyr, net, inp, iters, flow_init, want_mask=upsample)
+            return [flow_up if upsample else flow_lo], net, inp, flow_lo
         coords0 = coords_grid(B, h, w, fmap1.device)
         coords1 = coords0.clone() if flow_init is None else coords0 + flow_init
         W = self.weights()

@@ -1,0 +1,182 @@
+"""RAFT update operator on the tcgen05 convolution kernels (csrc/conv.cu, csrc/update_ops.cu).
+
+Same arithmetic graph as ``update.update_forward`` (reference: /root/reference/core/RAFT/core/update.py:79-136 and the
+loop body of core/RAFT/core/raft.py:112-132) with every convolution evaluated as an error-compensated bf16x3 implicit
+GEMM on the tensor cores, NHWC activations, no materialised concatenations and the whole 12-iteration loop resident in
+pre-allocated device buffers (one set per batch shape)."""
+import ctypes as C
+
+import torch
+
+from .... import _lib, ops
+from ....ops import _p, _stream, _timed, check
+
+ACT = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+
+def _split(t):
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def _pack_weight(w, c_lo, c_hi, cout_pad):
+    """(Cout, Cin, kh, kw) fp32 -> channel window [c_lo, c_hi) as [taps][cout_pad][c_pad64] split planes."""
+    cout, _, kh, kw = w.shape
+    cs = c_hi - c_lo
+    cpad = (cs + 63) // 64 * 64
+    out = torch.zeros((kh * kw, cout_pad, cpad), dtype=torch.float32, device=w.device)
+    out[:, :cout, :cs] = w[:, c_lo:c_hi].permute(2, 3, 0, 1).reshape(kh * kw, cout, cs)
+    return _split(out)
+
+
+class _Planes:
+    """NHWC bf16 split planes (hi, lo) of shape (N, H, W, C)."""
+
+    def __init__(self, n, h, w, c, device):
+        self.hi = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
+        self.c = c
+
+
+class UpdateTC:
+    def __init__(self, weights, prefix="update_block."):
+        """weights: flat {key: tensor} table of the RAFT module (fp32, on the device)."""
+        self.W = weights
+        self.prefix = prefix
+        self._packed = {}
+        self._shapes = {}
+
+    # ---- weights ---------------------------------------------------------------------------------------
+    def _w(self, name, c_lo, c_hi, cout_pad, transform=None):
+        key = (name, c_lo, c_hi, cout_pad)
+        if key not in self._packed:
+            w = self.W[self.prefix + name + ".weight"] if transform is None else transform()
+            self._packed[key] = _pack_weight(w.float(), c_lo, c_hi, cout_pad)
+        return self._packed[key]
+
+    def _bias(self, name, transform=None):
+        key = ("bias", name)
+        if key not in self._packed:
+            b = self.W[self.prefix + name + ".bias"] if transform is None else transform()
+            self._packed[key] = b.float().contiguous()
+        return self._packed[key]
+
+    # ---- plans -------------------------------------------------------------------------------------------
+    def _plan(self, st, name, inputs, kh, kw, cout, act, out_f32=None, f32_off=0, out_planes=None, bf_off=0, scale=1.0,
+              weight=None, bias=None):
+        """inputs: [(planes, c_offset, c_count_real, weight channel window start)]"""
+        cout_pad = (cout + 15) // 16 * 16
+        d = _lib.ConvDesc()
+        k = 0
+        keep = []
+        for planes, c_off, c_cnt, w_lo in inputs:
+            w_hi_t, w_lo_t = self._w(name, w_lo, w_lo + c_cnt, cout_pad, weight)
+            cpad = w_hi_t.shape[-1]
+            for a, wt in ((planes.hi, w_hi_t), (planes.lo, w_hi_t), (planes.hi, w_lo_t)):      # hi*hi + lo*hi + hi*lo
+                d.src[k].act, d.src[k].c_total, d.src[k].c_offset, d.src[k].c_count = a.data_ptr(), planes.c, c_off, cpad
+                d.src[k].weight = wt.data_ptr()
+                k += 1
+            keep += [w_hi_t, w_lo_t]
+        d.n_sources = k
+        d.N, d.H, d.W = st["dims"]
+        d.kh, d.kw, d.cout, d.cout_pad = kh, kw, cout, cout_pad
+        b = self._bias(name, bias)
+        d.bias = b.data_ptr()
+        d.activation, d.out_scale = ACT[act], scale
+        if out_f32 is not None:
+            d.out_f32, d.f32_ld, d.f32_offset = out_f32.data_ptr(), out_f32.shape[-1], f32_off
+        if out_planes is not None:
+            d.out_hi, d.out_lo, d.bf_ld, d.bf_offset = out_planes.hi.data_ptr(), out_planes.lo.data_ptr(), out_planes.c, bf_off
+        plan = C.c_void_p()
+        check(_lib.lib().rpe_conv_plan_create(C.byref(d), C.byref(plan)), f"rpe_conv_plan_create({name})")
+        st["keep"] += keep + [b]
+        return plan
+
+    def _state(self, n, h, w, device):
+        key = (n, h, w, device.index)
+        st = self._shapes.get(key)
+        if st is not None:
+            return st
+        P = lambda c: _Planes(n, h, w, c, device)
+        f32 = lambda c: torch.zeros((n, h, w, c), dtype=torch.float32, device=device)
+        st = {"dims": (n, h, w), "keep": []}
+        st.update(corr=P(384), cor1=P(256), cf=P(256), col=P(128), flo1=P(128), x=P(256), hp=P(128), rh=P(128), fh=P(256), mk=P(256),
+                  h=f32(128), zr=f32(256), q=f32(128), delta=f32(4), mask=f32(576),
+                  coords1=torch.zeros((n, 2, h, w), dtype=torch.float32, device=device))
+        W, pre = self.W, self.prefix
+        zr_w = lambda half: (lambda: torch.cat((W[pre + f"gru.convz{half}.weight"], W[pre + f"gru.convr{half}.weight"]), 0))
+        zr_b = lambda half: (lambda: torch.cat((W[pre + f"gru.convz{half}.bias"], W[pre + f"gru.convr{half}.bias"]), 0))
+        f1_w = lambda: W[pre + "encoder.convf1.weight"].permute(0, 2, 3, 1).reshape(128, 98, 1, 1)     # im2col order
+        pl = {}
+        pl["convc1"] = self._plan(st, "encoder.convc1", [(st["corr"], 0, 324, 0)], 1, 1, 256, "relu", out_planes=st["cor1"])
+        pl["convc2"] = self._plan(st, "encoder.convc2", [(st["cor1"], 0, 256, 0)], 3, 3, 192, "relu", out_planes=st["cf"], bf_off=0)
+        pl["convf1"] = self._plan(st, "encoder.convf1", [(st["col"], 0, 98, 0)], 1, 1, 128, "relu", out_planes=st["flo1"], weight=f1_w)
+        pl["convf2"] = self._plan(st, "encoder.convf2", [(st["flo1"], 0, 128, 0)], 3, 3, 64, "relu", out_planes=st["cf"], bf_off=192)
+        pl["conv"] = self._plan(st, "encoder.conv", [(st["cf"], 0, 256, 0)], 3, 3, 126, "relu", out_planes=st["x"], bf_off=128)
+        for half, (kh, kw) in (("1", (1, 5)), ("2", (5, 1))):
+            pl["zr" + half] = self._plan(st, "gru.convzr" + half, [(st["hp"], 0, 128, 0), (st["x"], 0, 256, 128)], kh, kw, 256, "sigmoid",
+                                         out_f32=st["zr"], weight=zr_w(half), bias=zr_b(half))
+            pl["q" + half] = self._plan(st, "gru.convq" + half, [(st["rh"], 0, 128, 0), (st["x"], 0, 256, 128)], kh, kw, 128, "tanh",
+                                        out_f32=st["q"])
+        pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["fh"])
+        pl["fh2"] = self._plan(st, "flow_head.conv2", [(st["fh"], 0, 256, 0)], 3, 3, 2, "none", out_f32=st["delta"])
+        pl["mask0"] = self._plan(st, "mask.0", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["mk"])
+        pl["mask2"] = self._plan(st, "mask.2", [(st["mk"], 0, 256, 0)], 1, 1, 576, "none", out_f32=st["mask"], scale=0.25)
+        st["plans"] = pl
+        self._shapes[key] = st
+        return st
+
+    # ---- execution ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _run(st, name):
+        with _timed("conv_tc", 1):
+            check(_lib.lib().rpe_conv_plan_run(st["plans"][name], _stream()), f"rpe_conv_plan_run({name})")
+
+    def refine(self, corr_pyr, net, inp, iters=12, flow_init=None, want_mask=True):
+        """corr_pyr: ops.CorrPyramid; net, inp (B,128,h,w) fp32 NCHW.  -> (flow_up or None, net NCHW, flow_lo (B,2,h,w))."""
+        B, _, h, w = net.shape
+        dev = net.device
+        st = self._state(B, h, w, dev)
+        l = _lib.lib()
+        s = _stream()
+        npix = B * h * w
+        # initial state: h (fp32 + planes), inp -> x[0:128], coords1 = grid (+ flow_init)
+        check(l.rpe_nchw_to_nhwc_split(_p(net.float().contiguous()), _p(st["hp"].hi), _p(st["hp"].lo), _p(st["h"]), B, 128, h, w, 128, 0,
+                                       128, 0, s), "rpe_nchw_to_nhwc_split")
+        check(l.rpe_nchw_to_nhwc_split(_p(inp.float().contiguous()), _p(st["x"].hi), _p(st["x"].lo), None, B, 128, h, w, 256, 0, 0, 0, s),
+              "rpe_nchw_to_nhwc_split")
+        ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+        grid = torch.stack((xs, ys), 0).float()
+        st["coords1"].copy_(grid[None].expand(B, 2, h, w) if flow_init is None else grid[None] + flow_init)
+        coords1 = st["coords1"]
+        for it in range(iters):
+            with _timed("corr_lookup", B):
+                check(l.rpe_corr_lookup_nhwc_bf16(_p(corr_pyr.pyramid), _p(coords1), _p(st["corr"].hi), _p(st["corr"].lo), 384, B, h, w,
+                                                  corr_pyr.num_levels, corr_pyr.radius, s), "rpe_corr_lookup_nhwc_bf16")
+            # flow = coords1 - coords0 -> im2col planes + GRU-input slots (coords were advanced at the end of the last iteration)
+            check(l.rpe_flow_step(_p(coords1), None, 4, _p(st["col"].hi), _p(st["col"].lo), 128, _p(st["x"].hi), _p(st["x"].lo), 256, 254,
+                                  B, h, w, s), "rpe_flow_step")
+            for name in ("convc1", "convc2", "convf1", "convf2", "conv"):
+                self._run(st, name)
+            for half in ("1", "2"):
+                self._run(st, "zr" + half)
+                check(l.rpe_gru_gate(_p(st["zr"]), _p(st["h"]), None, _p(st["rh"].hi), _p(st["rh"].lo), 128, 0, npix, 0, s), "rpe_gru_gate")
+                self._run(st, "q" + half)
+                check(l.rpe_gru_gate(_p(st["zr"]), _p(st["h"]), _p(st["q"]), _p(st["hp"].hi), _p(st["hp"].lo), 128, 0, npix, 1, s),
+                      "rpe_gru_gate")
+            self._run(st, "fh1")
+            self._run(st, "fh2")
+            coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))
+        flow_lo = coords1 - grid[None]
+        flow_up = None
+        if want_mask:
+            self._run(st, "mask0")
+            self._run(st, "mask2")
+            flow_up = torch.empty((B, 2, 8 * h, 8 * w), dtype=torch.float32, device=dev)
+            with _timed("convex_upsample8", B):
+                check(l.rpe_convex_upsample8_nhwc(_p(flow_lo.contiguous()), _p(st["mask"]), 576, _p(flow_up), B, h, w, s),
+                      "rpe_convex_upsample8_nhwc")
+        net_out = torch.empty((B, 128, h, w), dtype=torch.float32, device=dev)
+        check(l.rpe_nhwc_to_nchw(_p(st["h"]), _p(net_out), B, 128, h, w, 128, 0, s), "rpe_nhwc_to_nchw")
+        return flow_up, net_out, flow_lo

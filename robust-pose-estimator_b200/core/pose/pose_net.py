@@ -43,7 +43,7 @@ class PoseNet(nn.Module):
         sd = OrderedDict((k.replace("module.", ""), v) for k, v in state_dict.items())
         out = super().load_state_dict(sd, strict=strict, **kw)
         self._Wh = None
-        self.flow._W = None
+        self.flow._W = self.flow._tc = None
         return out
 
     def _head_weights(self):
@@ -85,7 +85,7 @@ class PoseNet(nn.Module):
             x2 = torch.cat((x3[:, :8], x3[:, 16:]), 1)
             W_ = self._head_weights()
             with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False,
-                                            allow_tf32=self.flow.precision != "fp32"):
+                                            allow_tf32=self.flow.precision not in ("fp32", "bf16x3")):
                 conf1 = torch.sigmoid(tiny_unet_forward(x2, W_, "weight_head_2d.0.", (H, W)))
                 conf2 = torch.sigmoid(tiny_unet_forward(x3, W_, "weight_head_3d.0.", (H, W)))
         else:

@@ -14,117 +14,11 @@
 #include <cstdio>
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace rpe {
-
-// ================================================================================================
-// PTX wrappers
-// ================================================================================================
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("rpe_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
-    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                     reinterpret_cast<uint64_t>(map)),
-                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int kPending>
-__device__ __forceinline__ void tma_store_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-// tcgen05: TMEM allocation, MMA, commit, load
-__device__ __forceinline__ void tmem_alloc(uint32_t *smem_result, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t *v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ================================================================================================
 // Operand preparation: (B, C, Q) fp32 -> (B, Q, Kp) tf32-rounded, K contiguous.
@@ -392,7 +286,9 @@ constexpr int kLookupQ = 32;
 constexpr int kMaxWin = 10;       // 2r+2 for r = 4
 
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restrict__ pyr, PyrDims d, const float *__restrict__ coords,
-                                                          float *__restrict__ out, int Q, int radius) {
+                                                          float *__restrict__ out, int Q, int radius,
+                                                          __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo,
+                                                          int nhwc_ld) {
     extern __shared__ float sm[];
     const int n = 2 * radius + 1, win = n + 1;
     const int nch = d.levels * n * n;
@@ -444,6 +340,20 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restric
     }
     __syncthreads();
     const int nq = min(kLookupQ, Q - q_base);
+    if (out_hi != nullptr) {
+        // NHWC bf16 hi/lo planes for the tcgen05 convolution path: 324 contiguous channels per query
+        for (int e = threadIdx.x; e < nch * kLookupQ; e += blockDim.x) {
+            const int qi = e / nch, c = e - qi * nch;
+            if (qi < nq) {
+                const float v = s_out[c * (kLookupQ + 1) + qi];
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                const size_t o = ((size_t)b * Q + q_base + qi) * nhwc_ld + c;
+                out_hi[o] = h;
+                out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < nch * kLookupQ; e += blockDim.x) {
         const int c = e / kLookupQ, qi = e - c * kLookupQ;
         if (qi < nq) out[((size_t)b * nch + c) * Q + q_base + qi] = s_out[c * (kLookupQ + 1) + qi];
@@ -583,10 +493,10 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     return RPE_OK;
 }
 
-int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B, int h, int w, int num_levels, int radius,
-                    void *stream) {
+static int corr_lookup_impl(const float *pyramid, const float *coords, float *out, void *out_hi, void *out_lo, int nhwc_ld, int B,
+                            int h, int w, int num_levels, int radius, void *stream) {
     using namespace rpe;
-    if (!pyramid || !coords || !out) return RPE_ERR_INVALID_ARG;
+    if (!pyramid || !coords || (!out && !out_hi)) return RPE_ERR_INVALID_ARG;
     if (B <= 0 || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4 || radius < 1 || 2 * radius + 2 > kMaxWin)
         return RPE_ERR_INVALID_ARG;
     const int Q = h * w;
@@ -600,9 +510,23 @@ int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B
         attr = smem;
     }
     dim3 grid((Q + kLookupQ - 1) / kLookupQ, B);
-    corr_lookup_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pyramid, d, coords, out, Q, radius);
+    corr_lookup_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pyramid, d, coords, out, Q, radius,
+                                                                  reinterpret_cast<__nv_bfloat16 *>(out_hi),
+                                                                  reinterpret_cast<__nv_bfloat16 *>(out_lo), nhwc_ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
+}
+
+int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B, int h, int w, int num_levels, int radius,
+                    void *stream) {
+    return corr_lookup_impl(pyramid, coords, out, nullptr, nullptr, 0, B, h, w, num_levels, radius, stream);
+}
+
+int rpe_corr_lookup_nhwc_bf16(const float *pyramid, const float *coords, void *out_hi, void *out_lo, int ld, int B, int h, int w,
+                              int num_levels, int radius, void *stream) {
+    const int n = 2 * radius + 1;
+    if (!out_hi || !out_lo || ld < num_levels * n * n) return RPE_ERR_INVALID_ARG;
+    return corr_lookup_impl(pyramid, coords, nullptr, out_hi, out_lo, ld, B, h, w, num_levels, radius, stream);
 }
 
 }  // extern "C"

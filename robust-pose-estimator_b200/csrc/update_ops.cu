@@ -1,0 +1,184 @@
+// Element-wise companions of the tcgen05 convolution path of the RAFT update operator
+// (reference: /root/reference/core/RAFT/core/update.py:33-60 SepConvGRU gating, :79-97 motion encoder inputs,
+// core/RAFT/core/raft.py:112-121 coordinate update).  All tensors NHWC; "split" = bf16 hi/lo planes (conv.cu).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace rpe {
+
+__device__ __forceinline__ void split_store(float v, __nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t o) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[o] = h;
+    lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// NCHW fp32 (n,C,H,W) -> NHWC split planes at channel offset `off` of a tensor with `ld` channels (+ optional fp32 NHWC copy).
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi,
+                                                                 __nv_bfloat16 *__restrict__ lo, float *__restrict__ f32, int C,
+                                                                 int HW, int ld, int off, int f32_ld, int f32_off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, p = p0 + tx;
+        tile[ty + 8 * j][tx] = (c < C && p < HW) ? __ldg(x + ((size_t)n * C + c) * HW + p) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = p0 + ty + 8 * j, c = c0 + tx;
+        if (p < HW && c < C) {
+            const float v = tile[tx][ty + 8 * j];
+            const size_t pix = (size_t)n * HW + p;
+            if (hi) split_store(v, hi, lo, pix * ld + off + c);
+            if (f32) f32[pix * f32_ld + f32_off + c] = v;
+        }
+    }
+}
+
+// NHWC fp32 (window of C channels at offset) -> NCHW fp32.
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float *__restrict__ x, float *__restrict__ out, int C, int HW, int ld,
+                                                           int off) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int p = p0 + ty + 8 * j, c = c0 + tx;
+        tile[ty + 8 * j][tx] = (c < C && p < HW) ? __ldg(x + ((size_t)n * HW + p) * ld + off + c) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, p = p0 + tx;
+        if (p < HW && c < C) out[((size_t)n * C + c) * HW + p] = tile[tx][ty + 8 * j];
+    }
+}
+
+// coords1 += delta (NHWC fp32, 2 of `d_ld` channels; skipped when delta == nullptr); flow = coords1 - coords0 with
+// coords0 = pixel grid; writes (i) the 7x7 im2col of the flow (98 of `col_ld` channels, tap-major: ch = (ky*7+kx)*2 + c)
+// as split planes and (ii) the flow itself into 2 channels at `x_off` of the GRU input tensor.
+__global__ void __launch_bounds__(256) flow_step_kernel(float *__restrict__ coords1, const float *__restrict__ delta, int d_ld,
+                                                        __nv_bfloat16 *__restrict__ col_hi, __nv_bfloat16 *__restrict__ col_lo, int col_ld,
+                                                        __nv_bfloat16 *__restrict__ x_hi, __nv_bfloat16 *__restrict__ x_lo, int x_ld,
+                                                        int x_off, int h, int w, int phase) {
+    const int n = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int hw = h * w;
+    if (p >= hw) return;
+    const int y = p / w, x = p - y * w;
+    float *c1 = coords1 + (size_t)n * 2 * hw;
+    if (phase == 0) {                      // pass 1: coordinate update (separate launch: pass 2 reads neighbours)
+        if (delta) {
+            const float *d = delta + ((size_t)n * hw + p) * d_ld;
+            c1[p] = c1[p] + d[0];
+            c1[hw + p] = c1[hw + p] + d[1];
+        }
+        return;
+    }
+    const size_t pix = (size_t)n * hw + p;
+    for (int ky = 0; ky < 7; ++ky) {
+        for (int kx = 0; kx < 7; ++kx) {
+            const int yy = y + ky - 3, xx = x + kx - 3;
+            float fx = 0.0f, fy = 0.0f;
+            if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+                fx = c1[yy * w + xx] - (float)xx;
+                fy = c1[hw + yy * w + xx] - (float)yy;
+            }
+            const size_t o = pix * col_ld + (ky * 7 + kx) * 2;
+            split_store(fx, col_hi, col_lo, o);
+            split_store(fy, col_hi, col_lo, o + 1);
+        }
+    }
+    const float fx = c1[p] - (float)x, fy = c1[hw + p] - (float)y;
+    split_store(fx, x_hi, x_lo, pix * x_ld + x_off);
+    split_store(fy, x_hi, x_lo, pix * x_ld + x_off + 1);
+}
+
+// GRU gating.  zr: fp32 NHWC (.., 256) = [z | r] after sigmoid; h: fp32 NHWC (.., 128).
+//   mode 0: rh = r * h                  -> split planes (conv input of the candidate state)
+//   mode 1: h  = (1 - z) * h + z * q    -> fp32 h (in place) + split planes
+__global__ void __launch_bounds__(256) gru_gate_kernel(const float *__restrict__ zr, float *__restrict__ h, const float *__restrict__ q,
+                                                       __nv_bfloat16 *__restrict__ o_hi, __nv_bfloat16 *__restrict__ o_lo, int o_ld,
+                                                       int o_off, size_t npix, int mode) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 4 channels of one pixel
+    if (i >= npix * 32) return;
+    const size_t pix = i >> 5;
+    const int c = (int)(i & 31) * 4;
+    const float4 hv = *reinterpret_cast<const float4 *>(h + pix * 128 + c);
+    float o[4];
+    if (mode == 0) {
+        const float4 r = *reinterpret_cast<const float4 *>(zr + pix * 256 + 128 + c);
+        o[0] = r.x * hv.x, o[1] = r.y * hv.y, o[2] = r.z * hv.z, o[3] = r.w * hv.w;
+    } else {
+        const float4 z = *reinterpret_cast<const float4 *>(zr + pix * 256 + c);
+        const float4 qv = *reinterpret_cast<const float4 *>(q + pix * 128 + c);
+        o[0] = (1.0f - z.x) * hv.x + z.x * qv.x;
+        o[1] = (1.0f - z.y) * hv.y + z.y * qv.y;
+        o[2] = (1.0f - z.z) * hv.z + z.z * qv.z;
+        o[3] = (1.0f - z.w) * hv.w + z.w * qv.w;
+        *reinterpret_cast<float4 *>(h + pix * 128 + c) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        hh[k] = __float2bfloat16_rn(o[k]);
+        ll[k] = __float2bfloat16_rn(o[k] - __bfloat162float(hh[k]));
+    }
+    *reinterpret_cast<uint2 *>(o_hi + pix * o_ld + o_off + c) = *reinterpret_cast<uint2 *>(hh);
+    *reinterpret_cast<uint2 *>(o_lo + pix * o_ld + o_off + c) = *reinterpret_cast<uint2 *>(ll);
+}
+
+}  // namespace rpe
+
+extern "C" {
+
+int rpe_nchw_to_nhwc_split(const float *x, void *hi, void *lo, float *f32, int n, int C, int H, int W, int ld, int off, int f32_ld,
+                           int f32_off, void *stream) {
+    if (!x || (!hi && !f32) || ((hi == nullptr) != (lo == nullptr)) || n <= 0 || C <= 0 || H <= 0 || W <= 0) return RPE_ERR_INVALID_ARG;
+    const int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n);
+    rpe::nchw_to_nhwc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, f32, C, HW, ld, off,
+                                                                          f32_ld, f32_off);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_nhwc_to_nchw(const float *x, float *out, int n, int C, int H, int W, int ld, int off, void *stream) {
+    if (!x || !out || n <= 0 || C <= 0 || H <= 0 || W <= 0) return RPE_ERR_INVALID_ARG;
+    const int HW = H * W;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, n);
+    rpe::nhwc_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, out, C, HW, ld, off);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi, void *col_lo, int col_ld, void *x_hi, void *x_lo,
+                  int x_ld, int x_off, int n, int h, int w, void *stream) {
+    if (!coords1 || !col_hi || !col_lo || !x_hi || !x_lo || n <= 0 || h <= 0 || w <= 0 || col_ld < 98) return RPE_ERR_INVALID_ARG;
+    dim3 grid((h * w + 255) / 256, n);
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 0 && !delta) continue;
+        rpe::flow_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(coords1, delta, delta_ld, (__nv_bfloat16 *)col_hi,
+                                                                     (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi,
+                                                                     (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w, phase);
+        RPE_LAUNCH_CHECK();
+    }
+    return RPE_OK;
+}
+
+int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *out_lo, int out_ld, int out_off, long long npix,
+                 int mode, void *stream) {
+    if (!zr || !h || !out_hi || !out_lo || npix <= 0 || (mode == 1 && !q) || (out_ld % 4) || (out_off % 4)) return RPE_ERR_INVALID_ARG;
+    const size_t threads = (size_t)npix * 32;
+    rpe::gru_gate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(zr, h, q, (__nv_bfloat16 *)out_hi,
+                                                                                             (__nv_bfloat16 *)out_lo, out_ld, out_off,
+                                                                                             (size_t)npix, mode);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+}  // extern "C"

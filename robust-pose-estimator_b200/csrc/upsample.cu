@@ -11,16 +11,23 @@ namespace rpe {
 constexpr int kUpCells = 32;
 
 __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float *__restrict__ flow, const float *__restrict__ mask,
-                                                               float *__restrict__ out, int h, int w) {
+                                                               float *__restrict__ out, int h, int w, int mask_nhwc_ld) {
     extern __shared__ float sm[];
     float *s_mask = sm;                                  // [576][33]
     float *s_flow = sm + 576 * (kUpCells + 1);           // [2][3][kUpCells + 2]
     const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * kUpCells;
     const int hw = h * w;
     const int ncell = min(kUpCells, w - x0);
-    for (int e = threadIdx.x; e < 576 * kUpCells; e += blockDim.x) {
-        const int ch = e / kUpCells, xl = e - ch * kUpCells;
-        s_mask[ch * (kUpCells + 1) + xl] = xl < ncell ? __ldg(mask + ((size_t)b * 576 + ch) * hw + y * w + x0 + xl) : 0.0f;
+    if (mask_nhwc_ld > 0) {               // mask (B,h,w,ld) channels-last (tcgen05 convolution path)
+        for (int e = threadIdx.x; e < 576 * kUpCells; e += blockDim.x) {
+            const int xl = e / 576, ch = e - xl * 576;
+            s_mask[ch * (kUpCells + 1) + xl] = xl < ncell ? __ldg(mask + ((size_t)b * hw + y * w + x0 + xl) * mask_nhwc_ld + ch) : 0.0f;
+        }
+    } else {
+        for (int e = threadIdx.x; e < 576 * kUpCells; e += blockDim.x) {
+            const int ch = e / kUpCells, xl = e - ch * kUpCells;
+            s_mask[ch * (kUpCells + 1) + xl] = xl < ncell ? __ldg(mask + ((size_t)b * 576 + ch) * hw + y * w + x0 + xl) : 0.0f;
+        }
     }
     for (int e = threadIdx.x; e < 2 * 3 * (kUpCells + 2); e += blockDim.x) {
         const int c = e / (3 * (kUpCells + 2));
@@ -66,7 +73,18 @@ __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float *__re
 
 }  // namespace rpe
 
+static int convex_upsample_impl(const float *flow, const float *mask, float *out, int B, int h, int w, int nhwc_ld, void *stream);
+
 extern "C" int rpe_convex_upsample8(const float *flow, const float *mask, float *out, int B, int h, int w, void *stream) {
+    return convex_upsample_impl(flow, mask, out, B, h, w, 0, stream);
+}
+
+extern "C" int rpe_convex_upsample8_nhwc(const float *flow, const float *mask, int mask_ld, float *out, int B, int h, int w, void *stream) {
+    if (mask_ld < 576) return RPE_ERR_INVALID_ARG;
+    return convex_upsample_impl(flow, mask, out, B, h, w, mask_ld, stream);
+}
+
+static int convex_upsample_impl(const float *flow, const float *mask, float *out, int B, int h, int w, int nhwc_ld, void *stream) {
     using namespace rpe;
     if (!flow || !mask || !out || B <= 0 || h <= 0 || w <= 0) return RPE_ERR_INVALID_ARG;
     const size_t smem = (576 * (kUpCells + 1) + 2 * 3 * (kUpCells + 2)) * sizeof(float);
@@ -76,7 +94,7 @@ extern "C" int rpe_convex_upsample8(const float *flow, const float *mask, float 
         attr = true;
     }
     dim3 grid((w + kUpCells - 1) / kUpCells, h, B);
-    convex_upsample8_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(flow, mask, out, h, w);
+    convex_upsample8_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(flow, mask, out, h, w, nhwc_ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

@@ -1,0 +1,77 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (bf16x3) and the tensor-core RAFT update operator against torch fp32
+convolutions (test-only reference of a floating-point kernel) and against the reference tracker's golden outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle.detrand import det_uniform, unpack
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CKPT = os.path.join(ROOT, "oracle", "_ref", "trained", "poseNet_2xf8up4b.pth")
+
+
+@pytest.fixture(scope="module")
+def ops(cuda):
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import ops as _ops
+    return _ops
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("cin,cout,kh,kw,H,W,act", [
+    (64, 64, 1, 1, 8, 16, "none"),          # exactly one tile, one K block
+    (128, 256, 3, 3, 64, 80, "relu"),       # flow_head.conv1 shape
+    (384, 256, 1, 5, 64, 80, "sigmoid"),    # GRU gates, horizontal
+    (384, 128, 5, 1, 64, 80, "tanh"),       # GRU candidate, vertical
+    (256, 2, 3, 3, 64, 80, "none"),         # flow_head.conv2 (N tile of 16)
+    (256, 126, 3, 3, 44, 48, "relu"),       # odd channel count, image not a multiple of the 8x16 tile
+    (324, 256, 1, 1, 36, 44, "relu"),       # convc1: K padded 324 -> 384
+    (256, 576, 1, 1, 64, 80, "none"),       # mask head: three N blocks of 192
+    (98, 128, 1, 1, 64, 80, "relu"),        # im2col'ed 7x7 flow convolution
+])
+def test_conv_bf16x3_vs_torch_fp32(ops, cin, cout, kh, kw, H, W, act):
+    n = 2
+    x = dev(det_uniform((n, cin, H, W), 101, -2.0, 2.0))
+    w = dev(det_uniform((cout, cin, kh, kw), 102, -1.0, 1.0)) * (1.0 / np.sqrt(cin * kh * kw))
+    b = dev(det_uniform((cout,), 103, -0.5, 0.5))
+    with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
+        ref = F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
+    ref = {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](ref).float()
+    got = ops.conv2d_bf16x3(x, w, b, activation=act)
+    err = (got - ref).abs().max().item()
+    print(f"conv {cin}->{cout} {kh}x{kw} {act}: max abs err {err:.2e} (|ref| max {ref.abs().max().item():.2f})")
+    assert err < 3e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_update_operator_vs_torch_trunk(ops):
+    """12 GRU iterations on the tensor-core path vs the torch fp32 trunk, trained weights, real feature maps."""
+    if not os.path.isfile(CKPT) or not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz")):
+        pytest.skip("checkpoint / full golden not shipped")
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_net import PoseNet
+    g = np.load(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz"))
+    ck = torch.load(CKPT, map_location="cpu", weights_only=False)
+    outs = {}
+    for prec in ("fp32", "bf16x3"):
+        cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision=prec)
+        model = PoseNet(cfg)
+        model.load_state_dict(ck["state_dict"])
+        model = model.cuda().eval()
+        i1 = dev(g["imgs_l"][1:3].astype(np.float32))
+        i2 = torch.cat((dev(g["imgs_l"][2:3].astype(np.float32)), dev(g["imgs_r"][2:3].astype(np.float32))))
+        preds, net, inp = model.flow(i1, i2)
+        outs[prec] = (preds[-1].clone(), net.clone())
+    epe = (outs["fp32"][0] - outs["bf16x3"][0]).pow(2).sum(1).sqrt()
+    print(f"bf16x3 update operator vs fp32 trunk: flow EPE mean {epe.mean().item():.2e} max {epe.max().item():.2e}; "
+          f"hidden state max diff {(outs['fp32'][1] - outs['bf16x3'][1]).abs().max().item():.2e}")
+    assert epe.mean().item() < 2e-4 and epe.max().item() < 5e-3
+    ref = dev(np.stack((g["s_time_flow"],)))
+    epe_ref = (outs["bf16x3"][0][0:1] - ref).pow(2).sum(1).sqrt()
+    assert epe_ref.mean().item() < 1e-2                                    # north-star flow gate vs the reference itself
