@@ -187,37 +187,46 @@ int rpe_convex_upsample8(const float *flow, const float *mask, float *out, int B
 int rpe_convex_upsample8_nhwc(const float *flow, const float *mask, int mask_ld, float *out, int B, int h, int w, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
- * "Next" row: the RAFT update operator on tcgen05 tensor cores.
- * Replaces the convolutions of BasicUpdateBlock (/root/reference/core/RAFT/core/update.py:79-136) that the
- * reference runs through cuDNN.  Activations are NHWC bf16 "split" planes (hi = bf16(v), lo = bf16(v - hi));
+ * "Next" row: the RAFT convolutional trunk on tcgen05 tensor cores.
+ * Replaces the convolutions of BasicUpdateBlock (/root/reference/core/RAFT/core/update.py:79-136) and of BasicEncoder
+ * (/root/reference/core/RAFT/core/extractor.py:118-192) that the reference runs through cuDNN.  Activations are NHWC bf16 "split" planes (hi = bf16(v), lo = bf16(v - hi));
  * a convolution contracts over a list of (activation plane, weight) sources, so concatenated inputs are never
  * materialised and hi*hi + lo*hi + hi*lo reproduces fp32 convolutions to ~1e-5.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rpe_conv_source {
-    const void *act;     /* bf16 NHWC (N,H,W,c_total)                                  */
-    int c_total;         /* channel stride of `act` (multiple of 8)                    */
-    int c_offset;        /* first channel read (multiple of 8)                         */
-    int c_count;         /* channels read (multiple of 64)                             */
-    const void *weight;  /* bf16 [kh*kw][cout_pad][c_count], K-major                   */
+    const void *act_hi;  /* bf16 NHWC (N,H,W,c_total): hi plane                                       */
+    const void *act_lo;  /* lo plane, or NULL for single-pass bf16 (then w_lo must be NULL too)       */
+    int c_total;         /* channel stride of the activation tensor (multiple of 8)                   */
+    int c_offset;        /* first channel read (multiple of 8)                                        */
+    int c_count;         /* channels read (multiple of 16); channels past the window read as zero     */
+    const void *w_hi;    /* bf16 [kh*kw][cout_pad][w_cstride], K-major: hi plane                      */
+    const void *w_lo;    /* lo plane or NULL                                                          */
+    int w_cstride;       /* channel pitch of the weight rows (>= c_count, multiple of 8)              */
 } rpe_conv_source;
 
 typedef struct rpe_conv_desc {
-    int n_sources;
-    rpe_conv_source src[8];
-    int N, H, W;
-    int kh, kw;          /* odd; stride 1, zero padding (kh/2, kw/2)                   */
-    int cout, cout_pad;  /* real / padded (multiple of 16) output channels             */
-    const float *bias;   /* (cout) or NULL                                             */
-    int activation;      /* 0 none, 1 relu, 2 sigmoid, 3 tanh                          */
-    float out_scale;     /* applied after the activation                               */
-    float *out_f32;      /* NHWC fp32 output (N,H,W,f32_ld) at channel f32_offset, or NULL */
+    int n_sources;       /* 1..4; all sources have the same number of planes                          */
+    rpe_conv_source src[4];
+    int N, H, W;         /* INPUT size; output = (H + 2(kh/2) - kh)/stride + 1, same for W            */
+    int kh, kw;          /* odd; zero padding (kh/2, kw/2)                                            */
+    int stride;          /* 1 or 2 (0 = 1)                                                            */
+    int cout, cout_pad;  /* real / padded (multiple of 16) output channels                            */
+    const float *bias;   /* (cout) or NULL                                                            */
+    const float *pre;    /* optional fp32 NHWC addend (N,OH,OW,pre_ld), added BEFORE the activation   */
+    int pre_ld;
+    const float *res;    /* optional fp32 NHWC residual: out = relu(act(v) * scale + res)             */
+    int res_ld;
+    int activation;      /* 0 none, 1 relu, 2 sigmoid, 3 tanh                                         */
+    float out_scale;     /* applied after the activation                                              */
+    float *out_f32;      /* NHWC fp32 output (N,OH,OW,f32_ld) at channel f32_offset, or NULL          */
     int f32_ld, f32_offset;
-    void *out_hi, *out_lo; /* NHWC bf16 split planes (N,H,W,bf_ld) at channel bf_offset, or NULL */
+    void *out_hi, *out_lo; /* NHWC bf16 planes (N,OH,OW,bf_ld) at channel bf_offset; out_lo may be NULL */
     int bf_ld, bf_offset;
 } rpe_conv_desc;
 
 int rpe_conv_plan_create(const rpe_conv_desc *desc, void **plan_out);   /* encodes the TMA descriptors once */
 int rpe_conv_plan_run(void *plan, void *stream);
+double rpe_conv_plan_flops(void *plan);      /* tensor-core flops of one run (x3 for the split arithmetic) */
 int rpe_conv_plan_destroy(void *plan);
 
 /* CorrBlock.__call__ writing the NHWC bf16 split planes the first motion-encoder convolution reads (ld >= 324). */

@@ -23,12 +23,14 @@ class PoseProblem(C.Structure):
 
 
 class ConvSource(C.Structure):
-    _fields_ = [("act", C.c_void_p), ("c_total", C.c_int), ("c_offset", C.c_int), ("c_count", C.c_int), ("weight", C.c_void_p)]
+    _fields_ = [("act_hi", C.c_void_p), ("act_lo", C.c_void_p), ("c_total", C.c_int), ("c_offset", C.c_int), ("c_count", C.c_int),
+                ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_cstride", C.c_int)]
 
 
 class ConvDesc(C.Structure):
-    _fields_ = [("n_sources", C.c_int), ("src", ConvSource * 8), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
-                ("kh", C.c_int), ("kw", C.c_int), ("cout", C.c_int), ("cout_pad", C.c_int), ("bias", C.c_void_p),
+    _fields_ = [("n_sources", C.c_int), ("src", ConvSource * 4), ("N", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("cout", C.c_int), ("cout_pad", C.c_int), ("bias", C.c_void_p),
+                ("pre", C.c_void_p), ("pre_ld", C.c_int), ("res", C.c_void_p), ("res_ld", C.c_int),
                 ("activation", C.c_int), ("out_scale", C.c_float), ("out_f32", C.c_void_p), ("f32_ld", C.c_int),
                 ("f32_offset", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("bf_ld", C.c_int),
                 ("bf_offset", C.c_int)]
@@ -61,6 +63,7 @@ SIGNATURES = {
     "rpe_convex_upsample8_nhwc": (_I, [_P, _P, _I, _P, _I, _I, _I, _P]),
     "rpe_conv_plan_create": (_I, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
     "rpe_conv_plan_run": (_I, [_P, _P]),
+    "rpe_conv_plan_flops": (C.c_double, [_P]),
     "rpe_conv_plan_destroy": (_I, [_P]),
     "rpe_corr_lookup_nhwc_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_nchw_to_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -4,39 +4,13 @@ Same arithmetic graph as ``update.update_forward`` (reference: /root/reference/c
 loop body of core/RAFT/core/raft.py:112-132) with every convolution evaluated as an error-compensated bf16x3 implicit
 GEMM on the tensor cores, NHWC activations, no materialised concatenations and the whole 12-iteration loop resident in
 pre-allocated device buffers (one set per batch shape)."""
-import ctypes as C
-
 import torch
 
-from .... import _lib, ops
+from .... import _lib
 from ....ops import _p, _stream, _timed, check
+from ....tc import ConvPlan, Planes, pack_weight
 
-ACT = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
-
-
-def _split(t):
-    hi = t.to(torch.bfloat16)
-    lo = (t - hi.float()).to(torch.bfloat16)
-    return hi.contiguous(), lo.contiguous()
-
-
-def _pack_weight(w, c_lo, c_hi, cout_pad):
-    """(Cout, Cin, kh, kw) fp32 -> channel window [c_lo, c_hi) as [taps][cout_pad][c_pad64] split planes."""
-    cout, _, kh, kw = w.shape
-    cs = c_hi - c_lo
-    cpad = (cs + 63) // 64 * 64
-    out = torch.zeros((kh * kw, cout_pad, cpad), dtype=torch.float32, device=w.device)
-    out[:, :cout, :cs] = w[:, c_lo:c_hi].permute(2, 3, 0, 1).reshape(kh * kw, cout, cs)
-    return _split(out)
-
-
-class _Planes:
-    """NHWC bf16 split planes (hi, lo) of shape (N, H, W, C)."""
-
-    def __init__(self, n, h, w, c, device):
-        self.hi = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
-        self.lo = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
-        self.c = c
+_Planes, _pack_weight = Planes, pack_weight          # (names used by ops.conv2d_bf16x3)
 
 
 class UpdateTC:
@@ -52,7 +26,7 @@ class UpdateTC:
         key = (name, c_lo, c_hi, cout_pad)
         if key not in self._packed:
             w = self.W[self.prefix + name + ".weight"] if transform is None else transform()
-            self._packed[key] = _pack_weight(w.float(), c_lo, c_hi, cout_pad)
+            self._packed[key] = pack_weight(w.float(), c_lo, c_hi, cout_pad)
         return self._packed[key]
 
     def _bias(self, name, transform=None):
@@ -67,40 +41,18 @@ class UpdateTC:
               weight=None, bias=None):
         """inputs: [(planes, c_offset, c_count_real, weight channel window start)]"""
         cout_pad = (cout + 15) // 16 * 16
-        d = _lib.ConvDesc()
-        k = 0
-        keep = []
-        for planes, c_off, c_cnt, w_lo in inputs:
-            w_hi_t, w_lo_t = self._w(name, w_lo, w_lo + c_cnt, cout_pad, weight)
-            cpad = w_hi_t.shape[-1]
-            for a, wt in ((planes.hi, w_hi_t), (planes.lo, w_hi_t), (planes.hi, w_lo_t)):      # hi*hi + lo*hi + hi*lo
-                d.src[k].act, d.src[k].c_total, d.src[k].c_offset, d.src[k].c_count = a.data_ptr(), planes.c, c_off, cpad
-                d.src[k].weight = wt.data_ptr()
-                k += 1
-            keep += [w_hi_t, w_lo_t]
-        d.n_sources = k
-        d.N, d.H, d.W = st["dims"]
-        d.kh, d.kw, d.cout, d.cout_pad = kh, kw, cout, cout_pad
-        b = self._bias(name, bias)
-        d.bias = b.data_ptr()
-        d.activation, d.out_scale = ACT[act], scale
-        if out_f32 is not None:
-            d.out_f32, d.f32_ld, d.f32_offset = out_f32.data_ptr(), out_f32.shape[-1], f32_off
-        if out_planes is not None:
-            d.out_hi, d.out_lo, d.bf_ld, d.bf_offset = out_planes.hi.data_ptr(), out_planes.lo.data_ptr(), out_planes.c, bf_off
-        plan = C.c_void_p()
-        check(_lib.lib().rpe_conv_plan_create(C.byref(d), C.byref(plan)), f"rpe_conv_plan_create({name})")
-        st["keep"] += keep + [b]
-        return plan
+        srcs = [(planes, c_off, c_cnt, self._w(name, w_lo, w_lo + c_cnt, cout_pad, weight)) for planes, c_off, c_cnt, w_lo in inputs]
+        return ConvPlan(name, srcs, st["dims"], kh, kw, cout, act, bias=self._bias(name, bias), out_f32=out_f32, f32_off=f32_off,
+                        out_planes=out_planes, bf_off=bf_off, scale=scale)
 
     def _state(self, n, h, w, device):
         key = (n, h, w, device.index)
         st = self._shapes.get(key)
         if st is not None:
             return st
-        P = lambda c: _Planes(n, h, w, c, device)
+        P = lambda c: Planes(n, h, w, c, device)
         f32 = lambda c: torch.zeros((n, h, w, c), dtype=torch.float32, device=device)
-        st = {"dims": (n, h, w), "keep": []}
+        st = {"dims": (n, h, w)}
         st.update(corr=P(384), cor1=P(256), cf=P(256), col=P(128), flo1=P(128), x=P(256), hp=P(128), rh=P(128), fh=P(256), mk=P(256),
                   h=f32(128), zr=f32(256), q=f32(128), delta=f32(4), mask=f32(576),
                   coords1=torch.zeros((n, 2, h, w), dtype=torch.float32, device=device))
@@ -130,8 +82,7 @@ class UpdateTC:
     # ---- execution ---------------------------------------------------------------------------------------
     @staticmethod
     def _run(st, name):
-        with _timed("conv_tc", 1):
-            check(_lib.lib().rpe_conv_plan_run(st["plans"][name], _stream()), f"rpe_conv_plan_run({name})")
+        st["plans"][name].run()
 
     def refine(self, corr_pyr, net, inp, iters=12, flow_init=None, want_mask=True):
         """corr_pyr: ops.CorrPyramid; net, inp (B,128,h,w) fp32 NCHW.  -> (flow_up or None, net NCHW, flow_lo (B,2,h,w))."""

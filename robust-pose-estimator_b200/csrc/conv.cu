@@ -1,17 +1,24 @@
-// Implicit-GEMM 2-D convolution on tcgen05 tensor cores for the RAFT update operator.
+// Implicit-GEMM 2-D convolution on tcgen05 tensor cores: the convolutional trunk of RAFT (SURVEY.md section 8f-1;
+// reference: /root/reference/core/RAFT/core/update.py:79-136 update operator, core/RAFT/core/extractor.py:118-192 encoders,
+// which the reference runs through cuDNN).
 //
-//   out[n, y, x, co] = act( bias[co] + sum_s sum_(dy,dx) sum_ci  A_s[n, y+dy, x+dx, ci] * W_s[tap][co][ci] ) * scale
+//   v[n, y, x, co]   = bias[co] + pre[n, y, x, co] + sum_s sum_(ky,kx) sum_ci  A_s[n, y*st+ky-ph, x*st+kx-pw, ci] * W_s[ky*kw+kx][co][ci]
+//   out[n, y, x, co] = act(v) * scale                       (then  out = relu(out + res[n, y, x, co])  when a residual is given)
 //
-// Activations are NHWC bf16 planes; the contraction runs over a LIST of (activation plane, weight) sources, which
-// gives both concatenation-free multi-input convolutions (cat(h, x) never materialised) and the error-compensated
-// "bf16x3" arithmetic: a value v is stored as two planes hi = bf16(v), lo = bf16(v - hi) and a product is evaluated as
-// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (16 mantissa bits per operand; measured pose deviation vs fp32
-// convolutions < 1e-5).  Stride 1, "same" zero padding (all update-block convolutions).
+// Activations are NHWC bf16 planes.  The contraction runs over a LIST of sources (activation tensor + its weight slice), so
+// concatenated inputs are never materialised, and every source may carry two planes hi = bf16(v), lo = bf16(v - hi): the
+// "bf16x3" arithmetic evaluates hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (16 mantissa bits per operand; measured
+// deviation from fp32 convolutions ~1e-5 relative).  Stride 1 or 2, "same"-style zero padding (k/2).
 //
-// Kernel: persistent, warp-specialised like corr_gemm_kernel.  M tile = 8x16 output pixels of one image (128 TMEM lanes),
-// N tile = up to 256 output channels, K block = 64 bf16 channels of one tap of one source.  The A tile of a tap is a
-// TMA box of the 4-D activation tensor map at (c, x0+dx, y0+dy, n): out-of-image coordinates are zero-filled by the TMA
-// unit, which IS the zero padding.  Epilogue: TMEM -> registers -> bias / activation -> fp32 and/or bf16 hi/lo NHWC.
+// Kernel: persistent, warp-specialised.  The output tile is 128 pixels = 16 (major) x 8 (minor) positions of one image; `orient`
+// picks which image axis is the minor one.  Shared memory holds an activation SLAB of (16 + kmaj - 1) x 8 positions x 64
+// channels per plane, laid out [major][minor][64 ch] with the 128-byte swizzle, so the UMMA descriptor of a filter tap that is
+// shifted along the major axis is the same slab advanced by 1024 bytes: one TMA load serves all kmaj taps of a filter column
+// (3x3: 3 loads instead of 9; 1x5 / 5x1: 1 load instead of 5).  Out-of-image coordinates are zero-filled by the TMA unit, which
+// IS the zero padding.  The hi and lo planes of a stage are loaded once and feed all three products.  Weights stream through
+// their own ring, one [bn][64] tile per tap.  Roles: warp 0 = activation TMA producer, warp 3 = weight TMA producer, warp 1 =
+// tcgen05.mma issuer (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias / addend /
+// activation / residual -> fp32 and/or bf16 hi/lo NHWC stores) overlapped with the next tile through two TMEM accumulator stages.
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>
 #include <math.h>
@@ -20,25 +27,33 @@
 
 namespace rpe {
 
-constexpr int kCvTH = 8, kCvTW = 16;                  // output tile: 8 rows x 16 cols = 128 pixels
-constexpr int kCvBK = 64;                             // bf16 channels per K block (128-byte swizzle row)
-constexpr int kCvStages = 4, kCvAcc = 2;
+constexpr int kCvBK = 64;                             // bf16 channels per K block (one 128-byte swizzle row)
+constexpr int kCvAcc = 2;                             // TMEM accumulator stages
 constexpr int kCvThreads = 256;
-constexpr int kCvABytes = 128 * kCvBK * 2;            // 16 KB
-constexpr int kCvMaxSrc = 8;
+constexpr int kCvMaxSrc = 4;
 constexpr int kCvMaxBN = 256;
-constexpr int kCvBBytesMax = kCvMaxBN * kCvBK * 2;    // 32 KB
-constexpr int kCvSmem = kCvStages * (kCvABytes + kCvBBytesMax) + 1024 + 256;
+constexpr int kCvMaxAStages = 4, kCvMaxBStages = 8;
+constexpr int kCvSmemData = 216 * 1024;               // budget for the two rings
+constexpr int kCvSmem = kCvSmemData + 1024 + 512;     // + alignment slack + barriers
 
 struct alignas(64) ConvParams {
-    CUtensorMap amap[kCvMaxSrc];
-    CUtensorMap wmap[kCvMaxSrc];
+    CUtensorMap amap[kCvMaxSrc][2];
+    CUtensorMap wmap[kCvMaxSrc][2];
     int cblocks[kCvMaxSrc];
-    int n_src;
-    int N, H, W, tiles_x, tiles_y;
-    int kh, kw;
+    int ksteps_last[kCvMaxSrc];                       // 16-channel MMA steps of the last K block (1..4)
+    int n_src, n_planes;
+    int N, OH, OW, tiles_min, tiles_maj;
+    int orient;                                       // 0: minor axis = x, 1: minor axis = y
+    int kmin, kmaj, pad_min, pad_maj, stride, kw;
+    int reuse;                                        // 1: one slab per filter column serves all kmaj taps (stride 1)
+    uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes;
+    int n_a_stages, n_b_stages;
     int cout, bn, n_blocks;
     const float *bias;
+    const float *pre;
+    int pre_ld;
+    const float *res;
+    int res_ld;
     int act;
     float scale;
     float *out_f32;
@@ -63,6 +78,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t cv_sw128_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
@@ -75,34 +91,55 @@ __device__ __forceinline__ float cv_activate(float v, int act) {
     return v;
 }
 
+struct CvTile {
+    int nb, img, omin0, omaj0;
+};
+__device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
+    CvTile t;
+    t.nb = tile % P.n_blocks;
+    const int t2 = tile / P.n_blocks;
+    const int per_img = P.tiles_min * P.tiles_maj;
+    t.img = t2 / per_img;
+    const int tr = t2 - t.img * per_img;
+    const int tj = tr / P.tiles_min;
+    t.omin0 = (tr - tj * P.tiles_min) * 8;
+    t.omaj0 = tj * 16;
+    return t;
+}
+
 __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_constant__ ConvParams P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
-    uint8_t *sB = sA + kCvStages * kCvABytes;
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(sB + kCvStages * kCvBBytesMax);
-    uint64_t *empty_bar = full_bar + kCvStages;
-    uint64_t *tmem_full = empty_bar + kCvStages;
+    uint8_t *sB = sA + (size_t)P.n_a_stages * P.a_stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kCvSmemData);
+    uint64_t *a_full = bars;
+    uint64_t *a_empty = a_full + kCvMaxAStages;
+    uint64_t *b_full = a_empty + kCvMaxAStages;
+    uint64_t *b_empty = b_full + kCvMaxBStages;
+    uint64_t *tmem_full = b_empty + kCvMaxBStages;
     uint64_t *tmem_empty = tmem_full + kCvAcc;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + kCvAcc);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_img = P.tiles_x * P.tiles_y;
-    const int num_tiles = P.N * tiles_per_img * P.n_blocks;
-    const int taps = P.kh * P.kw;
-    const int ph = P.kh / 2, pw = P.kw / 2;
-    const uint32_t b_bytes = (uint32_t)P.bn * kCvBK * 2;
+    const int num_tiles = P.N * P.tiles_min * P.tiles_maj * P.n_blocks;
+    const int a_units = P.reuse ? 1 : P.kmaj;        // slabs per filter column
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < P.n_src; ++s) {
-            prefetch_tmap(&P.amap[s]);
-            prefetch_tmap(&P.wmap[s]);
-        }
+        for (int s = 0; s < P.n_src; ++s)
+            for (int p = 0; p < P.n_planes; ++p) {
+                prefetch_tmap(&P.amap[s][p]);
+                prefetch_tmap(&P.wmap[s][p]);
+            }
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kCvStages; ++i) {
-            mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+        for (int i = 0; i < kCvMaxAStages; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < kCvMaxBStages; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
         }
         for (int i = 0; i < kCvAcc; ++i) {
             mbar_init(&tmem_full[i], 1);
@@ -120,77 +157,109 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== activation producer =====================
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int nb = tile % P.n_blocks;
-                const int t2 = tile / P.n_blocks;
-                const int img = t2 / tiles_per_img;
-                const int tr = t2 - img * tiles_per_img;
-                const int ty = tr / P.tiles_x, tx = tr - ty * P.tiles_x;
-                const int y0 = ty * kCvTH, x0 = tx * kCvTW;
-                for (int s = 0; s < P.n_src; ++s) {
-                    for (int tap = 0; tap < taps; ++tap) {
-                        const int dy = tap / P.kw - ph, dx = tap % P.kw - pw;
-                        for (int cb = 0; cb < P.cblocks[s]; ++cb) {
-                            mbar_wait(&empty_bar[stage], phase ^ 1);
-                            mbar_expect_tx(&full_bar[stage], kCvABytes + b_bytes);
-                            tma_load_4d(sA + stage * kCvABytes, &P.amap[s], &full_bar[stage], cb * kCvBK, x0 + dx, y0 + dy, img);
-                            tma_load_3d(sB + stage * kCvBBytesMax, &P.wmap[s], &full_bar[stage], cb * kCvBK, nb * P.bn, tap);
-                            if (++stage == kCvStages) stage = 0, phase ^= 1;
-                        }
-                    }
-                }
+                const CvTile t = cv_decode(P, tile);
+                for (int s = 0; s < P.n_src; ++s)
+                    for (int cb = 0; cb < P.cblocks[s]; ++cb)
+                        for (int tm = 0; tm < P.kmin; ++tm)
+                            for (int u = 0; u < a_units; ++u) {
+                                mbar_wait(&a_empty[stage], phase ^ 1);
+                                mbar_expect_tx(&a_full[stage], P.a_plane_bytes * P.n_planes);
+                                const int cmin = t.omin0 * P.stride + tm - P.pad_min;
+                                const int cmaj = t.omaj0 * P.stride + (P.reuse ? 0 : u) - P.pad_maj;
+                                uint8_t *dst = sA + (size_t)stage * P.a_stage_bytes;
+                                for (int p = 0; p < P.n_planes; ++p)
+                                    tma_load_4d(dst + p * P.a_plane_bytes, &P.amap[s][p], &a_full[stage], cb * kCvBK, cmin, cmaj, t.img);
+                                if (++stage == P.n_a_stages) stage = 0, phase ^= 1;
+                            }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== weight producer =====================
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const CvTile t = cv_decode(P, tile);
+                for (int s = 0; s < P.n_src; ++s)
+                    for (int cb = 0; cb < P.cblocks[s]; ++cb)
+                        for (int tm = 0; tm < P.kmin; ++tm)
+                            for (int tj = 0; tj < P.kmaj; ++tj) {
+                                mbar_wait(&b_empty[stage], phase ^ 1);
+                                mbar_expect_tx(&b_full[stage], P.b_plane_bytes * P.n_planes);
+                                const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
+                                uint8_t *dst = sB + (size_t)stage * P.b_stage_bytes;
+                                for (int p = 0; p < P.n_planes; ++p)
+                                    tma_load_3d(dst + p * P.b_plane_bytes, &P.wmap[s][p], &b_full[stage], cb * kCvBK, t.nb * P.bn, tap);
+                                if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                            }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
-            // instruction descriptor: D fp32, A/B bf16, K-major, N = bn, M = 128
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            int stage = 0;
-            uint32_t phase = 0;
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            int total_kb = 0;
-            for (int s = 0; s < P.n_src; ++s) total_kb += taps * P.cblocks[s];
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kCvMaxBN);
-                for (int kb = 0; kb < total_kb; ++kb) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tcgen05_fence_after();
-                    const uint64_t da = cv_sw128_desc(smem_u32(sA + stage * kCvABytes));
-                    const uint64_t db = cv_sw128_desc(smem_u32(sB + stage * kCvBBytesMax));
-#pragma unroll
-                    for (int k = 0; k < kCvBK / 16; ++k)
-                        umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == total_kb - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == kCvStages) stage = 0, phase ^= 1;
-                }
+                uint32_t accumulate = 0;
+                for (int s = 0; s < P.n_src; ++s)
+                    for (int cb = 0; cb < P.cblocks[s]; ++cb) {
+                        const int ksteps = (cb == P.cblocks[s] - 1) ? P.ksteps_last[s] : kCvBK / 16;
+                        for (int tm = 0; tm < P.kmin; ++tm)
+                            for (int tj = 0; tj < P.kmaj; ++tj) {
+                                if (!P.reuse || tj == 0) {
+                                    mbar_wait(&a_full[sa], pa);
+                                }
+                                mbar_wait(&b_full[sb], pb);
+                                tcgen05_fence_after();
+                                const uint32_t a0 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) + (P.reuse ? (uint32_t)tj * 1024u : 0u);
+                                const uint32_t b0 = smem_u32(sB + (size_t)sb * P.b_stage_bytes);
+                                const uint64_t da_hi = cv_sw128_desc(a0), db_hi = cv_sw128_desc(b0);
+                                for (int k = 0; k < ksteps; ++k) {
+                                    umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                if (P.n_planes == 2) {
+                                    const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes), db_lo = cv_sw128_desc(b0 + P.b_plane_bytes);
+                                    for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                    for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                }
+                                umma_commit(&b_empty[sb]);
+                                if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
+                                if (!P.reuse || tj == P.kmaj - 1) {
+                                    umma_commit(&a_empty[sa]);
+                                    if (++sa == P.n_a_stages) sa = 0, pa ^= 1;
+                                }
+                            }
+                    }
+                umma_commit(&tmem_full[acc]);
                 if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
-        // ===================== Epilogue =====================
+        // ===================== epilogue =====================
         const int wq = warp - 4;
-        const int p = wq * 32 + lane;                  // pixel inside the tile
-        const int py = p / kCvTW, px = p - py * kCvTW;
+        const int m = wq * 32 + lane;                  // accumulator row = pixel inside the tile
+        const int gi = m >> 3, mi = m & 7;             // (major, minor) position
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int nb = tile % P.n_blocks;
-            const int t2 = tile / P.n_blocks;
-            const int img = t2 / tiles_per_img;
-            const int tr = t2 - img * tiles_per_img;
-            const int ty = tr / P.tiles_x, tx = tr - ty * P.tiles_x;
-            const int y = ty * kCvTH + py, x = tx * kCvTW + px;
-            const bool inside = (y < P.H) && (x < P.W);
-            const size_t pix = ((size_t)img * P.H + y) * P.W + x;
+            const CvTile t = cv_decode(P, tile);
+            const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
+            const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
+            const bool inside = (y < P.OH) && (x < P.OW);
+            const size_t pix = ((size_t)t.img * P.OH + y) * P.OW + x;
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int n_chunks = P.bn / 16;
@@ -217,19 +286,38 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
                 if (!inside) continue;
-                const int co0 = nb * P.bn + c * 16;
+                const int co0 = t.nb * P.bn + c * 16;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (j >= cols) break;
+                    const int co = co0 + j;
+                    if (co >= P.cout) break;
+                    const bool full = co + 3 < P.cout;
                     float o[4];
+                    float add[4] = {0.0f, 0.0f, 0.0f, 0.0f}, rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    if (full) {
+                        if (P.pre) {
+                            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
+                            add[0] = a.x, add[1] = a.y, add[2] = a.z, add[3] = a.w;
+                        }
+                        if (P.res) {
+                            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
+                            rs[0] = a.x, rs[1] = a.y, rs[2] = a.z, rs[3] = a.w;
+                        }
+                    } else {
+                        for (int k = 0; k < 4 && co + k < P.cout; ++k) {
+                            if (P.pre) add[k] = __ldg(P.pre + pix * P.pre_ld + co + k);
+                            if (P.res) rs[k] = __ldg(P.res + pix * P.res_ld + co + k);
+                        }
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int co = co0 + j + k;
-                        const float b = (P.bias != nullptr && co < P.cout) ? __ldg(P.bias + co) : 0.0f;
-                        o[k] = cv_activate(__uint_as_float(v[j + k]) + b, P.act) * P.scale;
+                        const float b = (P.bias != nullptr && co + k < P.cout) ? __ldg(P.bias + co + k) : 0.0f;
+                        float r = cv_activate(__uint_as_float(v[j + k]) + b + add[k], P.act) * P.scale;
+                        if (P.res) r = fmaxf(r + rs[k], 0.0f);
+                        o[k] = r;
                     }
-                    const int co = co0 + j;
-                    if (co + 3 < P.cout) {
+                    if (full) {
                         if (P.out_f32)
                             *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
                         if (P.out_hi) {
@@ -240,7 +328,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                                 l[k] = __float2bfloat16_rn(o[k] - __bfloat162float(h[k]));
                             }
                             *reinterpret_cast<uint2 *>(P.out_hi + pix * P.bf_ld + P.bf_off + co) = *reinterpret_cast<uint2 *>(h);
-                            *reinterpret_cast<uint2 *>(P.out_lo + pix * P.bf_ld + P.bf_off + co) = *reinterpret_cast<uint2 *>(l);
+                            if (P.out_lo) *reinterpret_cast<uint2 *>(P.out_lo + pix * P.bf_ld + P.bf_off + co) = *reinterpret_cast<uint2 *>(l);
                         }
                     } else {
                         for (int k = 0; k < 4 && co + k < P.cout; ++k) {
@@ -248,7 +336,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                             if (P.out_hi) {
                                 const __nv_bfloat16 h = __float2bfloat16_rn(o[k]);
                                 P.out_hi[pix * P.bf_ld + P.bf_off + co + k] = h;
-                                P.out_lo[pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(o[k] - __bfloat162float(h));
+                                if (P.out_lo) P.out_lo[pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(o[k] - __bfloat162float(h));
                             }
                         }
                     }
@@ -280,6 +368,7 @@ static int cv_load_encode() {
 struct ConvPlan {
     ConvParams p;
     int grid;
+    double flops;          // real multiply-adds x 2 of one run (all products of the split arithmetic)
 };
 
 }  // namespace rpe
@@ -291,13 +380,17 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     if (!d || !plan_out) return RPE_ERR_INVALID_ARG;
     if (d->n_sources < 1 || d->n_sources > kCvMaxSrc) return RPE_ERR_INVALID_ARG;
     if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->kh < 1 || d->kw < 1 || !(d->kh & 1) || !(d->kw & 1)) return RPE_ERR_INVALID_ARG;
+    const int stride = d->stride <= 0 ? 1 : d->stride;
+    if (stride != 1 && stride != 2) return RPE_ERR_INVALID_ARG;
     if (d->cout <= 0 || d->cout_pad < d->cout || d->cout_pad % 16 != 0) return RPE_ERR_INVALID_ARG;
     if (!d->out_f32 && !d->out_hi) return RPE_ERR_INVALID_ARG;
-    if ((d->out_hi == nullptr) != (d->out_lo == nullptr)) return RPE_ERR_INVALID_ARG;
+    if (d->out_lo && !d->out_hi) return RPE_ERR_INVALID_ARG;
     if (d->out_f32 && ((d->f32_ld % 4) || (d->f32_offset % 4) || !aligned16(d->out_f32))) return RPE_ERR_ALIGNMENT;
     if (d->out_hi && ((d->bf_ld % 4) || (d->bf_offset % 4) || (reinterpret_cast<uintptr_t>(d->out_hi) & 7u) ||
                       (reinterpret_cast<uintptr_t>(d->out_lo) & 7u)))
         return RPE_ERR_ALIGNMENT;
+    if (d->pre && ((d->pre_ld % 4) || !aligned16(d->pre))) return RPE_ERR_ALIGNMENT;
+    if (d->res && ((d->res_ld % 4) || !aligned16(d->res))) return RPE_ERR_ALIGNMENT;
     int rc = cv_load_encode();
     if (rc != RPE_OK) return rc;
     ConvPlan *pl = new ConvPlan();
@@ -309,58 +402,101 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         delete pl;
         return RPE_ERR_INVALID_ARG;
     }
+    const int ph = d->kh / 2, pw = d->kw / 2;
+    const int OH = (d->H + 2 * ph - d->kh) / stride + 1, OW = (d->W + 2 * pw - d->kw) / stride + 1;
+    // orientation: the filter axis with more taps becomes the major axis (its taps share one slab); 3x3 keeps minor = x
+    const int orient = (d->kw > d->kh) ? 1 : 0;
+    p.orient = orient;
+    p.kmin = orient == 0 ? d->kw : d->kh;
+    p.kmaj = orient == 0 ? d->kh : d->kw;
+    p.pad_min = orient == 0 ? pw : ph;
+    p.pad_maj = orient == 0 ? ph : pw;
+    p.stride = stride, p.kw = d->kw;
+    p.reuse = (stride == 1) ? 1 : 0;
+    const int slab_rows = p.reuse ? 16 + p.kmaj - 1 : 16;
     p.n_src = d->n_sources;
+    p.n_planes = d->src[0].act_lo ? 2 : 1;
+    p.a_plane_bytes = (uint32_t)slab_rows * 8 * 128;
+    p.a_stage_bytes = p.a_plane_bytes * p.n_planes;
+    p.b_plane_bytes = (uint32_t)bn * 128;
+    p.b_stage_bytes = p.b_plane_bytes * p.n_planes;
+    // ring depths: at least two stages each, activations up to 3 slabs, the rest goes to the weight ring
+    p.n_a_stages = 2;
+    p.n_b_stages = (int)((kCvSmemData - 2 * (size_t)p.a_stage_bytes) / p.b_stage_bytes);
+    if (p.n_b_stages > 4 && p.n_a_stages < kCvMaxAStages &&
+        (size_t)(p.n_a_stages + 1) * p.a_stage_bytes + 4 * (size_t)p.b_stage_bytes <= (size_t)kCvSmemData) {
+        p.n_a_stages += 1;
+        p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_stage_bytes);
+    }
+    if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
+    if (p.n_b_stages < 2) {
+        delete pl;
+        return RPE_ERR_INVALID_ARG;
+    }
     const int taps = d->kh * d->kw;
+    double macs = 0.0;
     for (int s = 0; s < d->n_sources; ++s) {
         const rpe_conv_source &sc = d->src[s];
-        if (!sc.act || !sc.weight || sc.c_count <= 0 || (sc.c_count % kCvBK) || (sc.c_offset % 8) || (sc.c_total % 8) ||
-            sc.c_offset + sc.c_count > sc.c_total || (reinterpret_cast<uintptr_t>(sc.act) & 15u) ||
-            (reinterpret_cast<uintptr_t>(sc.weight) & 15u)) {
+        if (!sc.act_hi || !sc.w_hi || ((sc.act_lo != nullptr) != (p.n_planes == 2)) || ((sc.w_lo != nullptr) != (p.n_planes == 2)) ||
+            sc.c_count <= 0 || (sc.c_count % 16) || (sc.c_offset % 8) || (sc.c_total % 8) || sc.c_offset + sc.c_count > sc.c_total ||
+            sc.w_cstride < sc.c_count || (sc.w_cstride % 8)) {
             delete pl;
             return RPE_ERR_INVALID_ARG;
         }
-        p.cblocks[s] = sc.c_count / kCvBK;
-        {   // activations: (C, W, H, N) bf16, box (64, 16, 8, 1); the channel window starts at c_offset
-            const char *base = reinterpret_cast<const char *>(sc.act) + (size_t)sc.c_offset * 2;
-            cuuint64_t dims[4] = {(cuuint64_t)sc.c_count, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-            cuuint64_t strides[3] = {(cuuint64_t)sc.c_total * 2, (cuuint64_t)sc.c_total * 2 * d->W,
-                                     (cuuint64_t)sc.c_total * 2 * d->W * d->H};
-            cuuint32_t box[4] = {kCvBK, kCvTW, kCvTH, 1};
-            cuuint32_t es[4] = {1, 1, 1, 1};
-            CUresult r = g_cv_encode(&p.amap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char *>(base), dims, strides, box, es,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) {
-                g_last_cuda_error = 100000 + (int)r;
+        p.cblocks[s] = (sc.c_count + kCvBK - 1) / kCvBK;
+        p.ksteps_last[s] = (sc.c_count - (p.cblocks[s] - 1) * kCvBK) / 16;
+        macs += (double)sc.c_count * taps;
+        for (int pln = 0; pln < p.n_planes; ++pln) {
+            const void *act = pln == 0 ? sc.act_hi : sc.act_lo;
+            const void *wgt = pln == 0 ? sc.w_hi : sc.w_lo;
+            if ((reinterpret_cast<uintptr_t>(act) & 15u) || (reinterpret_cast<uintptr_t>(wgt) & 15u)) {
                 delete pl;
-                return RPE_ERR_CUDA;
+                return RPE_ERR_ALIGNMENT;
             }
-        }
-        {   // weights: (Cin_s, Cout_pad, taps) bf16, box (64, bn, 1)
-            cuuint64_t dims[3] = {(cuuint64_t)sc.c_count, (cuuint64_t)d->cout_pad, (cuuint64_t)taps};
-            cuuint64_t strides[2] = {(cuuint64_t)sc.c_count * 2, (cuuint64_t)sc.c_count * 2 * d->cout_pad};
-            cuuint32_t box[3] = {kCvBK, (cuuint32_t)bn, 1};
-            cuuint32_t es[3] = {1, 1, 1};
-            CUresult r = g_cv_encode(&p.wmap[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(sc.weight), dims, strides, box,
-                                     es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) {
-                g_last_cuda_error = 100000 + (int)r;
-                delete pl;
-                return RPE_ERR_CUDA;
+            {   // activations: (C, minor, major, N) bf16; the channel window starts at c_offset, channels beyond it read as zero
+                const char *base = reinterpret_cast<const char *>(act) + (size_t)sc.c_offset * 2;
+                const cuuint64_t pix = (cuuint64_t)sc.c_total * 2, row = pix * d->W;
+                cuuint64_t dims[4] = {(cuuint64_t)sc.c_count, (cuuint64_t)(orient == 0 ? d->W : d->H),
+                                      (cuuint64_t)(orient == 0 ? d->H : d->W), (cuuint64_t)d->N};
+                cuuint64_t strides[3] = {orient == 0 ? pix : row, orient == 0 ? row : pix, row * d->H};
+                cuuint32_t box[4] = {kCvBK, (cuuint32_t)(8 * stride), (cuuint32_t)(slab_rows * stride), 1};
+                cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+                CUresult r = g_cv_encode(&p.amap[s][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char *>(base), dims, strides, box,
+                                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    g_last_cuda_error = 100000 + (int)r;
+                    delete pl;
+                    return RPE_ERR_CUDA;
+                }
+            }
+            {   // weights: (Cin_s, Cout_pad, taps) bf16 with row pitch w_cstride, box (64, bn, 1)
+                cuuint64_t dims[3] = {(cuuint64_t)sc.c_count, (cuuint64_t)d->cout_pad, (cuuint64_t)taps};
+                cuuint64_t strides[2] = {(cuuint64_t)sc.w_cstride * 2, (cuuint64_t)sc.w_cstride * 2 * d->cout_pad};
+                cuuint32_t box[3] = {kCvBK, (cuuint32_t)bn, 1};
+                cuuint32_t es[3] = {1, 1, 1};
+                CUresult r = g_cv_encode(&p.wmap[s][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(wgt), dims, strides, box,
+                                         es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    g_last_cuda_error = 100000 + (int)r;
+                    delete pl;
+                    return RPE_ERR_CUDA;
+                }
             }
         }
     }
-    p.N = d->N, p.H = d->H, p.W = d->W;
-    p.tiles_x = (d->W + kCvTW - 1) / kCvTW;
-    p.tiles_y = (d->H + kCvTH - 1) / kCvTH;
-    p.kh = d->kh, p.kw = d->kw;
+    p.N = d->N, p.OH = OH, p.OW = OW;
+    p.tiles_min = ((orient == 0 ? OW : OH) + 7) / 8;
+    p.tiles_maj = ((orient == 0 ? OH : OW) + 15) / 16;
     p.cout = d->cout, p.bn = bn, p.n_blocks = n_blocks;
     p.bias = d->bias, p.act = d->activation, p.scale = d->out_scale;
+    p.pre = d->pre, p.pre_ld = d->pre_ld, p.res = d->res, p.res_ld = d->res_ld;
     p.out_f32 = d->out_f32, p.f32_ld = d->f32_ld, p.f32_off = d->f32_offset;
     p.out_hi = reinterpret_cast<__nv_bfloat16 *>(d->out_hi), p.out_lo = reinterpret_cast<__nv_bfloat16 *>(d->out_lo);
     p.bf_ld = d->bf_ld, p.bf_off = d->bf_offset;
-    const int tiles = p.N * p.tiles_x * p.tiles_y * p.n_blocks;
+    pl->flops = 2.0 * macs * (double)d->cout * (double)d->N * OH * OW * (p.n_planes == 2 ? 3.0 : 1.0);
+    const int tiles = p.N * p.tiles_min * p.tiles_maj * p.n_blocks;
     pl->grid = sm_count() < tiles ? sm_count() : tiles;
     if (pl->grid < 1) pl->grid = 1;
     static bool attr = false;
@@ -383,6 +519,11 @@ int rpe_conv_plan_run(void *plan, void *stream) {
     conv_bf16_kernel<<<pl->grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(pl->p);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
+}
+
+double rpe_conv_plan_flops(void *plan) {
+    if (!plan) return 0.0;
+    return reinterpret_cast<rpe::ConvPlan *>(plan)->flops;
 }
 
 int rpe_conv_plan_destroy(void *plan) {

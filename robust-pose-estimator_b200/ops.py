@@ -308,39 +308,28 @@ def convex_upsample8(flow, mask):
     return out
 
 
-def conv2d_bf16x3(x, weight, bias=None, activation="none", scale=1.0):
-    """Stride-1 'same' convolution of an NCHW fp32 tensor on the tcgen05 implicit-GEMM kernel with bf16x3 error
-    compensation (rpe_conv_plan_*).  Convenience / test entry: it re-packs weights and activations on every call;
-    the RAFT update operator keeps persistent plans instead (core/RAFT/core/update_tc.py)."""
-    from .core.RAFT.core.update_tc import ACT, _Planes, _pack_weight
+def conv2d_bf16x3(x, weight, bias=None, activation="none", scale=1.0, stride=1, pre=None, res=None, single_pass=False):
+    """Convolution ('same'-style padding k//2, stride 1 or 2) of an NCHW fp32 tensor on the tcgen05 implicit-GEMM kernel with
+    bf16x3 error compensation (rpe_conv_plan_*).  ``pre`` / ``res``: optional NCHW fp32 addend before the activation / residual
+    after it (out = relu(act(v) * scale + res)).  Convenience / test entry: it re-packs weights and activations on every call;
+    the RAFT trunk keeps persistent plans instead (core/RAFT/core/update_tc.py, encoder_tc.py)."""
+    from . import tc
     n, cin, H, W = x.shape
     cout, _, kh, kw = weight.shape
     _chk(x, torch.float32, "x")
-    cpad = (cin + 63) // 64 * 64
+    cpad = (cin + 15) // 16 * 16
     cout_pad = (cout + 15) // 16 * 16
-    planes = _Planes(n, H, W, cpad, x.device)
-    l = _lib.lib()
-    check(l.rpe_nchw_to_nhwc_split(_p(x), _p(planes.hi), _p(planes.lo), None, n, cin, H, W, cpad, 0, 0, 0, _stream()),
-          "rpe_nchw_to_nhwc_split")
-    w_hi, w_lo = _pack_weight(weight.float(), 0, cin, cout_pad)
+    planes = tc.Planes(n, H, W, cpad, x.device)
+    tc.nchw_to_planes(x, planes)
+    wts = tc.pack_weight(weight.float(), 0, cin, cout_pad)
+    OH, OW = (H + 2 * (kh // 2) - kh) // stride + 1, (W + 2 * (kw // 2) - kw) // stride + 1
     ld = (cout + 3) // 4 * 4
-    out = torch.zeros((n, H, W, ld), dtype=torch.float32, device=x.device)
-    d = _lib.ConvDesc()
-    for k, (a, wt) in enumerate(((planes.hi, w_hi), (planes.lo, w_hi), (planes.hi, w_lo))):
-        d.src[k].act, d.src[k].c_total, d.src[k].c_offset, d.src[k].c_count, d.src[k].weight = a.data_ptr(), cpad, 0, cpad, wt.data_ptr()
-    d.n_sources = 3
-    d.N, d.H, d.W, d.kh, d.kw, d.cout, d.cout_pad = n, H, W, kh, kw, cout, cout_pad
+    out = torch.zeros((n, OH, OW, ld), dtype=torch.float32, device=x.device)
+    nhwc = lambda t: None if t is None else torch.nn.functional.pad(t.permute(0, 2, 3, 1), (0, ld - cout)).contiguous()
     b = None if bias is None else bias.float().contiguous()
-    d.bias = 0 if b is None else b.data_ptr()
-    d.activation, d.out_scale = ACT[activation], float(scale)
-    d.out_f32, d.f32_ld, d.f32_offset = out.data_ptr(), ld, 0
-    plan = C.c_void_p()
-    check(l.rpe_conv_plan_create(C.byref(d), C.byref(plan)), "rpe_conv_plan_create")
-    try:
-        check(l.rpe_conv_plan_run(plan, _stream()), "rpe_conv_plan_run")
-        res = torch.empty((n, cout, H, W), dtype=torch.float32, device=x.device)
-        check(l.rpe_nhwc_to_nchw(_p(out), _p(res), n, cout, H, W, ld, 0, _stream()), "rpe_nhwc_to_nchw")
-        torch.cuda.current_stream().synchronize()
-    finally:
-        l.rpe_conv_plan_destroy(plan)
-    return res
+    plan = tc.ConvPlan("conv2d_bf16x3", [(planes, 0, cin, wts)], (n, H, W), kh, kw, cout, activation, bias=b, stride=stride,
+                       out_f32=out, scale=float(scale), pre=nhwc(pre), res=nhwc(res), single_pass=single_pass)
+    plan.run()
+    res_t = tc.nhwc_to_nchw(out, cout)
+    torch.cuda.current_stream().synchronize()
+    return res_t

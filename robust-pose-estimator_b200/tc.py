@@ -1,0 +1,104 @@
+"""Plumbing of the tcgen05 convolution plans (csrc/conv.cu, include/rpe_b200.h ``rpe_conv_plan_*``): NHWC bf16 split planes,
+weight packing, and a plan object that keeps every buffer it points to alive.  No arithmetic happens here."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .ops import _p, _stream, _timed, check
+
+ACT = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+
+def split_bf16(t):
+    """fp32 tensor -> (hi, lo) bf16 with hi + lo == t to 16 mantissa bits."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+def pack_weight(w, c_lo, c_hi, cout_pad):
+    """(Cout, Cin, kh, kw) fp32 -> the channel window [c_lo, c_hi) as [taps][cout_pad][c_pad64] hi / lo planes."""
+    cout, _, kh, kw = w.shape
+    cs = c_hi - c_lo
+    cpad = (cs + 63) // 64 * 64
+    out = torch.zeros((kh * kw, cout_pad, cpad), dtype=torch.float32, device=w.device)
+    out[:, :cout, :cs] = w[:, c_lo:c_hi].permute(2, 3, 0, 1).reshape(kh * kw, cout, cs)
+    return split_bf16(out)
+
+
+class Planes:
+    """NHWC bf16 split planes (hi, lo) of shape (N, H, W, C); channels are zero-initialised so padded channels read as 0."""
+
+    def __init__(self, n, h, w, c, device):
+        self.hi = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
+        self.lo = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
+        self.c = c
+        self.shape = (n, h, w, c)
+
+    def float(self):
+        return self.hi.float() + self.lo.float()
+
+
+class ConvPlan:
+    """One convolution bound to its input / output buffers.  ``inputs``: [(Planes, c_offset, c_count, (w_hi, w_lo))]."""
+
+    def __init__(self, name, inputs, dims, kh, kw, cout, act="none", bias=None, stride=1, out_f32=None, f32_off=0, out_planes=None,
+                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False):
+        n, h, w = dims
+        cout_pad = (cout + 15) // 16 * 16
+        d = _lib.ConvDesc()
+        self._keep = [bias, pre, res, out_f32, out_planes]
+        for k, (planes, c_off, c_cnt, (w_hi, w_lo)) in enumerate(inputs):
+            assert planes.shape[:3] == (n, h, w), f"{name}: source {k} has shape {planes.shape}, expected {(n, h, w)}"
+            assert w_hi.shape[1] == cout_pad, f"{name}: weight packed for cout_pad {w_hi.shape[1]}, plan needs {cout_pad}"
+            s = d.src[k]
+            s.act_hi, s.act_lo = planes.hi.data_ptr(), (0 if single_pass else planes.lo.data_ptr())
+            s.c_total, s.c_offset, s.c_count = planes.c, c_off, (c_cnt + 15) // 16 * 16
+            s.w_hi, s.w_lo, s.w_cstride = w_hi.data_ptr(), (0 if single_pass else w_lo.data_ptr()), w_hi.shape[-1]
+            self._keep += [planes, w_hi, w_lo]
+        d.n_sources = len(inputs)
+        d.N, d.H, d.W = n, h, w
+        d.kh, d.kw, d.stride, d.cout, d.cout_pad = kh, kw, stride, cout, cout_pad
+        d.bias = 0 if bias is None else bias.data_ptr()
+        if pre is not None:
+            d.pre, d.pre_ld = pre.data_ptr(), pre.shape[-1]
+        if res is not None:
+            d.res, d.res_ld = res.data_ptr(), res.shape[-1]
+        d.activation, d.out_scale = ACT[act], scale
+        if out_f32 is not None:
+            d.out_f32, d.f32_ld, d.f32_offset = out_f32.data_ptr(), out_f32.shape[-1], f32_off
+        if out_planes is not None:
+            d.out_hi, d.bf_ld, d.bf_offset = out_planes.hi.data_ptr(), out_planes.c, bf_off
+            d.out_lo = 0 if single_pass else out_planes.lo.data_ptr()
+        self.name = name
+        self._h = C.c_void_p()
+        check(_lib.lib().rpe_conv_plan_create(C.byref(d), C.byref(self._h)), f"rpe_conv_plan_create({name})")
+        self.flops = float(_lib.lib().rpe_conv_plan_flops(self._h))
+
+    def run(self, stage="conv_tc"):
+        with _timed(stage, self.flops):
+            check(_lib.lib().rpe_conv_plan_run(self._h, _stream()), f"rpe_conv_plan_run({self.name})")
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().rpe_conv_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+def nchw_to_planes(x, planes, c_off=0, f32=None, f32_off=0):
+    """NCHW fp32 -> split planes at channel offset c_off (+ optional fp32 NHWC copy)."""
+    n, c, h, w = x.shape
+    check(_lib.lib().rpe_nchw_to_nhwc_split(_p(x), _p(planes.hi), _p(planes.lo), _p(f32), n, c, h, w, planes.c, c_off,
+                                            0 if f32 is None else f32.shape[-1], f32_off, _stream()), "rpe_nchw_to_nhwc_split")
+
+
+def nhwc_to_nchw(x, c, c_off=0):
+    """fp32 NHWC (n,h,w,ld) channel window -> NCHW fp32."""
+    n, h, w, ld = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().rpe_nhwc_to_nchw(_p(x), _p(out), n, c, h, w, ld, c_off, _stream()), "rpe_nhwc_to_nchw")
+    return out

@@ -50,6 +50,44 @@ def test_conv_bf16x3_vs_torch_fp32(ops, cin, cout, kh, kw, H, W, act):
     assert err < 3e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", [
+    (64, 96, 3, 2, 64, 80),                 # encoder layer2 entry (3x3 / 2)
+    (64, 96, 1, 2, 64, 80),                 # its 1x1 / 2 skip projection
+    (96, 128, 3, 2, 32, 40),                # layer3 entry; 96 channels = one full + one half K block
+    (96, 96, 3, 1, 40, 48),                 # layer2 body
+    (160, 64, 1, 1, 64, 80),                # im2col'ed 7x7 / 2 stem (147 -> 160 channels)
+])
+def test_conv_strided_and_partial_blocks(ops, cin, cout, k, stride, H, W):
+    n = 2
+    x = dev(det_uniform((n, cin, H, W), 111, -2.0, 2.0))
+    w = dev(det_uniform((cout, cin, k, k), 112, -1.0, 1.0)) * (1.0 / np.sqrt(cin * k * k))
+    b = dev(det_uniform((cout,), 113, -0.5, 0.5))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=k // 2).float()
+    got = ops.conv2d_bf16x3(x, w, b, stride=stride)
+    assert got.shape == ref.shape
+    err = (got - ref).abs().max().item()
+    print(f"conv {cin}->{cout} {k}x{k}/{stride}: max abs err {err:.2e}")
+    assert err < 3e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv_addend_residual_and_single_pass(ops):
+    n, cin, cout, H, W = 2, 128, 128, 32, 40
+    x = dev(det_uniform((n, cin, H, W), 121, -2.0, 2.0))
+    w = dev(det_uniform((cout, cin, 3, 3), 122, -1.0, 1.0)) * (1.0 / np.sqrt(cin * 9))
+    b = dev(det_uniform((cout,), 123, -0.5, 0.5))
+    pre = dev(det_uniform((n, cout, H, W), 124, -1.0, 1.0))
+    res = dev(det_uniform((n, cout, H, W), 125, -1.0, 1.0))
+    conv = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    ref = torch.relu(torch.tanh(conv + pre.double()) + res.double()).float()
+    got = ops.conv2d_bf16x3(x, w, b, activation="tanh", pre=pre, res=res)
+    assert (got - ref).abs().max().item() < 3e-5
+    # single-pass bf16 (no compensation): only bf16-level agreement is expected
+    got1 = ops.conv2d_bf16x3(x, w, b, single_pass=True)
+    err1 = (got1 - conv.float()).abs().max().item()
+    print(f"single-pass bf16 conv: max abs err {err1:.2e}")
+    assert 1e-5 < err1 < 5e-2
+
+
 def test_update_operator_vs_torch_trunk(ops):
     """12 GRU iterations on the tensor-core path vs the torch fp32 trunk, trained weights, real feature maps."""
     if not os.path.isfile(CKPT) or not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz")):
