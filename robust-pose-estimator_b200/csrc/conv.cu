@@ -33,8 +33,9 @@ constexpr int kCvThreads = 256;
 constexpr int kCvMaxSrc = 4;
 constexpr int kCvMaxBN = 256;
 constexpr int kCvMaxAStages = 4, kCvMaxBStages = 8;
-constexpr int kCvSmemData = 216 * 1024;               // budget for the two rings
-constexpr int kCvSmem = kCvSmemData + 1024 + 512;     // + alignment slack + barriers
+constexpr int kCvSmemData = 214 * 1024;               // budget for the two rings
+constexpr int kCvMaxCout = 1024;                      // bias staged in shared memory
+constexpr int kCvSmem = kCvSmemData + 1024 + 512 + kCvMaxCout * 4;     // + alignment slack + barriers + bias
 
 struct alignas(64) ConvParams {
     CUtensorMap amap[kCvMaxSrc][2];
@@ -84,11 +85,79 @@ __device__ __forceinline__ uint64_t cv_sw128_desc(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 
-__device__ __forceinline__ float cv_activate(float v, int act) {
-    if (act == 1) return fmaxf(v, 0.0f);
-    if (act == 2) return 1.0f / (1.0f + expf(-v));
-    if (act == 3) return tanhf(v);
+template <int ACT>
+__device__ __forceinline__ float cv_activate(float v) {
+    if (ACT == 1) return fmaxf(v, 0.0f);
+    if (ACT == 2) return 1.0f / (1.0f + expf(-v));
+    if (ACT == 3) return tanhf(v);
     return v;
+}
+
+__device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, size_t o, const float *v) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2bfloat16_rn(v[k]);
+        l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k]));
+    }
+    *reinterpret_cast<uint2 *>(P.out_hi + o) = *reinterpret_cast<uint2 *>(h);
+    if (P.out_lo) *reinterpret_cast<uint2 *>(P.out_lo + o) = *reinterpret_cast<uint2 *>(l);
+}
+
+__device__ __forceinline__ float cv_activate_rt(float v, int act) {
+    return act == 1 ? cv_activate<1>(v) : act == 2 ? cv_activate<2>(v) : act == 3 ? cv_activate<3>(v) : v;
+}
+
+// Ragged tail (1..3 channels) of an output-channel count that is not a multiple of 4.
+__device__ __noinline__ void cv_epilogue_tail(const ConvParams &P, int act, float a0, float a1, float a2, const float *sbias, int co,
+                                              size_t pix) {
+    const float acc[3] = {a0, a1, a2};
+    for (int k = 0; k < 3 && co + k < P.cout; ++k) {
+        float r = acc[k] + sbias[co + k];
+        if (P.pre) r += __ldg(P.pre + pix * P.pre_ld + co + k);
+        r = cv_activate_rt(r, act) * P.scale;
+        if (P.res) r = fmaxf(r + __ldg(P.res + pix * P.res_ld + co + k), 0.0f);
+        if (P.out_f32) P.out_f32[pix * P.f32_ld + P.f32_off + co + k] = r;
+        if (P.out_hi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(r);
+            P.out_hi[pix * P.bf_ld + P.bf_off + co + k] = h;
+            if (P.out_lo) P.out_lo[pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(r - __bfloat162float(h));
+        }
+    }
+}
+
+// One group of 4 consecutive output channels of one pixel: bias / addend / activation / scale / residual / stores.
+template <int ACT>
+__device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const uint32_t *acc4, const float *sbias, int co, size_t pix) {
+    if (co >= P.cout) return;
+    float o[4];
+    if (co + 3 < P.cout) {
+        const float4 b = *reinterpret_cast<const float4 *>(sbias + co);
+        o[0] = __uint_as_float(acc4[0]) + b.x, o[1] = __uint_as_float(acc4[1]) + b.y;
+        o[2] = __uint_as_float(acc4[2]) + b.z, o[3] = __uint_as_float(acc4[3]) + b.w;
+        if (P.pre) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
+            o[0] += a.x, o[1] += a.y, o[2] += a.z, o[3] += a.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = cv_activate<ACT>(o[k]) * P.scale;
+        if (P.res) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
+            o[0] = fmaxf(o[0] + a.x, 0.0f), o[1] = fmaxf(o[1] + a.y, 0.0f);
+            o[2] = fmaxf(o[2] + a.z, 0.0f), o[3] = fmaxf(o[3] + a.w, 0.0f);
+        }
+        if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
+        if (P.out_hi) cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
+    } else {                                           // ragged tail of a channel count that is not a multiple of 4
+        cv_epilogue_tail(P, ACT, __uint_as_float(acc4[0]), __uint_as_float(acc4[1]), __uint_as_float(acc4[2]), sbias, co, pix);
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ void cv_epilogue_chunk(const ConvParams &P, const uint32_t *v, int cols, const float *sbias, int co0, size_t pix) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+        if (j < cols) cv_epilogue_group<ACT>(P, v + j, sbias, co0 + j, pix);
 }
 
 struct CvTile {
@@ -111,7 +180,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
-    uint8_t *sB = sA + (size_t)P.n_a_stages * P.a_stage_bytes;
+    uint8_t *sB = sA + (size_t)P.n_a_stages * P.a_stage_bytes;      // weight ring: n_b_stages entries of one plane tile
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kCvSmemData);
     uint64_t *a_full = bars;
     uint64_t *a_empty = a_full + kCvMaxAStages;
@@ -120,6 +189,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
     uint64_t *tmem_full = b_empty + kCvMaxBStages;
     uint64_t *tmem_empty = tmem_full + kCvAcc;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + kCvAcc);
+    float *sbias = reinterpret_cast<float *>(smem + kCvSmemData + 512);
+    for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = P.N * P.tiles_min * P.tiles_maj * P.n_blocks;
@@ -189,13 +260,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                     for (int cb = 0; cb < P.cblocks[s]; ++cb)
                         for (int tm = 0; tm < P.kmin; ++tm)
                             for (int tj = 0; tj < P.kmaj; ++tj) {
-                                mbar_wait(&b_empty[stage], phase ^ 1);
-                                mbar_expect_tx(&b_full[stage], P.b_plane_bytes * P.n_planes);
                                 const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
-                                uint8_t *dst = sB + (size_t)stage * P.b_stage_bytes;
-                                for (int p = 0; p < P.n_planes; ++p)
-                                    tma_load_3d(dst + p * P.b_plane_bytes, &P.wmap[s][p], &b_full[stage], cb * kCvBK, t.nb * P.bn, tap);
-                                if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                                for (int p = 0; p < P.n_planes; ++p) {          // one ring entry per plane tile
+                                    mbar_wait(&b_empty[stage], phase ^ 1);
+                                    mbar_expect_tx(&b_full[stage], P.b_plane_bytes);
+                                    tma_load_3d(sB + (size_t)stage * P.b_plane_bytes, &P.wmap[s][p], &b_full[stage], cb * kCvBK, t.nb * P.bn, tap);
+                                    if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                                }
                             }
             }
         }
@@ -224,15 +295,20 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                                 mbar_wait(&b_full[sb], pb);
                                 tcgen05_fence_after();
                                 const uint32_t a0 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) + (P.reuse ? (uint32_t)tj * 1024u : 0u);
-                                const uint32_t b0 = smem_u32(sB + (size_t)sb * P.b_stage_bytes);
-                                const uint64_t da_hi = cv_sw128_desc(a0), db_hi = cv_sw128_desc(b0);
+                                const uint64_t da_hi = cv_sw128_desc(a0);
+                                const uint64_t db_hi = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
                                 for (int k = 0; k < ksteps; ++k) {
                                     umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
                                     accumulate = 1;
                                 }
                                 if (P.n_planes == 2) {
-                                    const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes), db_lo = cv_sw128_desc(b0 + P.b_plane_bytes);
+                                    const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes);
                                     for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                    umma_commit(&b_empty[sb]);
+                                    if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
+                                    mbar_wait(&b_full[sb], pb);
+                                    tcgen05_fence_after();
+                                    const uint64_t db_lo = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
                                     for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
                                 }
                                 umma_commit(&b_empty[sb]);
@@ -287,59 +363,11 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                 }
                 if (!inside) continue;
                 const int co0 = t.nb * P.bn + c * 16;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (j >= cols) break;
-                    const int co = co0 + j;
-                    if (co >= P.cout) break;
-                    const bool full = co + 3 < P.cout;
-                    float o[4];
-                    float add[4] = {0.0f, 0.0f, 0.0f, 0.0f}, rs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                    if (full) {
-                        if (P.pre) {
-                            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
-                            add[0] = a.x, add[1] = a.y, add[2] = a.z, add[3] = a.w;
-                        }
-                        if (P.res) {
-                            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
-                            rs[0] = a.x, rs[1] = a.y, rs[2] = a.z, rs[3] = a.w;
-                        }
-                    } else {
-                        for (int k = 0; k < 4 && co + k < P.cout; ++k) {
-                            if (P.pre) add[k] = __ldg(P.pre + pix * P.pre_ld + co + k);
-                            if (P.res) rs[k] = __ldg(P.res + pix * P.res_ld + co + k);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float b = (P.bias != nullptr && co + k < P.cout) ? __ldg(P.bias + co + k) : 0.0f;
-                        float r = cv_activate(__uint_as_float(v[j + k]) + b + add[k], P.act) * P.scale;
-                        if (P.res) r = fmaxf(r + rs[k], 0.0f);
-                        o[k] = r;
-                    }
-                    if (full) {
-                        if (P.out_f32)
-                            *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
-                        if (P.out_hi) {
-                            __nv_bfloat16 h[4], l[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                h[k] = __float2bfloat16_rn(o[k]);
-                                l[k] = __float2bfloat16_rn(o[k] - __bfloat162float(h[k]));
-                            }
-                            *reinterpret_cast<uint2 *>(P.out_hi + pix * P.bf_ld + P.bf_off + co) = *reinterpret_cast<uint2 *>(h);
-                            if (P.out_lo) *reinterpret_cast<uint2 *>(P.out_lo + pix * P.bf_ld + P.bf_off + co) = *reinterpret_cast<uint2 *>(l);
-                        }
-                    } else {
-                        for (int k = 0; k < 4 && co + k < P.cout; ++k) {
-                            if (P.out_f32) P.out_f32[pix * P.f32_ld + P.f32_off + co + k] = o[k];
-                            if (P.out_hi) {
-                                const __nv_bfloat16 h = __float2bfloat16_rn(o[k]);
-                                P.out_hi[pix * P.bf_ld + P.bf_off + co + k] = h;
-                                if (P.out_lo) P.out_lo[pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(o[k] - __bfloat162float(h));
-                            }
-                        }
-                    }
+                switch (P.act) {
+                    case 1: cv_epilogue_chunk<1>(P, v, cols, sbias, co0, pix); break;
+                    case 2: cv_epilogue_chunk<2>(P, v, cols, sbias, co0, pix); break;
+                    case 3: cv_epilogue_chunk<3>(P, v, cols, sbias, co0, pix); break;
+                    default: cv_epilogue_chunk<0>(P, v, cols, sbias, co0, pix); break;
                 }
             }
             if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
@@ -382,7 +410,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->kh < 1 || d->kw < 1 || !(d->kh & 1) || !(d->kw & 1)) return RPE_ERR_INVALID_ARG;
     const int stride = d->stride <= 0 ? 1 : d->stride;
     if (stride != 1 && stride != 2) return RPE_ERR_INVALID_ARG;
-    if (d->cout <= 0 || d->cout_pad < d->cout || d->cout_pad % 16 != 0) return RPE_ERR_INVALID_ARG;
+    if (d->cout <= 0 || d->cout_pad < d->cout || d->cout_pad % 16 != 0 || d->cout_pad > kCvMaxCout) return RPE_ERR_INVALID_ARG;
     if (!d->out_f32 && !d->out_hi) return RPE_ERR_INVALID_ARG;
     if (d->out_lo && !d->out_hi) return RPE_ERR_INVALID_ARG;
     if (d->out_f32 && ((d->f32_ld % 4) || (d->f32_offset % 4) || !aligned16(d->out_f32))) return RPE_ERR_ALIGNMENT;
@@ -420,14 +448,11 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.a_stage_bytes = p.a_plane_bytes * p.n_planes;
     p.b_plane_bytes = (uint32_t)bn * 128;
     p.b_stage_bytes = p.b_plane_bytes * p.n_planes;
-    // ring depths: at least two stages each, activations up to 3 slabs, the rest goes to the weight ring
+    // ring depths: two activation stages (three when the weight tiles are small), every remaining byte goes to the weight
+    // ring, whose entries are single plane tiles so that many small loads are in flight
     p.n_a_stages = 2;
-    p.n_b_stages = (int)((kCvSmemData - 2 * (size_t)p.a_stage_bytes) / p.b_stage_bytes);
-    if (p.n_b_stages > 4 && p.n_a_stages < kCvMaxAStages &&
-        (size_t)(p.n_a_stages + 1) * p.a_stage_bytes + 4 * (size_t)p.b_stage_bytes <= (size_t)kCvSmemData) {
-        p.n_a_stages += 1;
-        p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_stage_bytes);
-    }
+    if (3 * (size_t)p.a_stage_bytes + 6 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
+    p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
     if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
     if (p.n_b_stages < 2) {
         delete pl;

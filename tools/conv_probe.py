@@ -36,7 +36,11 @@ def main():
     dev = torch.device("cuda")
     torch.manual_seed(0)
     single = "--single" in sys.argv
+    only = [a[7:] for a in sys.argv if a.startswith("--only=")]
+    reps = 1 if "--once" in sys.argv else 20
     for name, n, h, w, cins, cout, kh, kw, stride in SHAPES:
+        if only and not any(o in name for o in only):
+            continue
         cout_pad = (cout + 15) // 16 * 16
         srcs = []
         for cin in cins:
@@ -49,10 +53,9 @@ def main():
         outp = tc.Planes(n, oh, ow, cout_pad, dev)
         plan = tc.ConvPlan(name, srcs, (n, h, w), kh, kw, cout, "relu", bias=torch.zeros(cout, device=dev), stride=stride,
                            out_planes=outp, single_pass=single)
-        for _ in range(3):
+        for _ in range(0 if reps == 1 else 3):
             plan.run()
         torch.cuda.synchronize()
-        reps = 20
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
