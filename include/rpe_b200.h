@@ -241,6 +241,19 @@ int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi
 int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *out_lo, int out_ld, int out_off,
                  long long npix, int mode, void *stream);
 
+/* Encoder companions (reference: /root/reference/core/RAFT/core/extractor.py:118-192, raft.py:82-83).
+ * rpe_im2col7s2_split: 7x7 / stride 2 / pad 3 windows of the normalised image 2*(v/255)-1 as the K axis of a 1x1 convolution,
+ *   k = ky*24 + kx*3 + c (168 of `ld` channels); img NCHW fp32 (n,3,H,W) -> bf16 split planes (n, H/2, W/2, ld).
+ * rpe_instnorm_stats: InstanceNorm2d statistics (biased variance) of an NHWC fp32 tensor (n,HW,C): stats (n,C,2) = mean, rstd.
+ * rpe_norm_act_split: y = [relu]((a - mean_a) * rstd_a), optionally y = relu(y + (b - mean_b) * rstd_b) (stats may be NULL =
+ *   identity); writes fp32 NHWC and / or bf16 split planes with channel pitch ld. */
+int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream);
+size_t rpe_instnorm_workspace_bytes(int n, int C);
+int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float eps, void *workspace, size_t workspace_bytes,
+                       void *stream);
+int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
+                       void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

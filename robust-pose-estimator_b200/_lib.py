@@ -69,6 +69,10 @@ SIGNATURES = {
     "rpe_nchw_to_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_flow_step": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_im2col7s2_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "rpe_instnorm_workspace_bytes": (_Z, [_I, _I]),
+    "rpe_instnorm_stats": (_I, [_P, _P, _I, _I, _I, _F, _P, _Z, _P]),
+    "rpe_norm_act_split": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_gru_gate": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_longlong, _I, _P]),
 }
 

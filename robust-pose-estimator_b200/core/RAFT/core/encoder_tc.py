@@ -1,0 +1,186 @@
+"""RAFT feature / context encoders on the tcgen05 convolution kernels (csrc/conv.cu, csrc/encoder_ops.cu).
+
+Same arithmetic graph as ``extractor.encoder_forward`` (reference: /root/reference/core/RAFT/core/extractor.py:118-192
+``BasicEncoder``, :6-56 ``ResidualBlock``) with every convolution evaluated as an error-compensated bf16x3 implicit GEMM:
+  * the 7x7 / 2 stem is a 1x1 convolution over an im2col of the normalised image (rpe_im2col7s2_split);
+  * stride-2 convolutions read their input through strided TMA boxes;
+  * fnet (InstanceNorm2d): convolution -> raw fp32, rpe_instnorm_stats, rpe_norm_act_split (normalise / relu / residual);
+  * cnet (eval-mode BatchNorm2d): the affine map is folded into the convolution weights and the relu / residual run in the
+    convolution epilogue.
+All buffers and plans are created once per input shape."""
+import torch
+
+from .... import _lib
+from ....ops import _p, _stream, _timed, check
+from ....tc import ConvPlan, Planes, nhwc_to_nchw, pack_weight
+
+_STAGES = (("layer1", 64, 1), ("layer2", 96, 2), ("layer3", 128, 2))
+STEM_K = 168            # 7 filter rows x 24 (21 real taps*channels + 3 zeros)
+STEM_LD = 176
+
+
+def stem_planes(images, out=None):
+    """im2col of the 7x7 / 2 stem for NCHW fp32 images in 0..255 -> split planes (n, H/2, W/2, STEM_LD)."""
+    n, _, H, W = images.shape
+    if out is None:
+        out = Planes(n, (H - 1) // 2 + 1, (W - 1) // 2 + 1, STEM_LD, images.device)
+    with _timed("im2col_stem", n):
+        check(_lib.lib().rpe_im2col7s2_split(_p(images), _p(out.hi), _p(out.lo), n, H, W, STEM_LD, _stream()), "rpe_im2col7s2_split")
+    return out
+
+
+class EncoderTC:
+    def __init__(self, weights, prefix, norm, heads):
+        """weights: flat {key: tensor} table; norm 'instance' | 'batch'; heads: [(c_lo, c_hi, activation)] slices of the
+        final 1x1 convolution (fnet: one linear head of 256 channels; cnet: tanh / relu halves)."""
+        self.W, self.prefix, self.norm, self.heads = weights, prefix, norm, heads
+        self._packed = {}
+        self._shapes = {}
+
+    # ---- weights ---------------------------------------------------------------------------------------
+    def _folded(self, conv, bn):
+        """(weight, bias) of `conv` with the eval-mode BatchNorm `bn` folded in (identity for fnet)."""
+        W, p = self.W, self.prefix
+        w, b = W[p + conv + ".weight"].float(), W[p + conv + ".bias"].float()
+        if self.norm == "batch":
+            s = W[p + bn + ".weight"].float() / torch.sqrt(W[p + bn + ".running_var"].float() + 1e-5)
+            w = w * s[:, None, None, None]
+            b = (b - W[p + bn + ".running_mean"].float()) * s + W[p + bn + ".bias"].float()
+        return w, b
+
+    def _wb(self, conv, bn, c_lo=None, c_hi=None):
+        key = (conv, c_lo, c_hi)
+        if key not in self._packed:
+            w, b = self._folded(conv, bn) if bn else (self.W[self.prefix + conv + ".weight"].float(), self.W[self.prefix + conv + ".bias"].float())
+            if conv == "conv1":                                   # stem: K = ky*24 + kx*3 + c
+                wk = torch.zeros((w.shape[0], 7, 24), dtype=torch.float32, device=w.device)
+                wk[:, :, :21] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 7, 21)
+                w = wk.reshape(w.shape[0], STEM_K, 1, 1)
+            if c_lo is not None:
+                w, b = w[c_lo:c_hi], b[c_lo:c_hi]
+            cout = w.shape[0]
+            self._packed[key] = (pack_weight(w, 0, w.shape[1], (cout + 15) // 16 * 16), b.contiguous())
+        return self._packed[key]
+
+    # ---- per-shape state -------------------------------------------------------------------------------
+    def _state(self, n, H, W, device, shared_col=None):
+        key = (n, H, W, device.index, None if shared_col is None else shared_col.hi.data_ptr())
+        st = self._shapes.get(key)
+        if st is not None:
+            return st
+        inst = self.norm == "instance"
+        f32 = lambda h, w, c: torch.zeros((n, h, w, c), dtype=torch.float32, device=device)
+        st = {"steps": [], "keep": []}
+        h, w = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        l = _lib.lib()
+        ws = torch.empty(l.rpe_instnorm_workspace_bytes(n, 128), dtype=torch.uint8, device=device) if inst else None
+        st["keep"].append(ws)
+
+        def stats_of(raw, c, hw):
+            s = torch.empty((n, c, 2), dtype=torch.float32, device=device)
+            st["steps"].append(("stats", raw, s, hw, c, ws))
+            return s
+
+        def norm_act(a, sa, relu_a, b, sb, out, planes, hw, c):
+            st["steps"].append(("norm", a, sa, relu_a, b, sb, out, planes, hw, c))
+
+        def conv(name, bn, src, dims, k, cout, act, stride=1, out_f32=None, out_planes=None, res=None):
+            (wts, bias) = self._wb(name, bn)
+            cin = src.c if name != "conv1" else STEM_K
+            plan = ConvPlan(self.prefix + name, [(src, 0, min(cin, wts[0].shape[-1]), wts)], dims, k, k, cout, act, bias=bias, stride=stride,
+                            out_f32=out_f32, out_planes=out_planes, res=res)
+            st["steps"].append(("conv", plan))
+            return plan
+
+        # ---- stem
+        col = shared_col if shared_col is not None else Planes(n, h, w, STEM_LD, device)
+        st["col"] = col
+        x = f32(h, w, 64)
+        xp = Planes(n, h, w, 64, device)
+        raw = f32(h, w, 64)
+        if inst:
+            conv("conv1", None, col, (n, h, w), 1, 64, "none", out_f32=raw)
+            s = stats_of(raw, 64, h * w)
+            norm_act(raw, s, 1, None, None, x, xp, h * w, 64)
+        else:
+            conv("conv1", "norm1", col, (n, h, w), 1, 64, "relu", out_f32=x, out_planes=xp)
+        cin = 64
+        for layer, dim, stride in _STAGES:
+            for blk in (0, 1):
+                p = f"{layer}.{blk}."
+                s_ = stride if blk == 0 else 1
+                ih, iw = h, w
+                if s_ != 1:
+                    h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+                hw = h * w
+                yp = Planes(n, h, w, dim, device)
+                if s_ != 1 or raw.shape[-1] != dim:
+                    raw = f32(h, w, dim)
+                x_in, xp_in = x, xp
+                if s_ != 1:
+                    x, xp = f32(h, w, dim), Planes(n, h, w, dim, device)
+                if inst:
+                    conv(p + "conv1", None, xp_in, (n, ih, iw), 3, dim, "none", stride=s_, out_f32=raw)
+                    s1 = stats_of(raw, dim, hw)
+                    norm_act(raw, s1, 1, None, None, None, yp, hw, dim)
+                    raw2 = f32(h, w, dim) if s_ != 1 else raw
+                    if s_ != 1:                                     # projection of the skip path first (raw2 is reused below)
+                        rawd = f32(h, w, dim)
+                        conv(p + "downsample.0", None, xp_in, (n, ih, iw), 1, dim, "none", stride=s_, out_f32=rawd)
+                        sd = stats_of(rawd, dim, hw)
+                    conv(p + "conv2", None, yp, (n, h, w), 3, dim, "none", out_f32=raw2)
+                    s2 = stats_of(raw2, dim, hw)
+                    if s_ != 1:
+                        norm_act(raw2, s2, 1, rawd, sd, x, xp, hw, dim)
+                    else:
+                        norm_act(raw2, s2, 1, x_in, None, x, xp, hw, dim)
+                else:
+                    res = x_in
+                    if s_ != 1:
+                        res = f32(h, w, dim)
+                        conv(p + "downsample.0", p + "downsample.1", xp_in, (n, ih, iw), 1, dim, "none", stride=s_, out_f32=res)
+                    conv(p + "conv1", p + "norm1", xp_in, (n, ih, iw), 3, dim, "relu", stride=s_, out_planes=yp)
+                    conv(p + "conv2", p + "norm2", yp, (n, h, w), 3, dim, "relu", out_f32=x, out_planes=xp, res=res)
+                cin = dim
+        # ---- output heads (slices of the final 1x1 convolution)
+        outs = []
+        for c_lo, c_hi, act in self.heads:
+            o = f32(h, w, c_hi - c_lo)
+            (wts, bias) = self._wb("conv2", None, c_lo, c_hi)
+            plan = ConvPlan(self.prefix + "conv2", [(xp, 0, 128, wts)], (n, h, w), 1, 1, c_hi - c_lo, act, bias=bias, out_f32=o)
+            st["steps"].append(("conv", plan))
+            outs.append(o)
+        st["outs"] = outs
+        st["out_hw"] = (h, w)
+        self._shapes[key] = st
+        return st
+
+    # ---- execution ---------------------------------------------------------------------------------------
+    def forward(self, images, col=None):
+        """images (n,3,H,W) fp32 in 0..255 -> list of fp32 NHWC outputs, one per head (buffers reused by the next call).
+        ``col``: already filled im2col planes from ``stem_planes`` whose first n images are these images (the context encoder
+        reads the same left images as the feature encoder); the plans are then bound to that buffer."""
+        n, _, H, W = images.shape
+        st = self._state(n, H, W, images.device, col)
+        l = _lib.lib()
+        s = _stream()
+        if col is None:
+            stem_planes(images, st["col"])
+        for step in st["steps"]:
+            kind = step[0]
+            if kind == "conv":
+                step[1].run("conv_tc_enc")
+            elif kind == "stats":
+                _, raw, stats, hw, c, ws = step
+                with _timed("instnorm_stats", n):
+                    check(l.rpe_instnorm_stats(_p(raw), _p(stats), n, hw, c, 1e-5, _p(ws), ws.numel(), s), "rpe_instnorm_stats")
+            else:
+                _, a, sa, relu_a, b, sb, out, planes, hw, c = step
+                with _timed("norm_act", n):
+                    check(l.rpe_norm_act_split(_p(a), _p(sa), relu_a, _p(b), _p(sb), _p(out), _p(None if planes is None else planes.hi),
+                                               _p(None if planes is None else planes.lo), 0 if planes is None else planes.c, n, hw, c, s),
+                          "rpe_norm_act_split")
+        return st["outs"]
+
+    def forward_nchw(self, images, col=None):
+        return [nhwc_to_nchw(o, o.shape[-1]) for o in self.forward(images, col)]

@@ -6,8 +6,8 @@ do not change the consumed result:
   * only the final flow prediction is up-sampled unless ``all_predictions=True`` (the pose path
     reads ``flow_predictions[-1]`` only, pose_net.py:66-67);
   * ``precision``: "fp32" (cuDNN fp32, TF32 off, correlation TF32x3 split) |
-    "bf16x3" (parity-grade fast mode: encoders cuDNN fp32, the 12-iteration update operator on the tcgen05
-    bf16x3 convolution kernels, update_tc.py) | "tf32" | "bf16" / "fp16" (autocast like the reference's CUDA run,
+    "bf16x3" (parity-grade fast mode: encoders and the 12-iteration update operator on the tcgen05 bf16x3
+    convolution kernels, encoder_tc.py / update_tc.py; no cuDNN on the path) | "tf32" | "bf16" / "fp16" (autocast like the reference's CUDA run,
     raft.py:92,100,117)."""
 import contextlib
 
@@ -19,6 +19,7 @@ from ...utils.param_tree import build_tree
 from .corr import CorrBlock
 from .extractor import encoder_entries, encoder_forward
 from .update import prepare_update_weights, update_entries, update_forward
+from .encoder_tc import EncoderTC, stem_planes
 from .update_tc import UpdateTC
 
 _AUTOCAST = {"bf16": torch.bfloat16, "fp16": torch.float16}
@@ -44,14 +45,16 @@ class RAFT(nn.Module):
         self.fnet, self.cnet, self.update_block = tree.fnet, tree.cnet, tree.update_block
         self._W = None
         self._tc = None
+        self._enc_tc = None
+        self._col = {}
 
     # ---- weight table ------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
-        self._W = self._tc = None
+        self._W = self._tc = self._enc_tc = None
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._W = self._tc = None
+        self._W = self._tc = self._enc_tc = None
         return super().load_state_dict(*a, **k)
 
     def weights(self):
@@ -75,14 +78,42 @@ class RAFT(nn.Module):
         stack.enter_context(torch.autocast("cuda", dtype=dt) if dt is not None else torch.autocast("cuda", enabled=False))
         return stack
 
+    def _encoders(self):
+        if self._enc_tc is None:
+            W = self.weights()
+            self._enc_tc = (EncoderTC(W, "fnet.", "instance", [(0, 256, "none")]),
+                            EncoderTC(W, "cnet.", "batch", [(0, self.hidden_dim, "tanh"), (self.hidden_dim, 256, "relu")]))
+        return self._enc_tc
+
+    def encode(self, limg, rimg):
+        """fnet over the left and right images, cnet over the left ones -> (fmap_l, fmap_r, net, inp), NCHW float32.
+        On the tensor-core path the stem im2col of the left images is computed once and shared by both encoders."""
+        C = limg.shape[0]
+        imgs = torch.cat((limg, rimg), 0).float().contiguous()
+        if self.precision != "bf16x3":
+            f = self.features(imgs)
+            net, inp = self.context(limg)
+            return f[:C], f[C:], net, inp
+        fe, ce = self._encoders()
+        key = tuple(imgs.shape) + (imgs.device.index,)
+        col = self._col[key] = stem_planes(imgs, self._col.get(key))
+        f = fe.forward_nchw(imgs, col)[0]
+        net, inp = ce.forward_nchw(imgs[:C], col)
+        return f[:C], f[C:], net, inp
+
     def features(self, images):
         """fnet over (N,3,H,W) images in 0..255 -> (N,256,H/8,W/8) float32."""
+        if self.precision == "bf16x3":
+            return self._encoders()[0].forward_nchw(images.float().contiguous())[0]
         x = (2 * (images / 255.0) - 1.0).contiguous()
         with self._ctx():
             return encoder_forward(x, self.weights(), "fnet.", "instance").float()
 
     def context(self, images):
         """cnet -> (net, inp) = (tanh, relu) halves, each (N,128,H/8,W/8)."""
+        if self.precision == "bf16x3":
+            net, inp = self._encoders()[1].forward_nchw(images.float().contiguous())
+            return net, inp
         x = (2 * (images / 255.0) - 1.0).contiguous()
         with self._ctx():
             c = encoder_forward(x, self.weights(), "cnet.", "batch")

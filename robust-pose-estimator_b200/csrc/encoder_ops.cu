@@ -1,0 +1,211 @@
+// Element-wise / reduction companions of the tcgen05 convolution path of the RAFT encoders
+// (reference: /root/reference/core/RAFT/core/extractor.py:118-192 BasicEncoder, :6-56 ResidualBlock; input scaling
+// core/RAFT/core/raft.py:82-83).  All activations NHWC; "split" = bf16 hi/lo planes (conv.cu).
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace rpe {
+
+__device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        h[k] = __float2bfloat16_rn(v[k]);
+        l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k]));
+    }
+    hi = *reinterpret_cast<uint2 *>(h);
+    lo = *reinterpret_cast<uint2 *>(l);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem im2col: 7x7 / stride 2 / pad 3 windows of the normalised image 2*(v/255)-1 (raft.py:82-83), written as the K axis of
+// a 1x1 convolution: k = ky*24 + kx*3 + c (21 real values per filter row, padded to 24 so that every row is three aligned
+// 16-byte stores per plane).  img NCHW fp32 (n,3,H,W) -> planes (n, H/2, W/2, ld).  One thread = one (pixel, ky).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ hi,
+                                                        __nv_bfloat16 *__restrict__ lo, int H, int W, int OH, int OW, int ld,
+                                                        long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int ky = (int)(i % 7);
+    const long long pix = i / 7;
+    const int ox = (int)(pix % OW);
+    const int oy = (int)((pix / OW) % OH);
+    const int n = (int)(pix / ((long long)OW * OH));
+    const int y = 2 * oy + ky - 3;
+    float v[24];
+#pragma unroll
+    for (int k = 0; k < 24; ++k) v[k] = 0.0f;
+    if (y >= 0 && y < H) {
+        const float *base = img + (size_t)n * 3 * H * W + (size_t)y * W;
+#pragma unroll
+        for (int kx = 0; kx < 7; ++kx) {
+            const int x = 2 * ox + kx - 3;
+            if (x >= 0 && x < W) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) v[kx * 3 + c] = 2.0f * (__ldg(base + (size_t)c * H * W + x) / 255.0f) - 1.0f;
+            }
+        }
+    }
+    const size_t o = (size_t)pix * ld + ky * 24;
+#pragma unroll
+    for (int g = 0; g < 3; ++g) {
+        uint2 h0, l0, h1, l1;
+        split4(v + g * 8, h0, l0);
+        split4(v + g * 8 + 4, h1, l1);
+        *reinterpret_cast<uint4 *>(hi + o + g * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        *reinterpret_cast<uint4 *>(lo + o + g * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Instance-norm statistics (InstanceNorm2d without affine parameters, eps 1e-5, biased variance): per (sample, channel)
+// mean and 1/sqrt(var + eps) of an NHWC fp32 tensor.  Two deterministic passes: per-block partial sums in fp64, then a
+// fixed-order reduction of the partials.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatBlocks = 64;     // partial blocks per sample
+
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(const float *__restrict__ x, double *__restrict__ partial, int HW, int C,
+                                                               int ld) {
+    extern __shared__ double sred[];                 // [rows][C][2]
+    const int n = blockIdx.y, blk = blockIdx.x;
+    const int c4n = C / 4;
+    const int rows = 256 / c4n;
+    const int c4 = threadIdx.x % c4n, r = threadIdx.x / c4n;
+    double s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
+    if (r < rows) {
+        const int per = (HW + kStatBlocks - 1) / kStatBlocks;
+        const int p0 = blk * per, p1 = min(HW, p0 + per);
+        const float *base = x + (size_t)n * HW * ld + c4 * 4;
+        for (int p = p0 + r; p < p1; p += rows) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)p * ld));
+            s[0] += v.x, s[1] += v.y, s[2] += v.z, s[3] += v.w;
+            q[0] += (double)v.x * v.x, q[1] += (double)v.y * v.y, q[2] += (double)v.z * v.z, q[3] += (double)v.w * v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sred[((size_t)r * C + c4 * 4 + k) * 2] = s[k];
+            sred[((size_t)r * C + c4 * 4 + k) * 2 + 1] = q[k];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double a = 0, b = 0;
+        for (int rr = 0; rr < rows; ++rr) {
+            a += sred[((size_t)rr * C + c) * 2];
+            b += sred[((size_t)rr * C + c) * 2 + 1];
+        }
+        partial[(((size_t)n * kStatBlocks + blk) * C + c) * 2] = a;
+        partial[(((size_t)n * kStatBlocks + blk) * C + c) * 2 + 1] = b;
+    }
+}
+
+__global__ void instnorm_final_kernel(const double *__restrict__ partial, float *__restrict__ stats, int HW, int C, float eps) {
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double a = 0, b = 0;
+        for (int blk = 0; blk < kStatBlocks; ++blk) {
+            a += partial[(((size_t)n * kStatBlocks + blk) * C + c) * 2];
+            b += partial[(((size_t)n * kStatBlocks + blk) * C + c) * 2 + 1];
+        }
+        const double mean = a / HW;
+        double var = b / HW - mean * mean;
+        if (var < 0) var = 0;
+        stats[((size_t)n * C + c) * 2] = (float)mean;
+        stats[((size_t)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+//   ya = stats_a ? (a - mean_a) * rstd_a : a;   if relu_a: ya = max(ya, 0)
+//   y  = b ? max(ya + (stats_b ? (b - mean_b) * rstd_b : b), 0) : ya
+// a, b fp32 NHWC with C channels (dense); y -> optional fp32 NHWC (dense) and / or split planes with channel pitch ld.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__ a, const float *__restrict__ sa, int relu_a,
+                                                       const float *__restrict__ b, const float *__restrict__ sb, float *__restrict__ out,
+                                                       __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int ld, int HW, int C,
+                                                       long long total4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total4) return;
+    const int c4n = C / 4;
+    const int c = (int)(i % c4n) * 4;
+    const long long pix = i / c4n;
+    const int n = (int)(pix / HW);
+    const float4 av = __ldg(reinterpret_cast<const float4 *>(a + pix * C + c));
+    float y[4] = {av.x, av.y, av.z, av.w};
+    if (sa) {
+        const float *s = sa + ((size_t)n * C + c) * 2;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] = (y[k] - __ldg(s + 2 * k)) * __ldg(s + 2 * k + 1);
+    }
+    if (relu_a) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] = fmaxf(y[k], 0.0f);
+    }
+    if (b) {
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(b + pix * C + c));
+        float z[4] = {bv.x, bv.y, bv.z, bv.w};
+        if (sb) {
+            const float *s = sb + ((size_t)n * C + c) * 2;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) z[k] = (z[k] - __ldg(s + 2 * k)) * __ldg(s + 2 * k + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] = fmaxf(y[k] + z[k], 0.0f);
+    }
+    if (out) *reinterpret_cast<float4 *>(out + pix * C + c) = make_float4(y[0], y[1], y[2], y[3]);
+    if (hi) {
+        uint2 h, l;
+        split4(y, h, l);
+        *reinterpret_cast<uint2 *>(hi + pix * ld + c) = h;
+        *reinterpret_cast<uint2 *>(lo + pix * ld + c) = l;
+    }
+}
+
+}  // namespace rpe
+
+extern "C" {
+
+int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream) {
+    if (!img || !out_hi || !out_lo || n <= 0 || H <= 0 || W <= 0 || ld < 168 || (ld % 8)) return RPE_ERR_INVALID_ARG;
+    if ((reinterpret_cast<uintptr_t>(out_hi) & 15u) || (reinterpret_cast<uintptr_t>(out_lo) & 15u)) return RPE_ERR_ALIGNMENT;
+    const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+    const long long total = (long long)n * OH * OW * 7;
+    rpe::im2col7s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16 *)out_hi,
+                                                                                           (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld, total);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+size_t rpe_instnorm_workspace_bytes(int n, int C) { return (size_t)n * rpe::kStatBlocks * C * 2 * sizeof(double); }
+
+int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float eps, void *workspace, size_t workspace_bytes,
+                       void *stream) {
+    if (!x || !stats || !workspace || n <= 0 || HW <= 0 || C <= 0 || (C % 4) || C > 1024) return RPE_ERR_INVALID_ARG;
+    if (workspace_bytes < rpe_instnorm_workspace_bytes(n, C)) return RPE_ERR_WORKSPACE;
+    if (!rpe::aligned16(x) || (reinterpret_cast<uintptr_t>(workspace) & 7u)) return RPE_ERR_ALIGNMENT;
+    const int rows = 256 / (C / 4);
+    if (rows < 1) return RPE_ERR_INVALID_ARG;
+    const size_t smem = (size_t)rows * C * 2 * sizeof(double);
+    dim3 grid(rpe::kStatBlocks, n);
+    rpe::instnorm_partial_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (double *)workspace, HW, C, C);
+    RPE_LAUNCH_CHECK();
+    rpe::instnorm_final_kernel<<<n, 128, 0, (cudaStream_t)stream>>>((const double *)workspace, stats, HW, C, eps);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
+                       void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream) {
+    if (!a || n <= 0 || HW <= 0 || C <= 0 || (C % 4) || (!out_f32 && !out_hi) || ((out_hi == nullptr) != (out_lo == nullptr)))
+        return RPE_ERR_INVALID_ARG;
+    if (out_hi && (ld < C || (ld % 4))) return RPE_ERR_INVALID_ARG;
+    if (!rpe::aligned16(a) || (b && !rpe::aligned16(b)) || (out_f32 && !rpe::aligned16(out_f32))) return RPE_ERR_ALIGNMENT;
+    const long long total4 = (long long)n * HW * (C / 4);
+    rpe::norm_act_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        a, stats_a, relu_a, b, stats_b, out_f32, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, ld, HW, C, total4);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+}  // extern "C"

@@ -42,8 +42,8 @@ class F2FEngine:
         """First frame of a (shard of a) sequence: stereo depth only.  For the first frame of the SEQUENCE the
         stereo validity is NOT and-ed into the mask; for the halo frame of a later shard it is."""
         raft = self.model.flow
-        f = raft.features(torch.cat((limg, rimg), 0))
-        net, inp = raft.context(limg)
+        fl, fr, net, inp = raft.encode(limg, rimg)
+        f = torch.cat((fl, fr), 0)
         preds, _, _, _ = raft.refine(f[0:1].contiguous(), f[1:2].contiguous(), net, inp)
         bl = (self.est.baseline * self.est.scale).float().reshape(1)
         eye = torch.eye(3, device=limg.device)[None]
@@ -59,9 +59,7 @@ class F2FEngine:
         C = limg.shape[0]
         raft, model, est = self.model.flow, self.model, self.est
         H, W = limg.shape[-2:]
-        f = raft.features(torch.cat((limg, rimg), 0))
-        fL, fR = f[:C], f[C:]
-        net0, inp = raft.context(limg)
+        fL, fR, net0, inp = raft.encode(limg, rimg)
         fL_prev = torch.cat((prev.fmap, fL[:-1]), 0)
         net_prev = torch.cat((prev.net, net0[:-1]), 0)
         inp_prev = torch.cat((prev.inp, inp[:-1]), 0)

@@ -50,7 +50,7 @@ class ConvPlan:
         d = _lib.ConvDesc()
         self._keep = [bias, pre, res, out_f32, out_planes]
         for k, (planes, c_off, c_cnt, (w_hi, w_lo)) in enumerate(inputs):
-            assert planes.shape[:3] == (n, h, w), f"{name}: source {k} has shape {planes.shape}, expected {(n, h, w)}"
+            assert planes.shape[1:3] == (h, w) and planes.shape[0] >= n, f"{name}: source {k} has shape {planes.shape}, expected {(n, h, w)}"
             assert w_hi.shape[1] == cout_pad, f"{name}: weight packed for cout_pad {w_hi.shape[1]}, plan needs {cout_pad}"
             s = d.src[k]
             s.act_hi, s.act_lo = planes.hi.data_ptr(), (0 if single_pass else planes.lo.data_ptr())

@@ -113,3 +113,29 @@ def test_update_operator_vs_torch_trunk(ops):
     ref = dev(np.stack((g["s_time_flow"],)))
     epe_ref = (outs["bf16x3"][0][0:1] - ref).pow(2).sum(1).sqrt()
     assert epe_ref.mean().item() < 1e-2                                    # north-star flow gate vs the reference itself
+
+
+@pytest.mark.parametrize("which", ["fnet", "cnet"])
+def test_encoder_tc_vs_torch_fp32(ops, which):
+    """Feature / context encoder on the tensor-core path (instance-norm statistics, folded batch norm, strided TMA
+    convolutions, im2col stem) vs the torch fp32 encoder, trained weights, real 640x512 images."""
+    if not os.path.isfile(CKPT) or not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz")):
+        pytest.skip("checkpoint / full golden not shipped")
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_net import PoseNet
+    g = np.load(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz"))
+    ck = torch.load(CKPT, map_location="cpu", weights_only=False)
+    imgs = torch.cat((dev(g["imgs_l"][0:2].astype(np.float32)), dev(g["imgs_r"][0:1].astype(np.float32))))
+    outs = {}
+    for prec in ("fp32", "bf16x3"):
+        cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision=prec)
+        model = PoseNet(cfg)
+        model.load_state_dict(ck["state_dict"])
+        raft = model.cuda().eval().flow
+        with torch.no_grad():
+            outs[prec] = (raft.features(imgs),) if which == "fnet" else raft.context(imgs)
+    for a, b in zip(outs["fp32"], outs["bf16x3"]):
+        assert a.shape == b.shape
+        err = (a - b).abs().max().item()
+        print(f"{which}: max abs diff {err:.2e} (|ref| max {a.abs().max().item():.2f}, mean {a.abs().mean().item():.3f})")
+        assert err < 2e-4 * max(1.0, a.abs().max().item())
