@@ -222,6 +222,14 @@ typedef struct rpe_conv_desc {
     int f32_ld, f32_offset;
     void *out_hi, *out_lo; /* NHWC bf16 planes (N,OH,OW,bf_ld) at channel bf_offset; out_lo may be NULL */
     int bf_ld, bf_offset;
+    /* fused SepConvGRU epilogues (update.py:45-60); 0 = plain epilogue.
+     *   mode 1 (z|r gates, activation sigmoid, cout = 2*hidden): z = out[:hidden] -> out_f32, planes <- r * h  (h = aux)
+     *   mode 2 (candidate, activation tanh, cout = hidden): h <- (1 - z) * h + z * q in place (h = aux, z = aux2), planes <- h */
+    int mode;
+    float *aux;          /* hidden state h, fp32 NHWC (N,OH,OW,aux_ld)                                */
+    int aux_ld;
+    const float *aux2;   /* update gate z, fp32 NHWC (N,OH,OW,aux2_ld)                                */
+    int aux2_ld;
 } rpe_conv_desc;
 
 int rpe_conv_plan_create(const rpe_conv_desc *desc, void **plan_out);   /* encodes the TMA descriptors once */

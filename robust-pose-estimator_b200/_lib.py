@@ -33,7 +33,8 @@ class ConvDesc(C.Structure):
                 ("pre", C.c_void_p), ("pre_ld", C.c_int), ("res", C.c_void_p), ("res_ld", C.c_int),
                 ("activation", C.c_int), ("out_scale", C.c_float), ("out_f32", C.c_void_p), ("f32_ld", C.c_int),
                 ("f32_offset", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("bf_ld", C.c_int),
-                ("bf_offset", C.c_int)]
+                ("bf_offset", C.c_int), ("mode", C.c_int), ("aux", C.c_void_p), ("aux_ld", C.c_int), ("aux2", C.c_void_p),
+                ("aux2_ld", C.c_int)]
 
 
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t

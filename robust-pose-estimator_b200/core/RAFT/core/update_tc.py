@@ -38,12 +38,12 @@ class UpdateTC:
 
     # ---- plans -------------------------------------------------------------------------------------------
     def _plan(self, st, name, inputs, kh, kw, cout, act, out_f32=None, f32_off=0, out_planes=None, bf_off=0, scale=1.0,
-              weight=None, bias=None):
+              weight=None, bias=None, use_bias=True, **kw_extra):
         """inputs: [(planes, c_offset, c_count_real, weight channel window start)]"""
         cout_pad = (cout + 15) // 16 * 16
         srcs = [(planes, c_off, c_cnt, self._w(name, w_lo, w_lo + c_cnt, cout_pad, weight)) for planes, c_off, c_cnt, w_lo in inputs]
-        return ConvPlan(name, srcs, st["dims"], kh, kw, cout, act, bias=self._bias(name, bias), out_f32=out_f32, f32_off=f32_off,
-                        out_planes=out_planes, bf_off=bf_off, scale=scale)
+        return ConvPlan(name, srcs, st["dims"], kh, kw, cout, act, bias=self._bias(name, bias) if use_bias else None, out_f32=out_f32,
+                        f32_off=f32_off, out_planes=out_planes, bf_off=bf_off, scale=scale, **kw_extra)
 
     def _state(self, n, h, w, device):
         key = (n, h, w, device.index)
@@ -53,9 +53,11 @@ class UpdateTC:
         P = lambda c: Planes(n, h, w, c, device)
         f32 = lambda c: torch.zeros((n, h, w, c), dtype=torch.float32, device=device)
         st = {"dims": (n, h, w)}
-        st.update(corr=P(384), cor1=P(256), cf=P(256), col=P(128), flo1=P(128), x=P(256), hp=P(128), rh=P(128), fh=P(256), mk=P(256),
-                  h=f32(128), zr=f32(256), q=f32(128), delta=f32(4), mask=f32(576),
-                  coords1=torch.zeros((n, 2, h, w), dtype=torch.float32, device=device))
+        # GRU input x = cat(inp, motion features, flow) (update.py:96,134): `inp` is constant over the iterations, so its
+        # contribution to the six gate convolutions is evaluated once per refinement (pzr*/pq*) and enters as an addend
+        st.update(corr=P(384), cor1=P(256), cf=P(256), col=P(128), flo1=P(128), inp=P(128), mot=P(128), hp=P(128), rh=P(128),
+                  fh=P(256), mk=P(256), h=f32(128), z=f32(128), pzr1=f32(256), pzr2=f32(256), pq1=f32(128), pq2=f32(128),
+                  delta=f32(4), mask=f32(576), coords1=torch.zeros((n, 2, h, w), dtype=torch.float32, device=device))
         W, pre = self.W, self.prefix
         zr_w = lambda half: (lambda: torch.cat((W[pre + f"gru.convz{half}.weight"], W[pre + f"gru.convr{half}.weight"]), 0))
         zr_b = lambda half: (lambda: torch.cat((W[pre + f"gru.convz{half}.bias"], W[pre + f"gru.convr{half}.bias"]), 0))
@@ -65,12 +67,17 @@ class UpdateTC:
         pl["convc2"] = self._plan(st, "encoder.convc2", [(st["cor1"], 0, 256, 0)], 3, 3, 192, "relu", out_planes=st["cf"], bf_off=0)
         pl["convf1"] = self._plan(st, "encoder.convf1", [(st["col"], 0, 98, 0)], 1, 1, 128, "relu", out_planes=st["flo1"], weight=f1_w)
         pl["convf2"] = self._plan(st, "encoder.convf2", [(st["flo1"], 0, 128, 0)], 3, 3, 64, "relu", out_planes=st["cf"], bf_off=192)
-        pl["conv"] = self._plan(st, "encoder.conv", [(st["cf"], 0, 256, 0)], 3, 3, 126, "relu", out_planes=st["x"], bf_off=128)
+        pl["conv"] = self._plan(st, "encoder.conv", [(st["cf"], 0, 256, 0)], 3, 3, 126, "relu", out_planes=st["mot"], bf_off=0)
         for half, (kh, kw) in (("1", (1, 5)), ("2", (5, 1))):
-            pl["zr" + half] = self._plan(st, "gru.convzr" + half, [(st["hp"], 0, 128, 0), (st["x"], 0, 256, 128)], kh, kw, 256, "sigmoid",
-                                         out_f32=st["zr"], weight=zr_w(half), bias=zr_b(half))
-            pl["q" + half] = self._plan(st, "gru.convq" + half, [(st["rh"], 0, 128, 0), (st["x"], 0, 256, 128)], kh, kw, 128, "tanh",
-                                        out_f32=st["q"])
+            # hx = cat(h, inp, motion, flow): weight input channels [0,128) h, [128,256) inp, [256,384) motion + flow
+            pl["pzr" + half] = self._plan(st, "gru.convzr" + half, [(st["inp"], 0, 128, 128)], kh, kw, 256, "none", out_f32=st["pzr" + half],
+                                          weight=zr_w(half), bias=zr_b(half))
+            pl["pq" + half] = self._plan(st, "gru.convq" + half, [(st["inp"], 0, 128, 128)], kh, kw, 128, "none", out_f32=st["pq" + half])
+            pl["zr" + half] = self._plan(st, "gru.convzr" + half, [(st["hp"], 0, 128, 0), (st["mot"], 0, 128, 256)], kh, kw, 256, "sigmoid",
+                                         out_f32=st["z"], out_planes=st["rh"], weight=zr_w(half), use_bias=False, pre=st["pzr" + half],
+                                         mode=1, aux=st["h"])
+            pl["q" + half] = self._plan(st, "gru.convq" + half, [(st["rh"], 0, 128, 0), (st["mot"], 0, 128, 256)], kh, kw, 128, "tanh",
+                                        out_planes=st["hp"], use_bias=False, pre=st["pq" + half], mode=2, aux=st["h"], aux2=st["z"])
         pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["fh"])
         pl["fh2"] = self._plan(st, "flow_head.conv2", [(st["fh"], 0, 256, 0)], 3, 3, 2, "none", out_f32=st["delta"])
         pl["mask0"] = self._plan(st, "mask.0", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["mk"])
@@ -92,33 +99,28 @@ class UpdateTC:
         l = _lib.lib()
         s = _stream()
         npix = B * h * w
-        # initial state: h (fp32 + planes), inp -> x[0:128], coords1 = grid (+ flow_init)
+        # initial state: h (fp32 + planes), inp planes + its gate contributions, coords1 = grid (+ flow_init)
         check(l.rpe_nchw_to_nhwc_split(_p(net.float().contiguous()), _p(st["hp"].hi), _p(st["hp"].lo), _p(st["h"]), B, 128, h, w, 128, 0,
                                        128, 0, s), "rpe_nchw_to_nhwc_split")
-        check(l.rpe_nchw_to_nhwc_split(_p(inp.float().contiguous()), _p(st["x"].hi), _p(st["x"].lo), None, B, 128, h, w, 256, 0, 0, 0, s),
+        check(l.rpe_nchw_to_nhwc_split(_p(inp.float().contiguous()), _p(st["inp"].hi), _p(st["inp"].lo), None, B, 128, h, w, 128, 0, 0, 0, s),
               "rpe_nchw_to_nhwc_split")
+        for name in ("pzr1", "pq1", "pzr2", "pq2"):
+            self._run(st, name)
         ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
         grid = torch.stack((xs, ys), 0).float()
         st["coords1"].copy_(grid[None].expand(B, 2, h, w) if flow_init is None else grid[None] + flow_init)
         coords1 = st["coords1"]
         for it in range(iters):
+            # coords1 += delta of the previous iteration; flow = coords1 - coords0 -> im2col planes + GRU-input slots
+            with _timed("flow_step", B):
+                check(l.rpe_flow_step(_p(coords1), _p(st["delta"]) if it > 0 else None, 4, _p(st["col"].hi), _p(st["col"].lo), 128,
+                                      _p(st["mot"].hi), _p(st["mot"].lo), 128, 126, B, h, w, s), "rpe_flow_step")
             with _timed("corr_lookup", B):
                 check(l.rpe_corr_lookup_nhwc_bf16(_p(corr_pyr.pyramid), _p(coords1), _p(st["corr"].hi), _p(st["corr"].lo), 384, B, h, w,
                                                   corr_pyr.num_levels, corr_pyr.radius, s), "rpe_corr_lookup_nhwc_bf16")
-            # flow = coords1 - coords0 -> im2col planes + GRU-input slots (coords were advanced at the end of the last iteration)
-            check(l.rpe_flow_step(_p(coords1), None, 4, _p(st["col"].hi), _p(st["col"].lo), 128, _p(st["x"].hi), _p(st["x"].lo), 256, 254,
-                                  B, h, w, s), "rpe_flow_step")
-            for name in ("convc1", "convc2", "convf1", "convf2", "conv"):
+            for name in ("convc1", "convc2", "convf1", "convf2", "conv", "zr1", "q1", "zr2", "q2", "fh1", "fh2"):
                 self._run(st, name)
-            for half in ("1", "2"):
-                self._run(st, "zr" + half)
-                check(l.rpe_gru_gate(_p(st["zr"]), _p(st["h"]), None, _p(st["rh"].hi), _p(st["rh"].lo), 128, 0, npix, 0, s), "rpe_gru_gate")
-                self._run(st, "q" + half)
-                check(l.rpe_gru_gate(_p(st["zr"]), _p(st["h"]), _p(st["q"]), _p(st["hp"].hi), _p(st["hp"].lo), 128, 0, npix, 1, s),
-                      "rpe_gru_gate")
-            self._run(st, "fh1")
-            self._run(st, "fh2")
-            coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))
+        coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))
         flow_lo = coords1 - grid[None]
         flow_up = None
         if want_mask:

@@ -29,13 +29,15 @@ namespace rpe {
 
 constexpr int kCvBK = 64;                             // bf16 channels per K block (one 128-byte swizzle row)
 constexpr int kCvAcc = 2;                             // TMEM accumulator stages
-constexpr int kCvThreads = 256;
+constexpr int kCvEpiWarps = 8;                        // 2 per SM sub-partition: column halves of the same TMEM lanes
+constexpr int kCvThreads = 128 + 32 * kCvEpiWarps;
 constexpr int kCvMaxSrc = 4;
 constexpr int kCvMaxBN = 256;
-constexpr int kCvMaxAStages = 4, kCvMaxBStages = 8;
-constexpr int kCvSmemData = 214 * 1024;               // budget for the two rings
+constexpr int kCvMaxAStages = 4, kCvMaxBStages = 16;
+constexpr int kCvSmemData = 205 * 1024;               // budget for the two rings
 constexpr int kCvMaxCout = 1024;                      // bias staged in shared memory
-constexpr int kCvSmem = kCvSmemData + 1024 + 512 + kCvMaxCout * 4;     // + alignment slack + barriers + bias
+constexpr int kCvStageBytes = kCvEpiWarps * 32 * 16 * 4;   // epilogue transpose tiles: one [32 rows][16 floats] per warp
+constexpr int kCvSmem = kCvSmemData + 1024 + 512 + kCvMaxCout * 4 + kCvStageBytes;   // + alignment slack + barriers + bias + staging
 
 struct alignas(64) ConvParams {
     CUtensorMap amap[kCvMaxSrc][2];
@@ -49,6 +51,8 @@ struct alignas(64) ConvParams {
     int reuse;                                        // 1: one slab per filter column serves all kmaj taps (stride 1)
     uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes;
     int n_a_stages, n_b_stages;
+    int resident_b;                                   // 1: the whole weight set stays in shared memory (loaded once per CTA)
+    int cb_base[kCvMaxSrc];                           // first K block of each source in the resident weight array
     int cout, bn, n_blocks;
     const float *bias;
     const float *pre;
@@ -61,6 +65,11 @@ struct alignas(64) ConvParams {
     int f32_ld, f32_off;
     __nv_bfloat16 *out_hi, *out_lo;
     int bf_ld, bf_off;
+    int mode;                                         // 0 plain, 1 GRU z|r gates, 2 GRU candidate + state update
+    float *aux;                                       // mode 1/2: hidden state h (fp32 NHWC, updated in place by mode 2)
+    int aux_ld;
+    const float *aux2;                                // mode 2: update gate z (fp32 NHWC)
+    int aux2_ld;
 };
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -85,27 +94,29 @@ __device__ __forceinline__ uint64_t cv_sw128_desc(uint32_t smem_addr) {
            ((uint64_t)2 << 61);
 }
 
-template <int ACT>
-__device__ __forceinline__ float cv_activate(float v) {
-    if (ACT == 1) return fmaxf(v, 0.0f);
-    if (ACT == 2) return 1.0f / (1.0f + expf(-v));
-    if (ACT == 3) return tanhf(v);
+__device__ __forceinline__ float cv_activate_rt(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.0f);
+    if (act == 2) return 1.0f / (1.0f + expf(-v));
+    if (act == 3) return tanhf(v);
     return v;
 }
 
+// fp32 x4 -> bf16 hi / lo planes (hi = bf16(v), lo = bf16(v - hi)), packed conversions
 __device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, size_t o, const float *v) {
-    __nv_bfloat16 h[4], l[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        h[k] = __float2bfloat16_rn(v[k]);
-        l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k]));
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 hv;
+    hv.x = *reinterpret_cast<const uint32_t *>(&h01);
+    hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+    *reinterpret_cast<uint2 *>(P.out_hi + o) = hv;
+    if (P.out_lo) {
+        const float r0 = v[0] - __uint_as_float(hv.x << 16), r1 = v[1] - __uint_as_float(hv.x & 0xffff0000u);
+        const float r2 = v[2] - __uint_as_float(hv.y << 16), r3 = v[3] - __uint_as_float(hv.y & 0xffff0000u);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(r0, r1), l23 = __floats2bfloat162_rn(r2, r3);
+        uint2 lv;
+        lv.x = *reinterpret_cast<const uint32_t *>(&l01);
+        lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+        *reinterpret_cast<uint2 *>(P.out_lo + o) = lv;
     }
-    *reinterpret_cast<uint2 *>(P.out_hi + o) = *reinterpret_cast<uint2 *>(h);
-    if (P.out_lo) *reinterpret_cast<uint2 *>(P.out_lo + o) = *reinterpret_cast<uint2 *>(l);
-}
-
-__device__ __forceinline__ float cv_activate_rt(float v, int act) {
-    return act == 1 ? cv_activate<1>(v) : act == 2 ? cv_activate<2>(v) : act == 3 ? cv_activate<3>(v) : v;
 }
 
 // Ragged tail (1..3 channels) of an output-channel count that is not a multiple of 4.
@@ -126,38 +137,95 @@ __device__ __noinline__ void cv_epilogue_tail(const ConvParams &P, int act, floa
     }
 }
 
+// Side inputs of one group of 4 channels (addend, residual / hidden state, update gate); loaded for several groups at once
+// so that their latencies overlap.  Every element is read at most once before any write to it.
+struct CvSide {
+    float4 pre, a, z;
+};
+
+__device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, int co, size_t pix) {
+    if (co + 3 >= P.cout) return;
+    if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
+    if (P.mode == 0) {
+        if (P.res) sd.a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
+    } else if (P.mode == 1) {
+        const int half = P.cout >> 1;
+        if (co >= half) sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + pix * P.aux_ld + (co - half)));
+    } else {
+        sd.z = __ldg(reinterpret_cast<const float4 *>(P.aux2 + pix * P.aux2_ld + co));
+        sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + pix * P.aux_ld + co));
+    }
+}
+
 // One group of 4 consecutive output channels of one pixel: bias / addend / activation / scale / residual / stores.
-template <int ACT>
-__device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const uint32_t *acc4, const float *sbias, int co, size_t pix) {
+__device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const float4 acc, const CvSide &sd, const float *sbias, int co,
+                                                  size_t pix) {
     if (co >= P.cout) return;
     float o[4];
     if (co + 3 < P.cout) {
         const float4 b = *reinterpret_cast<const float4 *>(sbias + co);
-        o[0] = __uint_as_float(acc4[0]) + b.x, o[1] = __uint_as_float(acc4[1]) + b.y;
-        o[2] = __uint_as_float(acc4[2]) + b.z, o[3] = __uint_as_float(acc4[3]) + b.w;
-        if (P.pre) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
-            o[0] += a.x, o[1] += a.y, o[2] += a.z, o[3] += a.w;
-        }
+        o[0] = acc.x + b.x, o[1] = acc.y + b.y, o[2] = acc.z + b.z, o[3] = acc.w + b.w;
+        if (P.pre) o[0] += sd.pre.x, o[1] += sd.pre.y, o[2] += sd.pre.z, o[3] += sd.pre.w;
+        if (P.act == 1) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = cv_activate<ACT>(o[k]) * P.scale;
-        if (P.res) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
-            o[0] = fmaxf(o[0] + a.x, 0.0f), o[1] = fmaxf(o[1] + a.y, 0.0f);
-            o[2] = fmaxf(o[2] + a.z, 0.0f), o[3] = fmaxf(o[3] + a.w, 0.0f);
+            for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.0f);
+        } else if (P.act == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = 1.0f / (1.0f + expf(-o[k]));
+        } else if (P.act == 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = tanhf(o[k]);
         }
-        if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
-        if (P.out_hi) cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
+        if (P.scale != 1.0f) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] *= P.scale;
+        }
+        if (P.mode == 0) {
+            if (P.res) {
+                o[0] = fmaxf(o[0] + sd.a.x, 0.0f), o[1] = fmaxf(o[1] + sd.a.y, 0.0f);
+                o[2] = fmaxf(o[2] + sd.a.z, 0.0f), o[3] = fmaxf(o[3] + sd.a.w, 0.0f);
+            }
+            if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
+            if (P.out_hi) cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
+        } else if (P.mode == 1) {
+            // SepConvGRU gates (update.py:45-50, 53-58): channels [0, cout/2) = z -> fp32; [cout/2, cout) = r -> planes of r * h
+            const int half = P.cout >> 1;
+            if (co < half) {
+                *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+                o[0] *= sd.a.x, o[1] *= sd.a.y, o[2] *= sd.a.z, o[3] *= sd.a.w;
+                cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + (co - half), o);
+            }
+        } else {
+            // candidate state q = tanh(.) and the state update h = (1 - z) * h + z * q, fp32 in place + planes
+            o[0] = (1.0f - sd.z.x) * sd.a.x + sd.z.x * o[0];
+            o[1] = (1.0f - sd.z.y) * sd.a.y + sd.z.y * o[1];
+            o[2] = (1.0f - sd.z.z) * sd.a.z + sd.z.z * o[2];
+            o[3] = (1.0f - sd.z.w) * sd.a.w + sd.z.w * o[3];
+            *reinterpret_cast<float4 *>(P.aux + pix * P.aux_ld + co) = make_float4(o[0], o[1], o[2], o[3]);
+            cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
+        }
     } else {                                           // ragged tail of a channel count that is not a multiple of 4
-        cv_epilogue_tail(P, ACT, __uint_as_float(acc4[0]), __uint_as_float(acc4[1]), __uint_as_float(acc4[2]), sbias, co, pix);
+        cv_epilogue_tail(P, P.act, acc.x, acc.y, acc.z, sbias, co, pix);
     }
 }
 
-template <int ACT>
-__device__ __forceinline__ void cv_epilogue_chunk(const ConvParams &P, const uint32_t *v, int cols, const float *sbias, int co0, size_t pix) {
+// 16 accumulator columns of the warp's 32 pixels, already transposed through shared memory: lane = (pixel row it*8 + lane/4,
+// channel group lane%4), i.e. 4 lanes cover 64 contiguous bytes of one pixel and a warp instruction touches 8 pixels.
+// stage: [32 rows][4 chunks of 16 B], chunk k of row r stored at k ^ ((r >> 1) & 3) (conflict-free both ways).
+__device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const float *stage, const float *sbias, int co, const size_t *pix,
+                                                 uint32_t inside_mask, int lane) {
+    CvSide sd[4];
+    float4 acc[4];
 #pragma unroll
-    for (int j = 0; j < 32; j += 4)
-        if (j < cols) cv_epilogue_group<ACT>(P, v + j, sbias, co0 + j, pix);
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        acc[it] = *reinterpret_cast<const float4 *>(stage + r * 16 + (((lane & 3) ^ ((r >> 1) & 3)) << 2));
+        if ((inside_mask >> it) & 1u) cv_side_load(P, sd[it], co, pix[it]);
+    }
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+        if ((inside_mask >> it) & 1u) cv_epilogue_group(P, acc[it], sd[it], sbias, co, pix[it]);
 }
 
 struct CvTile {
@@ -190,6 +258,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
     uint64_t *tmem_empty = tmem_full + kCvAcc;
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + kCvAcc);
     float *sbias = reinterpret_cast<float *>(smem + kCvSmemData + 512);
+    float *sstage = reinterpret_cast<float *>(smem + kCvSmemData + 512 + kCvMaxCout * 4);
     for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -214,7 +283,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         }
         for (int i = 0; i < kCvAcc; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], kCvEpiWarps);
         }
         fence_barrier_init();
     }
@@ -252,22 +321,39 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
     } else if (warp == 3) {
         // ===================== weight producer =====================
         if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const CvTile t = cv_decode(P, tile);
-                for (int s = 0; s < P.n_src; ++s)
-                    for (int cb = 0; cb < P.cblocks[s]; ++cb)
-                        for (int tm = 0; tm < P.kmin; ++tm)
-                            for (int tj = 0; tj < P.kmaj; ++tj) {
-                                const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
-                                for (int p = 0; p < P.n_planes; ++p) {          // one ring entry per plane tile
-                                    mbar_wait(&b_empty[stage], phase ^ 1);
-                                    mbar_expect_tx(&b_full[stage], P.b_plane_bytes);
-                                    tma_load_3d(sB + (size_t)stage * P.b_plane_bytes, &P.wmap[s][p], &b_full[stage], cb * kCvBK, t.nb * P.bn, tap);
-                                    if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+            const int taps = P.kmin * P.kmaj;
+            if (P.resident_b) {
+                // the whole weight set fits: one load per CTA, [source K block][tap][plane] tiles
+                uint32_t total = 0;
+                for (int s = 0; s < P.n_src; ++s) total += (uint32_t)P.cblocks[s] * taps * P.n_planes * P.b_plane_bytes;
+                if (blockIdx.x < num_tiles) {
+                    mbar_expect_tx(&b_full[0], total);
+                    for (int s = 0; s < P.n_src; ++s)
+                        for (int cb = 0; cb < P.cblocks[s]; ++cb)
+                            for (int tap = 0; tap < taps; ++tap)
+                                for (int p = 0; p < P.n_planes; ++p)
+                                    tma_load_3d(sB + (size_t)(((P.cb_base[s] + cb) * taps + tap) * P.n_planes + p) * P.b_plane_bytes,
+                                                &P.wmap[s][p], &b_full[0], cb * kCvBK, 0, tap);
+                }
+            } else {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                    const CvTile t = cv_decode(P, tile);
+                    for (int s = 0; s < P.n_src; ++s)
+                        for (int cb = 0; cb < P.cblocks[s]; ++cb)
+                            for (int tm = 0; tm < P.kmin; ++tm)
+                                for (int tj = 0; tj < P.kmaj; ++tj) {
+                                    const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
+                                    for (int p = 0; p < P.n_planes; ++p) {          // one ring entry per plane tile
+                                        mbar_wait(&b_empty[stage], phase ^ 1);
+                                        mbar_expect_tx(&b_full[stage], P.b_plane_bytes);
+                                        tma_load_3d(sB + (size_t)stage * P.b_plane_bytes, &P.wmap[s][p], &b_full[stage], cb * kCvBK,
+                                                    t.nb * P.bn, tap);
+                                        if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                                    }
                                 }
-                            }
+                }
             }
         }
     } else if (warp == 1) {
@@ -279,6 +365,7 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
             uint32_t pa = 0, pb = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            bool b_ready = false;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
@@ -292,27 +379,47 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                                 if (!P.reuse || tj == 0) {
                                     mbar_wait(&a_full[sa], pa);
                                 }
-                                mbar_wait(&b_full[sb], pb);
-                                tcgen05_fence_after();
                                 const uint32_t a0 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) + (P.reuse ? (uint32_t)tj * 1024u : 0u);
                                 const uint64_t da_hi = cv_sw128_desc(a0);
-                                const uint64_t db_hi = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
-                                for (int k = 0; k < ksteps; ++k) {
-                                    umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
-                                    accumulate = 1;
-                                }
-                                if (P.n_planes == 2) {
-                                    const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes);
-                                    for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                    umma_commit(&b_empty[sb]);
-                                    if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
+                                if (P.resident_b) {
+                                    if (!b_ready) {
+                                        mbar_wait(&b_full[0], 0);
+                                        b_ready = true;
+                                    }
+                                    tcgen05_fence_after();
+                                    const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
+                                    const uint32_t b0 = smem_u32(sB) + (uint32_t)(((P.cb_base[s] + cb) * (P.kmin * P.kmaj) + tap) * P.n_planes) * P.b_plane_bytes;
+                                    const uint64_t db_hi = cv_sw128_desc(b0);
+                                    for (int k = 0; k < ksteps; ++k) {
+                                        umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                        accumulate = 1;
+                                    }
+                                    if (P.n_planes == 2) {
+                                        const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes), db_lo = cv_sw128_desc(b0 + P.b_plane_bytes);
+                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                    }
+                                } else {
                                     mbar_wait(&b_full[sb], pb);
                                     tcgen05_fence_after();
-                                    const uint64_t db_lo = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
-                                    for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                    const uint64_t db_hi = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
+                                    for (int k = 0; k < ksteps; ++k) {
+                                        umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                        accumulate = 1;
+                                    }
+                                    if (P.n_planes == 2) {
+                                        const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes);
+                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                        umma_commit(&b_empty[sb]);
+                                        if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
+                                        mbar_wait(&b_full[sb], pb);
+                                        tcgen05_fence_after();
+                                        const uint64_t db_lo = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
+                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                    }
+                                    umma_commit(&b_empty[sb]);
+                                    if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
                                 }
-                                umma_commit(&b_empty[sb]);
-                                if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
                                 if (!P.reuse || tj == P.kmaj - 1) {
                                     umma_commit(&a_empty[sa]);
                                     if (++sa == P.n_a_stages) sa = 0, pa ^= 1;
@@ -325,50 +432,59 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int wq = warp - 4;
-        const int m = wq * 32 + lane;                  // accumulator row = pixel inside the tile
-        const int gi = m >> 3, mi = m & 7;             // (major, minor) position
+        // TMEM lane = pixel row of the tile.  Every 16 accumulator columns are transposed through a 2 KB per-warp staging
+        // tile so that the global side loads and the stores are coalesced (64 contiguous bytes per pixel per instruction).
+        const int wq = warp & 3;                               // TMEM lane quarter this warp may access
+        const int chalf = (warp - 4) >> 2;                     // which half of the accumulator columns it drains
+        float *stage = sstage + (warp - 4) * (32 * 16);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const CvTile t = cv_decode(P, tile);
-            const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
-            const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
-            const bool inside = (y < P.OH) && (x < P.OW);
-            const size_t pix = ((size_t)t.img * P.OH + y) * P.OW + x;
+            size_t pix[4];
+            uint32_t inside_mask = 0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int m = wq * 32 + it * 8 + (lane >> 2);      // accumulator row handled in the transposed mapping
+                const int gi = m >> 3, mi = m & 7;                 // (major, minor) position inside the tile
+                const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
+                const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
+                if (y < P.OH && x < P.OW) inside_mask |= 1u << it;
+                pix[it] = ((size_t)t.img * P.OH + y) * P.OW + x;
+            }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
             const int n_chunks = P.bn / 16;
-            for (int c = 0; c < n_chunks; c += 2) {
-                // 32 columns per TMEM load when available, 16 for the tail of a bn that is not a multiple of 32
-                uint32_t v[32];
-                const int cols = (c + 1 < n_chunks) ? 32 : 16;
+            const int c_begin = chalf * ((n_chunks + 1) / 2), c_end = chalf == 0 ? (n_chunks + 1) / 2 : n_chunks;
+            if (c_begin >= c_end) {                                // nothing to drain (bn = 16): just release the accumulator
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            for (int c = c_begin; c < c_end; ++c) {
+                uint32_t v[16];
                 const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kCvMaxBN + c * 16);
-                if (cols == 32) {
-                    tmem_ld_32x32b_x32(taddr, v);
-                } else {
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                        : "r"(taddr)
-                        : "memory");
-                }
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                    : "r"(taddr)
+                    : "memory");
                 tmem_ld_wait();
-                if (c + 2 >= n_chunks) {
+                if (c + 1 == c_end) {
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
-                if (!inside) continue;
-                const int co0 = t.nb * P.bn + c * 16;
-                switch (P.act) {
-                    case 1: cv_epilogue_chunk<1>(P, v, cols, sbias, co0, pix); break;
-                    case 2: cv_epilogue_chunk<2>(P, v, cols, sbias, co0, pix); break;
-                    case 3: cv_epilogue_chunk<3>(P, v, cols, sbias, co0, pix); break;
-                    default: cv_epilogue_chunk<0>(P, v, cols, sbias, co0, pix); break;
-                }
+                __syncwarp();                                      // previous chunk's reads of the staging tile are done
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
+                        make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                __syncwarp();
+                const int co = t.nb * P.bn + c * 16 + ((lane & 3) << 2);
+                cv_epilogue_half(P, stage, sbias, co, pix, inside_mask, lane);
             }
             if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
         }
@@ -448,17 +564,26 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.a_stage_bytes = p.a_plane_bytes * p.n_planes;
     p.b_plane_bytes = (uint32_t)bn * 128;
     p.b_stage_bytes = p.b_plane_bytes * p.n_planes;
-    // ring depths: two activation stages (three when the weight tiles are small), every remaining byte goes to the weight
-    // ring, whose entries are single plane tiles so that many small loads are in flight
-    p.n_a_stages = 2;
-    if (3 * (size_t)p.a_stage_bytes + 6 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
-    p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
-    if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
-    if (p.n_b_stages < 2) {
-        delete pl;
-        return RPE_ERR_INVALID_ARG;
-    }
     const int taps = d->kh * d->kw;
+    // Weights resident in shared memory when the whole set fits beside two activation stages (small layers: every tile would
+    // otherwise re-stream them); else a ring whose entries are single plane tiles, so that many small loads are in flight.
+    size_t total_b = 0;
+    for (int s = 0; s < d->n_sources; ++s) total_b += (size_t)((d->src[s].c_count + kCvBK - 1) / kCvBK) * taps * p.n_planes * p.b_plane_bytes;
+    p.resident_b = (n_blocks == 1 && total_b + 2 * (size_t)p.a_stage_bytes <= (size_t)kCvSmemData) ? 1 : 0;
+    if (p.resident_b) {
+        p.n_a_stages = (int)(((size_t)kCvSmemData - total_b) / p.a_stage_bytes);
+        if (p.n_a_stages > kCvMaxAStages) p.n_a_stages = kCvMaxAStages;
+        p.n_b_stages = 1;
+    } else {
+        p.n_a_stages = 2;
+        if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
+        p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
+        if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
+        if (p.n_b_stages < 2) {
+            delete pl;
+            return RPE_ERR_INVALID_ARG;
+        }
+    }
     double macs = 0.0;
     for (int s = 0; s < d->n_sources; ++s) {
         const rpe_conv_source &sc = d->src[s];
@@ -469,6 +594,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
             return RPE_ERR_INVALID_ARG;
         }
         p.cblocks[s] = (sc.c_count + kCvBK - 1) / kCvBK;
+        p.cb_base[s] = s == 0 ? 0 : p.cb_base[s - 1] + p.cblocks[s - 1];
         p.ksteps_last[s] = (sc.c_count - (p.cblocks[s] - 1) * kCvBK) / 16;
         macs += (double)sc.c_count * taps;
         for (int pln = 0; pln < p.n_planes; ++pln) {
@@ -520,6 +646,17 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.out_f32 = d->out_f32, p.f32_ld = d->f32_ld, p.f32_off = d->f32_offset;
     p.out_hi = reinterpret_cast<__nv_bfloat16 *>(d->out_hi), p.out_lo = reinterpret_cast<__nv_bfloat16 *>(d->out_lo);
     p.bf_ld = d->bf_ld, p.bf_off = d->bf_offset;
+    p.mode = d->mode, p.aux = d->aux, p.aux_ld = d->aux_ld, p.aux2 = d->aux2, p.aux2_ld = d->aux2_ld;
+    if (p.mode != 0) {
+        // GRU epilogues: channel groups of 4 never straddle the z|r boundary; state tensors must be 16-byte addressable
+        const bool ok = (p.mode == 1 || p.mode == 2) && d->aux && aligned16(d->aux) && (d->aux_ld % 4) == 0 && d->out_hi && d->out_lo &&
+                        (d->cout % 8) == 0 && n_blocks == 1 &&
+                        (p.mode == 1 ? (d->out_f32 != nullptr) : (d->aux2 != nullptr && aligned16(d->aux2) && (d->aux2_ld % 4) == 0));
+        if (!ok) {
+            delete pl;
+            return RPE_ERR_INVALID_ARG;
+        }
+    }
     pl->flops = 2.0 * macs * (double)d->cout * (double)d->N * OH * OW * (p.n_planes == 2 ? 3.0 : 1.0);
     const int tiles = p.N * p.tiles_min * p.tiles_maj * p.n_blocks;
     pl->grid = sm_count() < tiles ? sm_count() : tiles;

@@ -58,44 +58,50 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const float *__restri
     }
 }
 
-// coords1 += delta (NHWC fp32, 2 of `d_ld` channels; skipped when delta == nullptr); flow = coords1 - coords0 with
-// coords0 = pixel grid; writes (i) the 7x7 im2col of the flow (98 of `col_ld` channels, tap-major: ch = (ky*7+kx)*2 + c)
-// as split planes and (ii) the flow itself into 2 channels at `x_off` of the GRU input tensor.
-__global__ void __launch_bounds__(256) flow_step_kernel(float *__restrict__ coords1, const float *__restrict__ delta, int d_ld,
-                                                        __nv_bfloat16 *__restrict__ col_hi, __nv_bfloat16 *__restrict__ col_lo, int col_ld,
-                                                        __nv_bfloat16 *__restrict__ x_hi, __nv_bfloat16 *__restrict__ x_lo, int x_ld,
-                                                        int x_off, int h, int w, int phase) {
+// coords1 += delta (NHWC fp32, 2 of `d_ld` channels): raft.py:121.  Separate launch: the im2col below reads neighbours.
+__global__ void __launch_bounds__(256) coords_add_kernel(float *__restrict__ coords1, const float *__restrict__ delta, int d_ld, int hw) {
     const int n = blockIdx.y;
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int hw = h * w;
     if (p >= hw) return;
-    const int y = p / w, x = p - y * w;
     float *c1 = coords1 + (size_t)n * 2 * hw;
-    if (phase == 0) {                      // pass 1: coordinate update (separate launch: pass 2 reads neighbours)
-        if (delta) {
-            const float *d = delta + ((size_t)n * hw + p) * d_ld;
-            c1[p] = c1[p] + d[0];
-            c1[hw + p] = c1[hw + p] + d[1];
-        }
-        return;
+    const float *d = delta + ((size_t)n * hw + p) * d_ld;
+    c1[p] = c1[p] + d[0];
+    c1[hw + p] = c1[hw + p] + d[1];
+}
+
+// flow = coords1 - coords0 with coords0 = pixel grid; writes (i) the 7x7 im2col of the flow (98 of `col_ld` channels,
+// tap-major: ch = (ky*7+kx)*2 + c) as split planes and (ii) the flow itself into 2 channels at `x_off` of the GRU input
+// tensor.  One thread = one (pixel, tap): consecutive threads write consecutive 4-byte (fx, fy) pairs.
+__global__ void __launch_bounds__(256) flow_im2col_kernel(const float *__restrict__ coords1, __nv_bfloat16 *__restrict__ col_hi,
+                                                          __nv_bfloat16 *__restrict__ col_lo, int col_ld, __nv_bfloat16 *__restrict__ x_hi,
+                                                          __nv_bfloat16 *__restrict__ x_lo, int x_ld, int x_off, int h, int w,
+                                                          long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int tap = (int)(i % 49);
+    const long long pix = i / 49;
+    const int hw = h * w;
+    const int n = (int)(pix / hw);
+    const int p = (int)(pix - (long long)n * hw);
+    const int y = p / w, x = p - y * w;
+    const int ky = tap / 7, kx = tap - ky * 7;
+    const int yy = y + ky - 3, xx = x + kx - 3;
+    float fx = 0.0f, fy = 0.0f;
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+        const float *c1 = coords1 + (size_t)n * 2 * hw;
+        fx = __ldg(c1 + yy * w + xx) - (float)xx;
+        fy = __ldg(c1 + hw + yy * w + xx) - (float)yy;
     }
-    const size_t pix = (size_t)n * hw + p;
-    for (int ky = 0; ky < 7; ++ky) {
-        for (int kx = 0; kx < 7; ++kx) {
-            const int yy = y + ky - 3, xx = x + kx - 3;
-            float fx = 0.0f, fy = 0.0f;
-            if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
-                fx = c1[yy * w + xx] - (float)xx;
-                fy = c1[hw + yy * w + xx] - (float)yy;
-            }
-            const size_t o = pix * col_ld + (ky * 7 + kx) * 2;
-            split_store(fx, col_hi, col_lo, o);
-            split_store(fy, col_hi, col_lo, o + 1);
-        }
+    const __nv_bfloat16 hx = __float2bfloat16_rn(fx), hy = __float2bfloat16_rn(fy);
+    const __nv_bfloat162 hi2 = __halves2bfloat162(hx, hy);
+    const __nv_bfloat162 lo2 = __halves2bfloat162(__float2bfloat16_rn(fx - __bfloat162float(hx)), __float2bfloat16_rn(fy - __bfloat162float(hy)));
+    const size_t o = (size_t)pix * col_ld + tap * 2;
+    *reinterpret_cast<__nv_bfloat162 *>(col_hi + o) = hi2;
+    *reinterpret_cast<__nv_bfloat162 *>(col_lo + o) = lo2;
+    if (tap == 24) {
+        *reinterpret_cast<__nv_bfloat162 *>(x_hi + (size_t)pix * x_ld + x_off) = hi2;
+        *reinterpret_cast<__nv_bfloat162 *>(x_lo + (size_t)pix * x_ld + x_off) = lo2;
     }
-    const float fx = c1[p] - (float)x, fy = c1[hw + p] - (float)y;
-    split_store(fx, x_hi, x_lo, pix * x_ld + x_off);
-    split_store(fy, x_hi, x_lo, pix * x_ld + x_off + 1);
 }
 
 // GRU gating.  zr: fp32 NHWC (.., 256) = [z | r] after sigmoid; h: fp32 NHWC (.., 128).
@@ -158,15 +164,19 @@ int rpe_nhwc_to_nchw(const float *x, float *out, int n, int C, int H, int W, int
 
 int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi, void *col_lo, int col_ld, void *x_hi, void *x_lo,
                   int x_ld, int x_off, int n, int h, int w, void *stream) {
-    if (!coords1 || !col_hi || !col_lo || !x_hi || !x_lo || n <= 0 || h <= 0 || w <= 0 || col_ld < 98) return RPE_ERR_INVALID_ARG;
-    dim3 grid((h * w + 255) / 256, n);
-    for (int phase = 0; phase < 2; ++phase) {
-        if (phase == 0 && !delta) continue;
-        rpe::flow_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(coords1, delta, delta_ld, (__nv_bfloat16 *)col_hi,
-                                                                     (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi,
-                                                                     (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w, phase);
+    if (!coords1 || !col_hi || !col_lo || !x_hi || !x_lo || n <= 0 || h <= 0 || w <= 0 || col_ld < 98 || (col_ld % 2) || (x_ld % 2) ||
+        (x_off % 2))
+        return RPE_ERR_INVALID_ARG;
+    if (delta) {
+        dim3 grid((h * w + 255) / 256, n);
+        rpe::coords_add_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(coords1, delta, delta_ld, h * w);
         RPE_LAUNCH_CHECK();
     }
+    const long long total = (long long)n * h * w * 49;
+    rpe::flow_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
+        total);
+    RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
 

@@ -44,11 +44,16 @@ class ConvPlan:
     """One convolution bound to its input / output buffers.  ``inputs``: [(Planes, c_offset, c_count, (w_hi, w_lo))]."""
 
     def __init__(self, name, inputs, dims, kh, kw, cout, act="none", bias=None, stride=1, out_f32=None, f32_off=0, out_planes=None,
-                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False):
+                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None):
         n, h, w = dims
         cout_pad = (cout + 15) // 16 * 16
         d = _lib.ConvDesc()
-        self._keep = [bias, pre, res, out_f32, out_planes]
+        self._keep = [bias, pre, res, out_f32, out_planes, aux, aux2]
+        d.mode = mode
+        if aux is not None:
+            d.aux, d.aux_ld = aux.data_ptr(), aux.shape[-1]
+        if aux2 is not None:
+            d.aux2, d.aux2_ld = aux2.data_ptr(), aux2.shape[-1]
         for k, (planes, c_off, c_cnt, (w_hi, w_lo)) in enumerate(inputs):
             assert planes.shape[1:3] == (h, w) and planes.shape[0] >= n, f"{name}: source {k} has shape {planes.shape}, expected {(n, h, w)}"
             assert w_hi.shape[1] == cout_pad, f"{name}: weight packed for cout_pad {w_hi.shape[1]}, plan needs {cout_pad}"

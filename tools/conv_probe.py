@@ -15,10 +15,10 @@ SHAPES = [
     ("convc2 3x3 256->192", 16, 64, 80, [256], 192, 3, 3, 1),
     ("convf2 3x3 128->64", 16, 64, 80, [128], 64, 3, 3, 1),
     ("conv   3x3 256->126", 16, 64, 80, [256], 126, 3, 3, 1),
-    ("zr1    1x5 384->256", 16, 64, 80, [128, 256], 256, 1, 5, 1),
-    ("q1     1x5 384->128", 16, 64, 80, [128, 256], 128, 1, 5, 1),
-    ("zr2    5x1 384->256", 16, 64, 80, [128, 256], 256, 5, 1, 1),
-    ("q2     5x1 384->128", 16, 64, 80, [128, 256], 128, 5, 1, 1),
+    ("zr1    1x5 256->256", 16, 64, 80, [128, 128], 256, 1, 5, 1),
+    ("q1     1x5 256->128", 16, 64, 80, [128, 128], 128, 1, 5, 1),
+    ("zr2    5x1 256->256", 16, 64, 80, [128, 128], 256, 5, 1, 1),
+    ("q2     5x1 256->128", 16, 64, 80, [128, 128], 128, 5, 1, 1),
     ("fh1    3x3 128->256", 16, 64, 80, [128], 256, 3, 3, 1),
     ("fh2    3x3 256->2", 16, 64, 80, [256], 2, 3, 3, 1),
     ("mask2  1x1 256->576", 16, 64, 80, [256], 576, 1, 1, 1),
@@ -51,8 +51,19 @@ def main():
             srcs.append((pl, 0, cin, wt))
         oh, ow = (h + 2 * (kh // 2) - kh) // stride + 1, (w + 2 * (kw // 2) - kw) // stride + 1
         outp = tc.Planes(n, oh, ow, cout_pad, dev)
-        plan = tc.ConvPlan(name, srcs, (n, h, w), kh, kw, cout, "relu", bias=torch.zeros(cout, device=dev), stride=stride,
-                           out_planes=outp, single_pass=single)
+        extra = {}
+        act = "relu"
+        if name.startswith("zr") and not single:        # fused GRU epilogues as used by the update operator
+            hbuf = torch.randn(n, oh, ow, 128, device=dev)
+            outp = tc.Planes(n, oh, ow, 128, dev)
+            extra = dict(mode=1, aux=hbuf, out_f32=torch.zeros(n, oh, ow, 128, device=dev), pre=torch.randn(n, oh, ow, 256, device=dev))
+            act = "sigmoid"
+        elif name.startswith("q") and not single:
+            extra = dict(mode=2, aux=torch.randn(n, oh, ow, 128, device=dev), aux2=torch.rand(n, oh, ow, 128, device=dev),
+                         pre=torch.randn(n, oh, ow, 128, device=dev))
+            act = "tanh"
+        plan = tc.ConvPlan(name, srcs, (n, h, w), kh, kw, cout, act, bias=torch.zeros(cout, device=dev), stride=stride,
+                           out_planes=outp, single_pass=single, **extra)
         for _ in range(0 if reps == 1 else 3):
             plan.run()
         torch.cuda.synchronize()
