@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the f2f pose path (BASELINE.json metric: f2f frame-pairs/sec @640x512 stereo).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp32|tf32|fp16|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16x3|fp32|tf32|fp16|bf16]
 
 A step = one pass of the hot path over one batch of synthetic input: a 65-frame 640x512 stereo sequence
 (64 frame pairs) per rank (weak scaling; pairs are independent in f2f).
@@ -176,8 +176,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "tf32", "fp16", "bf16"])
-    ap.add_argument("--chunk", type=int, default=8)
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "tf32", "fp16", "bf16"],
+                    help="bf16x3 (default): whole trunk on the hand-written tcgen05 kernels, fp32-equivalent split arithmetic "
+                         "(parity-gated); fp32: cuDNN fp32 trunk; tf32 / fp16 / bf16: cuDNN reduced precision (not parity-gated)")
+    ap.add_argument("--chunk", type=int, default=11, help="frames per engine chunk (11 -> 880 conv tiles = 5.95 waves of 148 SMs)")
     ap.add_argument("--pairs", type=int, default=64)
     ap.add_argument("--graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,24 +297,49 @@ def main():
 
     pairs_total = world * args.pairs * args.steps
     value = pairs_total / (ms / 1e3)
-    hbm_peak, peak_src = 6650.0, "fallback"
+    hbm_peak, tc_peak, peak_src = 6650.0, 1400.0, "fallback"     # B200_PROFILING.md fallbacks: copy GB/s, sustained cuBLAS bf16 TFLOP/s
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         hbm_peak, peak_src = float(mp["hbm_gbs"]), "measured"
+        tc_peak = float(mp.get("bf16_tflops_sustained", mp.get("bf16_tflops", tc_peak)))
     except (OSError, KeyError, ValueError):
         pass
-    # dominant hand-written kernel of the step -> roofline
-    own = {k: v for k, v in stage.items() if k in ALG_BYTES}
-    dom = max(own, key=lambda k: own[k]["total_ms"])
-    d = own[dom]
-    per_launch_units = d["units"] / d["launches"]
-    if dom == "pose_solve":
-        alg = ALG_BYTES[dom] * evals_total / (args.pairs / args.chunk if args.pairs >= args.chunk else 1)
+    # per-kernel rooflines from the in-run CUDA-event timers.  Convolution stages carry their executed tensor-core flops
+    # as "units" (3 bf16 MMAs per multiply-add in the bf16x3 split); the algorithmic (fp32-equivalent) flops are a third.
+    split = 3.0 if args.precision == "bf16x3" else 1.0
+    kernels = {}
+    for name, d in stage.items():
+        secs = d["total_ms"] * 1e-3
+        if name.startswith("conv_tc"):
+            kernels[name] = {"bound": "tensor", "unit": "TFLOP/s", "achieved": d["units"] / split / secs / 1e12,
+                             "executed": d["units"] / secs / 1e12, "peak": tc_peak}
+        elif name in ALG_BYTES:
+            units = evals_total * args.steps if name == "pose_solve" else d["units"]
+            kernels[name] = {"bound": "hbm", "unit": "GB/s", "achieved": ALG_BYTES[name] * units / secs / 1e9, "peak": hbm_peak}
+        else:
+            continue
+        kernels[name]["frac"] = kernels[name]["achieved"] / kernels[name]["peak"]
+        kernels[name]["share_of_step"] = d["total_ms"] / ms
+    conv = [k for k in stage if k.startswith("conv_tc")]
+    own = {k: v for k, v in stage.items() if k in kernels and not k.startswith("conv_tc")}
+    conv_ms = sum(stage[k]["total_ms"] for k in conv)
+    if conv and conv_ms >= max([v["total_ms"] for v in own.values()] + [0.0]):
+        # dominant kernel = conv_bf16_kernel (tcgen05 implicit-GEMM convolution; update operator + encoders)
+        flops_exec = sum(stage[k]["units"] for k in conv)
+        n_launch = sum(stage[k]["launches"] for k in conv)
+        achieved = flops_exec / split / (conv_ms * 1e-3) / 1e12
+        roofline = {"kernel": "conv_bf16_kernel", "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src,
+                    "avg_launch_us": 1e3 * conv_ms / n_launch, "algorithmic_flops_per_launch": flops_exec / split / n_launch,
+                    "executed_tflops": flops_exec / (conv_ms * 1e-3) / 1e12, "executed_frac": flops_exec / (conv_ms * 1e-3) / 1e12 / tc_peak,
+                    "note": "algorithmic = fp32-equivalent convolution flops; the bf16x3 split executes 3 bf16 MMAs per multiply-add, "
+                            "so executed_frac is the tensor-pipe figure and frac <= 1/3 by construction"}
     else:
-        alg = ALG_BYTES[dom] * per_launch_units
-    achieved = alg / (d["avg_us"] * 1e-6) / 1e9
-    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_us": d["avg_us"], "algorithmic_bytes_per_launch": alg}
+        dom = max(own, key=lambda k: own[k]["total_ms"])
+        d = own[dom]
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src, "avg_launch_us": d["avg_us"],
+                    "algorithmic_bytes_per_launch": kernels[dom]["achieved"] * 1e9 * d["avg_us"] * 1e-6}
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32-equivalent split, fp32 accumulate)", "tf32": "tf32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
@@ -325,7 +352,7 @@ def main():
             "e2e": {"value": pairs_total / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(world * args.pairs * 13 * 4), "input": "pinned uint8 frames + bool masks",
                     "failed_pairs": int(failed.sum())},
-            "roofline": roofline, "stages": stage, "lbfgs_evals_per_pair": evals_total / args.pairs}
+            "roofline": roofline, "kernels": kernels, "stages": stage, "lbfgs_evals_per_pair": evals_total / args.pairs}
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(L, R, M, seq)
         line["cpu_baseline"] = cb

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -230,12 +231,20 @@ __device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const floa
 
 struct CvTile {
     int nb, img, omin0, omaj0;
+    bool ghost;                                        // pair mode: padding tile of an odd tile count (computed, never stored)
 };
-__device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
+// Work unit u of CTA `rank`: a single tile, or (pair mode) one of two adjacent pixel tiles that share the weight block nb.
+template <bool kPair>
+__device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int u, int rank) {
     CvTile t;
-    t.nb = tile % P.n_blocks;
-    const int t2 = tile / P.n_blocks;
+    t.nb = u % P.n_blocks;
+    int t2 = u / P.n_blocks;
     const int per_img = P.tiles_min * P.tiles_maj;
+    t.ghost = false;
+    if (kPair) {
+        t2 = 2 * t2 + rank;
+        if (t2 >= P.N * per_img) t2 = P.N * per_img - 1, t.ghost = true;
+    }
     t.img = t2 / per_img;
     const int tr = t2 - t.img * per_img;
     const int tj = tr / P.tiles_min;
@@ -244,7 +253,31 @@ __device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int tile) {
     return t;
 }
 
-__global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_constant__ ConvParams P) {
+template <bool kPair>
+__device__ __forceinline__ void cv_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (kPair) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+    }
+}
+template <bool kPair>
+__device__ __forceinline__ void cv_commit(uint64_t *bar) {
+    if (kPair) umma_commit_pair(bar, 3);
+    else umma_commit(bar);
+}
+
+// In pair mode (cta_group::2) two CTAs of a cluster own two adjacent pixel tiles: each loads its own activations and HALF of
+// the weight tile, the leader (rank 0) issues M = 256 MMAs that read both shared memories and write both tensor memories,
+// and every TMA load of either CTA counts its bytes on the leader's "full" barrier; the MMA commits are multicast to the
+// "empty" / "accumulator full" barriers of both CTAs.
+template <bool kPair>
+__device__ __forceinline__ void conv_body(const ConvParams &P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *sA = smem;
@@ -262,8 +295,13 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
     for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_tiles = P.N * P.tiles_min * P.tiles_maj * P.n_blocks;
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    const int px_tiles = P.N * P.tiles_min * P.tiles_maj;
+    const int num_units = (kPair ? (px_tiles + 1) / 2 : px_tiles) * P.n_blocks;
+    const int u_first = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int u_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int a_units = P.reuse ? 1 : P.kmaj;        // slabs per filter column
+    const uint32_t load_mult = kPair ? 2u : 1u;      // the leader's barriers count the bytes of both CTAs
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < P.n_src; ++s)
@@ -283,16 +321,22 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         }
         for (int i = 0; i < kCvAcc; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kCvEpiWarps);
+            mbar_init(&tmem_empty[i], kCvEpiWarps * load_mult);
         }
         fence_barrier_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr, 512);
-        tmem_relinquish();
+        if (kPair) {
+            tmem_alloc_pair(tmem_ptr, 512);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_ptr, 512);
+            tmem_relinquish();
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all();
+    else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -301,19 +345,24 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const CvTile t = cv_decode(P, tile);
+            for (int u = u_first; u < num_units; u += u_step) {
+                const CvTile t = cv_decode<kPair>(P, u, rank);
                 for (int s = 0; s < P.n_src; ++s)
                     for (int cb = 0; cb < P.cblocks[s]; ++cb)
                         for (int tm = 0; tm < P.kmin; ++tm)
-                            for (int u = 0; u < a_units; ++u) {
+                            for (int au = 0; au < a_units; ++au) {
                                 mbar_wait(&a_empty[stage], phase ^ 1);
-                                mbar_expect_tx(&a_full[stage], P.a_plane_bytes * P.n_planes);
+                                if (rank == 0) mbar_expect_tx(&a_full[stage], P.a_plane_bytes * P.n_planes * load_mult);
                                 const int cmin = t.omin0 * P.stride + tm - P.pad_min;
-                                const int cmaj = t.omaj0 * P.stride + (P.reuse ? 0 : u) - P.pad_maj;
+                                const int cmaj = t.omaj0 * P.stride + (P.reuse ? 0 : au) - P.pad_maj;
                                 uint8_t *dst = sA + (size_t)stage * P.a_stage_bytes;
-                                for (int p = 0; p < P.n_planes; ++p)
-                                    tma_load_4d(dst + p * P.a_plane_bytes, &P.amap[s][p], &a_full[stage], cb * kCvBK, cmin, cmaj, t.img);
+                                for (int p = 0; p < P.n_planes; ++p) {
+                                    if (kPair)
+                                        tma_load_4d_pair(dst + p * P.a_plane_bytes, &P.amap[s][p], mapa_shared(smem_u32(&a_full[stage]), 0),
+                                                         cb * kCvBK, cmin, cmaj, t.img);
+                                    else
+                                        tma_load_4d(dst + p * P.a_plane_bytes, &P.amap[s][p], &a_full[stage], cb * kCvBK, cmin, cmaj, t.img);
+                                }
                                 if (++stage == P.n_a_stages) stage = 0, phase ^= 1;
                             }
             }
@@ -322,24 +371,27 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         // ===================== weight producer =====================
         if (elect_one()) {
             const int taps = P.kmin * P.kmaj;
+            const int brow = kPair ? rank * (P.bn >> 1) : 0;          // this CTA's half of the weight rows
             if (P.resident_b) {
                 // the whole weight set fits: one load per CTA, [source K block][tap][plane] tiles
                 uint32_t total = 0;
                 for (int s = 0; s < P.n_src; ++s) total += (uint32_t)P.cblocks[s] * taps * P.n_planes * P.b_plane_bytes;
-                if (blockIdx.x < num_tiles) {
-                    mbar_expect_tx(&b_full[0], total);
+                if (u_first < num_units) {
+                    if (rank == 0) mbar_expect_tx(&b_full[0], total * load_mult);
                     for (int s = 0; s < P.n_src; ++s)
                         for (int cb = 0; cb < P.cblocks[s]; ++cb)
                             for (int tap = 0; tap < taps; ++tap)
-                                for (int p = 0; p < P.n_planes; ++p)
-                                    tma_load_3d(sB + (size_t)(((P.cb_base[s] + cb) * taps + tap) * P.n_planes + p) * P.b_plane_bytes,
-                                                &P.wmap[s][p], &b_full[0], cb * kCvBK, 0, tap);
+                                for (int p = 0; p < P.n_planes; ++p) {
+                                    uint8_t *dst = sB + (size_t)(((P.cb_base[s] + cb) * taps + tap) * P.n_planes + p) * P.b_plane_bytes;
+                                    if (kPair) tma_load_3d_pair(dst, &P.wmap[s][p], mapa_shared(smem_u32(&b_full[0]), 0), cb * kCvBK, brow, tap);
+                                    else tma_load_3d(dst, &P.wmap[s][p], &b_full[0], cb * kCvBK, 0, tap);
+                                }
                 }
             } else {
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                    const CvTile t = cv_decode(P, tile);
+                for (int u = u_first; u < num_units; u += u_step) {
+                    const int nb = u % P.n_blocks;
                     for (int s = 0; s < P.n_src; ++s)
                         for (int cb = 0; cb < P.cblocks[s]; ++cb)
                             for (int tm = 0; tm < P.kmin; ++tm)
@@ -347,26 +399,31 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                                     const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
                                     for (int p = 0; p < P.n_planes; ++p) {          // one ring entry per plane tile
                                         mbar_wait(&b_empty[stage], phase ^ 1);
-                                        mbar_expect_tx(&b_full[stage], P.b_plane_bytes);
-                                        tma_load_3d(sB + (size_t)stage * P.b_plane_bytes, &P.wmap[s][p], &b_full[stage], cb * kCvBK,
-                                                    t.nb * P.bn, tap);
+                                        if (rank == 0) mbar_expect_tx(&b_full[stage], P.b_plane_bytes * load_mult);
+                                        uint8_t *dst = sB + (size_t)stage * P.b_plane_bytes;
+                                        if (kPair)
+                                            tma_load_3d_pair(dst, &P.wmap[s][p], mapa_shared(smem_u32(&b_full[stage]), 0), cb * kCvBK,
+                                                             nb * P.bn + brow, tap);
+                                        else
+                                            tma_load_3d(dst, &P.wmap[s][p], &b_full[stage], cb * kCvBK, nb * P.bn, tap);
                                         if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
                                     }
                                 }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+    } else if (warp == 1 && rank == 0) {
+        // ===================== MMA issuer (the leader CTA in pair mode) =====================
         if (elect_one()) {
-            // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128 (256 across a CTA pair)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+                                   ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             bool b_ready = false;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int u = u_first; u < num_units; u += u_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kCvMaxBN);
@@ -391,42 +448,42 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                                     const uint32_t b0 = smem_u32(sB) + (uint32_t)(((P.cb_base[s] + cb) * (P.kmin * P.kmaj) + tap) * P.n_planes) * P.b_plane_bytes;
                                     const uint64_t db_hi = cv_sw128_desc(b0);
                                     for (int k = 0; k < ksteps; ++k) {
-                                        umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                        cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
                                         accumulate = 1;
                                     }
                                     if (P.n_planes == 2) {
                                         const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes), db_lo = cv_sw128_desc(b0 + P.b_plane_bytes);
-                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
                                     }
                                 } else {
                                     mbar_wait(&b_full[sb], pb);
                                     tcgen05_fence_after();
                                     const uint64_t db_hi = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
                                     for (int k = 0; k < ksteps; ++k) {
-                                        umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                        cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
                                         accumulate = 1;
                                     }
                                     if (P.n_planes == 2) {
                                         const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes);
-                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                        umma_commit(&b_empty[sb]);
+                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                        cv_commit<kPair>(&b_empty[sb]);
                                         if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
                                         mbar_wait(&b_full[sb], pb);
                                         tcgen05_fence_after();
                                         const uint64_t db_lo = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
-                                        for (int k = 0; k < ksteps; ++k) umma_bf16(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
                                     }
-                                    umma_commit(&b_empty[sb]);
+                                    cv_commit<kPair>(&b_empty[sb]);
                                     if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
                                 }
                                 if (!P.reuse || tj == P.kmaj - 1) {
-                                    umma_commit(&a_empty[sa]);
+                                    cv_commit<kPair>(&a_empty[sa]);
                                     if (++sa == P.n_a_stages) sa = 0, pa ^= 1;
                                 }
                             }
                     }
-                umma_commit(&tmem_full[acc]);
+                cv_commit<kPair>(&tmem_full[acc]);
                 if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
             }
         }
@@ -439,8 +496,8 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         float *stage = sstage + (warp - 4) * (32 * 16);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const CvTile t = cv_decode(P, tile);
+        for (int u = u_first; u < num_units; u += u_step) {
+            const CvTile t = cv_decode<kPair>(P, u, rank);
             size_t pix[4];
             uint32_t inside_mask = 0;
 #pragma unroll
@@ -449,17 +506,21 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                 const int gi = m >> 3, mi = m & 7;                 // (major, minor) position inside the tile
                 const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
                 const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
-                if (y < P.OH && x < P.OW) inside_mask |= 1u << it;
+                if (y < P.OH && x < P.OW && !t.ghost) inside_mask |= 1u << it;
                 pix[it] = ((size_t)t.img * P.OH + y) * P.OW + x;
             }
             mbar_wait(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
+            const uint32_t empty_addr = kPair ? mapa_shared(smem_u32(&tmem_empty[acc]), 0) : 0u;
             const int n_chunks = P.bn / 16;
             const int c_begin = chalf * ((n_chunks + 1) / 2), c_end = chalf == 0 ? (n_chunks + 1) / 2 : n_chunks;
             if (c_begin >= c_end) {                                // nothing to drain (bn = 16): just release the accumulator
                 tcgen05_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                if (lane == 0) {
+                    if (kPair) mbar_arrive_cluster(empty_addr);
+                    else mbar_arrive(&tmem_empty[acc]);
+                }
             }
             for (int c = c_begin; c < c_end; ++c) {
                 uint32_t v[16];
@@ -475,7 +536,10 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
                 if (c + 1 == c_end) {
                     tcgen05_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) {
+                        if (kPair) mbar_arrive_cluster(empty_addr);
+                        else mbar_arrive(&tmem_empty[acc]);
+                    }
                 }
                 __syncwarp();                                      // previous chunk's reads of the staging tile are done
 #pragma unroll
@@ -490,8 +554,18 @@ __global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_c
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (kPair) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 2) {
+        if (kPair) tmem_dealloc_pair(tmem_base, 512);
+        else tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_constant__ ConvParams P) { conv_body<false>(P); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_bf16_pair_kernel(const __grid_constant__ ConvParams P) {
+    conv_body<true>(P);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,6 +586,7 @@ static int cv_load_encode() {
 struct ConvPlan {
     ConvParams p;
     int grid;
+    bool pair;             // CTA-pair kernel (cta_group::2)
     double flops;          // real multiply-adds x 2 of one run (all products of the split arithmetic)
 };
 
@@ -560,9 +635,14 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     const int slab_rows = p.reuse ? 16 + p.kmaj - 1 : 16;
     p.n_src = d->n_sources;
     p.n_planes = d->src[0].act_lo ? 2 : 1;
+    // CTA pairs (cta_group::2): each CTA of a 2-cluster loads half of every weight tile.  RPE_CONV_PAIR=0 disables.
+    const char *pair_env = getenv("RPE_CONV_PAIR");
+    const int px_tiles = d->N * (((orient == 0 ? OW : OH) + 7) / 8) * (((orient == 0 ? OH : OW) + 15) / 16);
+    pl->pair = !(pair_env && pair_env[0] == '0') && (bn % 32 == 0) && px_tiles >= 2 && sm_count() >= 2;
+    const int b_rows = pl->pair ? bn / 2 : bn;
     p.a_plane_bytes = (uint32_t)slab_rows * 8 * 128;
     p.a_stage_bytes = p.a_plane_bytes * p.n_planes;
-    p.b_plane_bytes = (uint32_t)bn * 128;
+    p.b_plane_bytes = (uint32_t)b_rows * 128;
     p.b_stage_bytes = p.b_plane_bytes * p.n_planes;
     const int taps = d->kh * d->kw;
     // Weights resident in shared memory when the whole set fits beside two activation stages (small layers: every tile would
@@ -624,7 +704,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
             {   // weights: (Cin_s, Cout_pad, taps) bf16 with row pitch w_cstride, box (64, bn, 1)
                 cuuint64_t dims[3] = {(cuuint64_t)sc.c_count, (cuuint64_t)d->cout_pad, (cuuint64_t)taps};
                 cuuint64_t strides[2] = {(cuuint64_t)sc.w_cstride * 2, (cuuint64_t)sc.w_cstride * 2 * d->cout_pad};
-                cuuint32_t box[3] = {kCvBK, (cuuint32_t)bn, 1};
+                cuuint32_t box[3] = {kCvBK, (cuuint32_t)b_rows, 1};
                 cuuint32_t es[3] = {1, 1, 1};
                 CUresult r = g_cv_encode(&p.wmap[s][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(wgt), dims, strides, box,
                                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -658,12 +738,20 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         }
     }
     pl->flops = 2.0 * macs * (double)d->cout * (double)d->N * OH * OW * (p.n_planes == 2 ? 3.0 : 1.0);
-    const int tiles = p.N * p.tiles_min * p.tiles_maj * p.n_blocks;
-    pl->grid = sm_count() < tiles ? sm_count() : tiles;
-    if (pl->grid < 1) pl->grid = 1;
+    if (pl->pair) {
+        const int units = ((px_tiles + 1) / 2) * p.n_blocks;
+        int clusters = sm_count() / 2;
+        if (clusters > units) clusters = units;
+        pl->grid = 2 * (clusters < 1 ? 1 : clusters);
+    } else {
+        const int tiles = px_tiles * p.n_blocks;
+        pl->grid = sm_count() < tiles ? sm_count() : tiles;
+        if (pl->grid < 1) pl->grid = 1;
+    }
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
         if (e != cudaSuccess) {
             delete pl;
             return cuda_fail(e);
@@ -678,7 +766,8 @@ int rpe_conv_plan_run(void *plan, void *stream) {
     using namespace rpe;
     if (!plan) return RPE_ERR_INVALID_ARG;
     ConvPlan *pl = reinterpret_cast<ConvPlan *>(plan);
-    conv_bf16_kernel<<<pl->grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(pl->p);
+    if (pl->pair) conv_bf16_pair_kernel<<<pl->grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(pl->p);
+    else conv_bf16_kernel<<<pl->grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(pl->p);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
