@@ -6,7 +6,7 @@ GEMM on the tensor cores, NHWC activations, no materialised concatenations and t
 pre-allocated device buffers (one set per batch shape)."""
 import torch
 
-from .... import _lib
+from .... import _lib, ops
 from ....ops import _p, _stream, _timed, check
 from ....tc import ConvPlan, Planes, pack_weight
 
@@ -115,9 +115,7 @@ class UpdateTC:
             with _timed("flow_step", B):
                 check(l.rpe_flow_step(_p(coords1), _p(st["delta"]) if it > 0 else None, 4, _p(st["col"].hi), _p(st["col"].lo), 128,
                                       _p(st["mot"].hi), _p(st["mot"].lo), 128, 126, B, h, w, s), "rpe_flow_step")
-            with _timed("corr_lookup", B):
-                check(l.rpe_corr_lookup_nhwc_bf16(_p(corr_pyr.pyramid), _p(coords1), _p(st["corr"].hi), _p(st["corr"].lo), 384, B, h, w,
-                                                  corr_pyr.num_levels, corr_pyr.radius, s), "rpe_corr_lookup_nhwc_bf16")
+            ops.corr_lookup_planes(corr_pyr, coords1, st["corr"])
             for name in ("convc1", "convc2", "convf1", "convf2", "conv", "zr1", "q1", "zr2", "q2", "fh1", "fh2"):
                 self._run(st, name)
         coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))

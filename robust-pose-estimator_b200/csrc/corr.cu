@@ -360,6 +360,108 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Window lookup for the tensor-core update operator: output NHWC bf16 hi/lo planes, (L*(2r+1)^2) contiguous channels per
+// query -- no transposition is needed, so one WARP owns one query: all L*(2r+2)^2 neighbourhood loads of the query are issued
+// back to back (up to 13 per lane in flight: a single memory round trip per query instead of one per level), staged in a
+// private shared-memory patch, then the lanes evaluate two adjacent channels each and store packed bf16 pairs.
+// Coordinate arithmetic and interpolation order are those of corr_lookup_kernel (bit-identical values before the split).
+// ------------------------------------------------------------------------------------------------
+constexpr int kLkWarps = 8;
+constexpr int kLkMaxElems = 4 * kMaxWin * kMaxWin;     // 400 patch values per query
+constexpr int kLkRounds = (kLkMaxElems + 31) / 32;     // 13
+
+template <int kRadius>      // compile-time radius: the index arithmetic below is all divisions by window sizes
+__global__ void __launch_bounds__(32 * kLkWarps) corr_lookup_nhwc_kernel(const float *__restrict__ pyr, PyrDims d,
+                                                                         const float *__restrict__ coords,
+                                                                         __nv_bfloat16 *__restrict__ out_hi,
+                                                                         __nv_bfloat16 *__restrict__ out_lo, int ld, int Q,
+                                                                         long long total_q, int radius_rt) {
+    __shared__ float s_patch[kLkWarps][kLkMaxElems];
+    __shared__ float s_frac[kLkWarps][8];               // fx, fy per level
+    __shared__ int s_org[kLkWarps][8];                  // x0, y0 per level
+    __shared__ size_t s_off[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int radius = kRadius > 0 ? kRadius : radius_rt;
+    const int n = 2 * radius + 1, win = n + 1, ww = win * win, nn = n * n;
+    const int n_elems = d.levels * ww, nch = d.levels * nn;
+    const int h0 = d.h[0], w0 = d.w[0];                 // level l is (h0 >> l) x (w0 >> l)
+    if (threadIdx.x < 4) s_off[threadIdx.x] = d.off[threadIdx.x];
+    __syncthreads();
+    float *patch = s_patch[warp];
+    for (long long gq = (long long)blockIdx.x * kLkWarps + warp; gq < total_q; gq += (long long)gridDim.x * kLkWarps) {
+        const int b = (int)(gq / Q), q = (int)(gq - (long long)b * Q);
+        if (lane < d.levels) {
+            const int l = lane;
+            const float cx = __ldg(coords + ((size_t)b * 2 + 0) * Q + q);
+            const float cy = __ldg(coords + ((size_t)b * 2 + 1) * Q + q);
+            const int hl = h0 >> l, wl = w0 >> l;
+            const float inv = 1.0f / (float)(1 << l);
+            const float xc = __fmul_rn(cx, inv), yc = __fmul_rn(cy, inv);
+            const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, xc), (float)(wl - 1)), 1.0f);
+            const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, yc), (float)(hl - 1)), 1.0f);
+            const float ix = __fmul_rn(__fadd_rn(gx, 1.0f), (float)(wl - 1) * 0.5f);
+            const float iy = __fmul_rn(__fadd_rn(gy, 1.0f), (float)(hl - 1) * 0.5f);
+            const float x0f = floorf(ix), y0f = floorf(iy);
+            const float lim = 1.0e6f;
+            s_frac[warp][2 * l] = ix - x0f;
+            s_frac[warp][2 * l + 1] = iy - y0f;
+            s_org[warp][2 * l] = (int)fminf(fmaxf(x0f, -lim), lim) - radius;
+            s_org[warp][2 * l + 1] = (int)fminf(fmaxf(y0f, -lim), lim) - radius;
+        }
+        __syncwarp();
+        float v[kLkRounds];
+#pragma unroll
+        for (int k = 0; k < kLkRounds; ++k) {
+            const int e = lane + 32 * k;
+            v[k] = 0.0f;
+            if (e < n_elems) {
+                const int l = e / ww, r = e - l * ww;
+                const int ry = r / win, rx = r - ry * win;
+                const int hl = h0 >> l, wl = w0 >> l;
+                const int yy = s_org[warp][2 * l + 1] + ry, xx = s_org[warp][2 * l] + rx;
+                if (yy >= 0 && yy < hl && xx >= 0 && xx < wl)
+                    v[k] = __ldg(pyr + s_off[l] + (size_t)gq * (size_t)(hl * wl) + yy * wl + xx);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kLkRounds; ++k) {
+            const int e = lane + 32 * k;
+            if (e < n_elems) patch[e] = v[k];
+        }
+        __syncwarp();
+        const size_t obase = (size_t)gq * ld;
+        for (int c = 2 * lane; c < nch; c += 64) {
+            float o[2];
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int cc = c + t;
+                o[t] = 0.0f;
+                if (cc < nch) {
+                    const int l = cc / nn, e = cc - l * nn;
+                    const int i = e / n, j = e - i * n;          // i: x-offset index (slow), j: y-offset index (fast)
+                    const float fx = s_frac[warp][2 * l], fy = s_frac[warp][2 * l + 1];
+                    const float w00 = (1.0f - fy) * (1.0f - fx), w01 = (1.0f - fy) * fx, w10 = fy * (1.0f - fx), w11 = fy * fx;
+                    const float *pp = patch + l * ww + j * win + i;
+                    o[t] = pp[0] * w00 + pp[1] * w01 + pp[win] * w10 + pp[win + 1] * w11;
+                }
+            }
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(o[0]), h1 = __float2bfloat16_rn(o[1]);
+            const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+            const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(o[0] - __bfloat162float(h0)),
+                                                         __float2bfloat16_rn(o[1] - __bfloat162float(h1)));
+            if (c + 1 < nch) {
+                *reinterpret_cast<__nv_bfloat162 *>(out_hi + obase + c) = hh;
+                *reinterpret_cast<__nv_bfloat162 *>(out_lo + obase + c) = ll;
+            } else {
+                out_hi[obase + c] = h0;
+                out_lo[obase + c] = __low2bfloat16(ll);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ================================================================================================
 // Host side
 // ================================================================================================
@@ -503,6 +605,22 @@ static int corr_lookup_impl(const float *pyramid, const float *coords, float *ou
     PyrDims d = pyr_dims(B, h, w, num_levels);
     const int n = 2 * radius + 1;
     const int nch = num_levels * n * n;
+    if (out_hi && (nhwc_ld % 2) == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 3u) == 0 && (reinterpret_cast<uintptr_t>(out_lo) & 3u) == 0) {
+        const long long total_q = (long long)B * Q;
+        long long blocks = (total_q + kLkWarps - 1) / kLkWarps;
+        const long long cap = (long long)sm_count() * 8 * 4;
+        if (blocks > cap) blocks = cap;
+        if (radius == 4)
+            corr_lookup_nhwc_kernel<4><<<(unsigned)blocks, 32 * kLkWarps, 0, (cudaStream_t)stream>>>(
+                pyramid, d, coords, reinterpret_cast<__nv_bfloat16 *>(out_hi), reinterpret_cast<__nv_bfloat16 *>(out_lo), nhwc_ld, Q,
+                total_q, radius);
+        else
+            corr_lookup_nhwc_kernel<0><<<(unsigned)blocks, 32 * kLkWarps, 0, (cudaStream_t)stream>>>(
+                pyramid, d, coords, reinterpret_cast<__nv_bfloat16 *>(out_hi), reinterpret_cast<__nv_bfloat16 *>(out_lo), nhwc_ld, Q,
+                total_q, radius);
+        RPE_LAUNCH_CHECK();
+        return RPE_OK;
+    }
     const size_t smem = ((size_t)nch * (kLookupQ + 1) + 8 * kMaxWin * kMaxWin) * sizeof(float);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

@@ -297,6 +297,15 @@ class CorrPyramid:
         return out
 
 
+def corr_lookup_planes(pyr, coords, planes):
+    """rpe_corr_lookup_nhwc_bf16: CorrBlock.__call__ written as NHWC bf16 hi/lo planes (tc.Planes with >= 324 channels)."""
+    _chk(coords, torch.float32, "coords", (pyr.B, 2, pyr.h, pyr.w))
+    with _timed("corr_lookup", pyr.B):
+        check(_lib.lib().rpe_corr_lookup_nhwc_bf16(_p(pyr.pyramid), _p(coords), _p(planes.hi), _p(planes.lo), planes.c, pyr.B, pyr.h, pyr.w,
+                                                   pyr.num_levels, pyr.radius, _stream()), "rpe_corr_lookup_nhwc_bf16")
+    return planes
+
+
 def convex_upsample8(flow, mask):
     """rpe_convex_upsample8: flow (B,2,h,w), mask (B,576,h,w) -> (B,2,8h,8w)."""
     B, _, h, w = flow.shape

@@ -100,3 +100,26 @@ def test_lookup_full_size_vs_oracle_sample(ops):
     cp.pyramid.mul_(2.0)
     out2 = cp(dev(coords)).cpu().numpy()
     np.testing.assert_allclose(out2, 2.0 * out, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("h,w,B", [(64, 80, 3), (16, 24, 2), (46, 62, 1)])
+def test_lookup_planes_match_nchw_lookup(ops, h, w, B):
+    """The warp-per-query NHWC bf16 hi/lo lookup (tensor-core path) reproduces the NCHW fp32 lookup to the 16-bit split."""
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import tc
+    f1 = torch.from_numpy(det_uniform((B, 64, h, w), 31)).cuda()
+    f2 = torch.from_numpy(det_uniform((B, 64, h, w), 32)).cuda()
+    cp = ops.CorrPyramid(f1, f2, precision=ops.CORR_TF32)
+    ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    coords = np.stack((xs, ys), 0)[None].astype(np.float32) + det_uniform((B, 2, h, w), 33, -9, 9)
+    coords[:, :, 0, 0] = -50.0                                  # fully outside windows read zeros
+    coords = torch.from_numpy(np.ascontiguousarray(coords.astype(np.float32))).cuda()
+    ref = cp(coords)                                            # (B,324,h,w)
+    planes = tc.Planes(B, h, w, 384, f1.device)
+    ops.corr_lookup_planes(cp, coords, planes)
+    got = planes.float()[..., :324].permute(0, 3, 1, 2)
+    assert float(planes.float()[..., 324:].abs().max()) == 0.0
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    print(f"lookup planes vs NCHW lookup: max abs err {err:.2e} (|ref| max {scale:.2f})")
+    assert err <= scale * 2.0 ** -15
