@@ -204,6 +204,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (the NCCL banner goes to stdout)
         dist.init_process_group("nccl", device_id=dev)
     if rank == 0:
         build.build()
