@@ -71,6 +71,7 @@ struct alignas(64) ConvParams {
     int aux_ld;
     const float *aux2;                                // mode 2: update gate z (fp32 NHWC)
     int aux2_ld;
+    int dbg;                                          // RPE_CONV_DEBUG bits (probe only): 1 no loads, 2 no MMAs, 4 no epilogue memory traffic
 };
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -342,7 +343,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
 
     if (warp == 0) {
         // ===================== activation producer =====================
-        if (elect_one()) {
+        if (!(P.dbg & 1) && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int u = u_first; u < num_units; u += u_step) {
@@ -369,7 +370,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         }
     } else if (warp == 3) {
         // ===================== weight producer =====================
-        if (elect_one()) {
+        if (!(P.dbg & 1) && elect_one()) {
             const int taps = P.kmin * P.kmaj;
             const int brow = kPair ? rank * (P.bn >> 1) : 0;          // this CTA's half of the weight rows
             if (P.resident_b) {
@@ -422,7 +423,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
             uint32_t pa = 0, pb = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            bool b_ready = false;
+            bool b_ready = (P.dbg & 1) != 0;
+            const bool no_load = (P.dbg & 1) != 0, no_mma = (P.dbg & 2) != 0;
             for (int u = u_first; u < num_units; u += u_step) {
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tcgen05_fence_after();
@@ -433,7 +435,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                         const int ksteps = (cb == P.cblocks[s] - 1) ? P.ksteps_last[s] : kCvBK / 16;
                         for (int tm = 0; tm < P.kmin; ++tm)
                             for (int tj = 0; tj < P.kmaj; ++tj) {
-                                if (!P.reuse || tj == 0) {
+                                if ((!P.reuse || tj == 0) && !no_load) {
                                     mbar_wait(&a_full[sa], pa);
                                 }
                                 const uint32_t a0 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) + (P.reuse ? (uint32_t)tj * 1024u : 0u);
@@ -448,37 +450,37 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                     const uint32_t b0 = smem_u32(sB) + (uint32_t)(((P.cb_base[s] + cb) * (P.kmin * P.kmaj) + tap) * P.n_planes) * P.b_plane_bytes;
                                     const uint64_t db_hi = cv_sw128_desc(b0);
                                     for (int k = 0; k < ksteps; ++k) {
-                                        cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                        if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
                                         accumulate = 1;
                                     }
                                     if (P.n_planes == 2) {
                                         const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes), db_lo = cv_sw128_desc(b0 + P.b_plane_bytes);
-                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
                                     }
                                 } else {
-                                    mbar_wait(&b_full[sb], pb);
+                                    if (!no_load) mbar_wait(&b_full[sb], pb);
                                     tcgen05_fence_after();
                                     const uint64_t db_hi = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
                                     for (int k = 0; k < ksteps; ++k) {
-                                        cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
+                                        if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
                                         accumulate = 1;
                                     }
                                     if (P.n_planes == 2) {
                                         const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes);
-                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                        cv_commit<kPair>(&b_empty[sb]);
+                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
+                                        if (!no_load) cv_commit<kPair>(&b_empty[sb]);
                                         if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
-                                        mbar_wait(&b_full[sb], pb);
+                                        if (!no_load) mbar_wait(&b_full[sb], pb);
                                         tcgen05_fence_after();
                                         const uint64_t db_lo = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
-                                        for (int k = 0; k < ksteps; ++k) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
+                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
                                     }
-                                    cv_commit<kPair>(&b_empty[sb]);
+                                    if (!no_load) cv_commit<kPair>(&b_empty[sb]);
                                     if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
                                 }
                                 if (!P.reuse || tj == P.kmaj - 1) {
-                                    cv_commit<kPair>(&a_empty[sa]);
+                                    if (!no_load) cv_commit<kPair>(&a_empty[sa]);
                                     if (++sa == P.n_a_stages) sa = 0, pa ^= 1;
                                 }
                             }
@@ -541,6 +543,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                         else mbar_arrive(&tmem_empty[acc]);
                     }
                 }
+                if (P.dbg & 4) continue;
                 __syncwarp();                                      // previous chunk's reads of the staging tile are done
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -657,6 +660,10 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     } else {
         p.n_a_stages = 2;
         if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
+        if (const char *as_env = getenv("RPE_CONV_ASTAGES")) {      // probe only
+            const int v = atoi(as_env);
+            if (v >= 1 && v <= kCvMaxAStages && (size_t)v * p.a_stage_bytes + 2 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = v;
+        }
         p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
         if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
         if (p.n_b_stages < 2) {
@@ -727,6 +734,10 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.out_hi = reinterpret_cast<__nv_bfloat16 *>(d->out_hi), p.out_lo = reinterpret_cast<__nv_bfloat16 *>(d->out_lo);
     p.bf_ld = d->bf_ld, p.bf_off = d->bf_offset;
     p.mode = d->mode, p.aux = d->aux, p.aux_ld = d->aux_ld, p.aux2 = d->aux2, p.aux2_ld = d->aux2_ld;
+    {
+        const char *dbg_env = getenv("RPE_CONV_DEBUG");
+        p.dbg = dbg_env ? atoi(dbg_env) : 0;
+    }
     if (p.mode != 0) {
         // GRU epilogues: channel groups of 4 never straddle the z|r boundary; state tensors must be 16-byte addressable
         const bool ok = (p.mode == 1 || p.mode == 2) && d->aux && aligned16(d->aux) && (d->aux_ld % 4) == 0 && d->out_hi && d->out_lo &&

@@ -38,7 +38,9 @@ def main():
     single = "--single" in sys.argv
     only = [a[7:] for a in sys.argv if a.startswith("--only=")]
     reps = 1 if "--once" in sys.argv else 20
+    n_over = [int(a[4:]) for a in sys.argv if a.startswith("--n=")]
     for name, n, h, w, cins, cout, kh, kw, stride in SHAPES:
+        n = n_over[0] if n_over else n
         if only and not any(o in name for o in only):
             continue
         cout_pad = (cout + 15) // 16 * 16
