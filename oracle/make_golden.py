@@ -57,7 +57,7 @@ class Recorder:
         self.stage = {}
 
 
-def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True):
+def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True, loss_weight_mask=None):
     """Run the reference tracker over a synthetic sequence and record every stage of the last pair."""
     from core.pose.pose_estimator import PoseEstimator
     import core.pose.pose_net as pose_net_mod
@@ -74,6 +74,11 @@ def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True)
     est = PoseEstimator(config["slam"], torch.tensor(seq.calib["intrinsics"]["left"]), baseline=seq.calib["bf"],
                         checkpoint=ckpt, img_shape=config["img_size"], init_pose=SE3.Identity(1))
     model = est.model
+    if loss_weight_mask is not None:
+        # the shipped code has no switch to drop a residual term; "3D-only" = the reference objective run with
+        # loss_weight[1] (the 2D term, pose_head.py:53-58) zeroed
+        with torch.no_grad():
+            model.loss_weight.mul_(torch.tensor(loss_weight_mask, dtype=model.loss_weight.dtype))
     rec = Recorder()
 
     # ---- hooks (wrap, never modify, the reference callables) ------------------------------
@@ -360,6 +365,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also write the 640x512 dump to oracle/_ref")
     ap.add_argument("--skip-small", action="store_true")
+    ap.add_argument("--variants", action="store_true",
+                    help="BASELINE configs 4/5: infer_f2f_nw (no confidence heads) trajectory -> tests/golden, only3d 1280x1024 -> oracle/_ref")
     args = ap.parse_args()
     assert os.path.isdir(REF), "reference not mounted"
     torch.manual_seed(0)
@@ -395,6 +402,28 @@ def main():
             out[f"c_coords{it}"] = cb._rec["lookups"][it][0].numpy()
             out[f"c_lookup{it}"] = cb._rec["lookups"][it][1].numpy()
         np.savez(os.path.join(refdir, "golden_full.npz"), **out)
+    if args.variants:
+        from core.utils.trajectory import save_trajectory
+        from lietorch import SE3
+        import tempfile
+        print("infer_f2f_nw: 384x352, 5 frames, conf_weighing False, trajectory.freiburg")
+        out, rec, est = run_sequence((384, 352), seed=3, n_frames=5, ckpt=ckpt, conf=False)
+        traj = [{"camera-pose": SE3(torch.from_numpy(p)[None]), "timestamp": i} for i, p in enumerate(out["traj"])]
+        with tempfile.TemporaryDirectory() as td:
+            save_trajectory(traj, td)                                  # the reference's writer (core/utils/trajectory.py:17-23)
+            out["freiburg"] = np.frombuffer(open(os.path.join(td, "trajectory.freiburg"), "rb").read(), dtype=np.uint8)
+        out["n_evals"] = np.array([out[f"pair{k}_eval_pose"].shape[0] for k in range(4)])
+        keep = ("K", "bf", "size", "seed", "imgs_l", "imgs_r", "masks_in", "traj", "freiburg", "n_evals")
+        np.savez_compressed(os.path.join(gold, "e2e_nw_384x352.npz"), **{k: out[k] for k in keep})
+        print("only3d_1a7ix98y.pth, loss_weight[1] = 0, 1280x1024, 2 frames")
+        out, rec, est = run_sequence((1280, 1024), seed=4, n_frames=2, ckpt=os.path.join(REF, "trained", "only3d_1a7ix98y.pth"),
+                                     loss_weight_mask=(1.0, 0.0))
+        st = rec.stage
+        out["n_evals"] = np.array([out["pair0_eval_pose"].shape[0]])
+        out["s_time_flow_ds4"] = st["time_flow"][0, :, ::4, ::4].numpy()
+        out["s_stereo_flow2_ds4"] = st["stereo_flow2"][0, :, ::4, ::4].numpy()
+        out["s_mask2w"] = pack(st["mask2w"][0, 0].numpy())
+        np.savez_compressed(os.path.join(refdir, "golden_only3d_1280x1024.npz"), **out)
     print("done")
 
 

@@ -21,7 +21,8 @@ class PoseEstimator(torch.nn.Module):
     def __init__(self, config, intrinsics, baseline, checkpoint, img_shape, init_pose=None):
         """
         :param config: the ``slam`` section of configuration/infer_f2f.yaml (+ optional keys
-                       ``precision`` fp32|tf32|bf16|fp16, ``solver`` lbfgs_ref|gn, ``sync_guard``)
+                       ``precision`` fp32|bf16x3|tf32|bf16|fp16, ``solver`` lbfgs_ref|gn, ``residuals`` 2d3d|3d|2d,
+                       ``sync_guard``)
         :param intrinsics: rectified camera intrinsics (3,3)
         :param baseline: stereo baseline x focal length in pixel * mm ("bf")
         :param checkpoint: path of a reference checkpoint (trained/*.pth), or a dict {state_dict, config},
@@ -47,6 +48,14 @@ class PoseEstimator(torch.nn.Module):
         model = PoseNet(mcfg)
         if checkp["state_dict"] is not None:
             model.load_state_dict(OrderedDict((k.replace("module.", ""), v) for k, v in checkp["state_dict"].items()))
+        # the shipped code always adds both residual terms (pose_head.py:53-58); '3d' / '2d' zero the other
+        # term's loss weight (index 1 = 2-D reprojection, index 0 = 3-D point-to-point)
+        residuals = config.get("residuals", "2d3d")
+        if residuals not in ("2d3d", "3d", "2d"):
+            raise ValueError(f"residuals must be '2d3d', '3d' or '2d', got {residuals!r}")
+        if residuals != "2d3d":
+            with torch.no_grad():
+                model.loss_weight[1 if residuals == "3d" else 0] = 0.0
         model.eval()
         self.model = model
         self.intrinsics = intrinsics.unsqueeze(0).float()

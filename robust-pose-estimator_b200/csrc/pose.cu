@@ -187,7 +187,8 @@ __device__ __forceinline__ void accumulate_pixel(const PixelConsts &c, const dou
     const double qz = c.K[6] * X + c.K[7] * Y + c.K[8] * Z;
     const double den = fmax(qz, 1e-12);
     const double pass = (qz >= 1e-12) ? 1.0 : 0.0;
-    const double pix = qx / den, piy = qy / den;
+    const double inv = 1.0 / den;                      // one fp64 division per pixel; q * inv differs from q / den by <= 1 ulp
+    const double pix = qx * inv, piy = qy * inv;
     const int row = idx / c.W, col = idx - row * c.W;
     const double tx = ((double)col + 0.5) + (double)fx;
     const double ty = ((double)row + 0.5) + (double)fy;
@@ -198,7 +199,6 @@ __device__ __forceinline__ void accumulate_pixel(const PixelConsts &c, const dou
     acc[0] += bad ? 0.0 : e2;
     const double c2 = bad ? 0.0 : 2.0 * (double)w1 * c.s2;
     // ---- gradient wrt the left perturbation: J = [I | -[p']x]
-    const double inv = 1.0 / den;
     const double gpx = c2 * (-r2x), gpy = c2 * (-r2y);
     const double gqx = gpx * inv, gqy = gpy * inv, gqz = -(gpx * qx + gpy * qy) * inv * inv * pass;
     const double ax = c3 * r3x + (c.K[0] * gqx + c.K[3] * gqy + c.K[6] * gqz);
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_solve_kernel(PoseParams P) 
     }
 }
 
-static int g_pose_groups = 8;
+static int g_pose_groups = 16;   // upper bound on concurrently solved pairs
 
 }  // namespace rpe
 
@@ -642,7 +642,10 @@ int rpe_pose_solve(const rpe_pose_problem *pb, int mode, int max_iter, int with_
     // g_pose_groups concurrent groups so that the barrier latency of one group overlaps the fp64
     // math of the others (throughput path).
     const long long px_per_block_iter = (long long)kPoseThreads * 4;
-    int n_groups = pb->n < g_pose_groups ? pb->n : g_pose_groups;
+    // Pairs are dealt round-robin to the groups, so the group count is balanced against the number of rounds: 11 pairs run
+    // as one round of 11 groups rather than 8 + 3.
+    const int rounds = (pb->n + g_pose_groups - 1) / g_pose_groups;
+    int n_groups = (pb->n + rounds - 1) / rounds;
     if (n_groups < 1) n_groups = 1;
     if (n_groups > 256) n_groups = 256;
     int bpg = max_blocks / n_groups;
