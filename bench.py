@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--pairs", type=int, default=64)
     ap.add_argument("--graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency-frames", type=int, default=40, help="batch-1 latency leg (config 2): pairs timed one by one; 0 = off")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -288,6 +289,23 @@ def main():
         traj, failed = e2e_step()
     sync_all()
     e2e_s = time.perf_counter() - t0
+    # ---- latency path (BASELINE config 2: batch 1, the per-frame tracker call of the reference API), rank 0, outside `value`
+    latency = None
+    if rank == 0 and args.latency_frames > 0:
+        est.frame = est.last_frame = None
+        est.failure_flags = []
+        nlat = min(args.latency_frames, T - 1)
+        evs = []
+        for k in range(nlat + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            est(dL[k:k + 1], dR[k:k + 1], dM[k:k + 1].clone())
+            b.record()
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        lat = np.array([a.elapsed_time(b) for a, b in evs[1 + min(5, nlat // 4):]])   # frame 0 has no pair; skip warm-up pairs
+        latency = {"p50_ms_per_pair": float(np.percentile(lat, 50)), "p90_ms_per_pair": float(np.percentile(lat, 90)),
+                   "pairs": int(lat.size), "call": "PoseEstimator.forward, batch 1, device-resident frame, CUDA events"}
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -354,7 +372,8 @@ def main():
             "e2e": {"value": pairs_total / (e2e_ms / 1e3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(world * args.pairs * 13 * 4), "input": "pinned uint8 frames + bool masks",
                     "failed_pairs": int(failed.sum())},
-            "roofline": roofline, "kernels": kernels, "stages": stage, "lbfgs_evals_per_pair": evals_total / args.pairs}
+            "roofline": roofline, "latency": latency, "kernels": kernels, "stages": stage,
+            "lbfgs_evals_per_pair": evals_total / args.pairs}
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(L, R, M, seq)
         line["cpu_baseline"] = cb

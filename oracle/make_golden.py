@@ -367,6 +367,7 @@ def main():
     ap.add_argument("--skip-small", action="store_true")
     ap.add_argument("--variants", action="store_true",
                     help="BASELINE configs 4/5: infer_f2f_nw (no confidence heads) trajectory -> tests/golden, only3d 1280x1024 -> oracle/_ref")
+    ap.add_argument("--skip-nw", action="store_true", help="with --variants: only the (git-ignored) only3d 1280x1024 golden")
     args = ap.parse_args()
     assert os.path.isdir(REF), "reference not mounted"
     torch.manual_seed(0)
@@ -406,6 +407,7 @@ def main():
         from core.utils.trajectory import save_trajectory
         from lietorch import SE3
         import tempfile
+    if args.variants and not args.skip_nw:
         print("infer_f2f_nw: 384x352, 5 frames, conf_weighing False, trajectory.freiburg")
         out, rec, est = run_sequence((384, 352), seed=3, n_frames=5, ckpt=ckpt, conf=False)
         traj = [{"camera-pose": SE3(torch.from_numpy(p)[None]), "timestamp": i} for i, p in enumerate(out["traj"])]
@@ -415,6 +417,7 @@ def main():
         out["n_evals"] = np.array([out[f"pair{k}_eval_pose"].shape[0] for k in range(4)])
         keep = ("K", "bf", "size", "seed", "imgs_l", "imgs_r", "masks_in", "traj", "freiburg", "n_evals")
         np.savez_compressed(os.path.join(gold, "e2e_nw_384x352.npz"), **{k: out[k] for k in keep})
+    if args.variants:
         print("only3d_1a7ix98y.pth, loss_weight[1] = 0, 1280x1024, 2 frames")
         out, rec, est = run_sequence((1280, 1024), seed=4, n_frames=2, ckpt=os.path.join(REF, "trained", "only3d_1a7ix98y.pth"),
                                      loss_weight_mask=(1.0, 0.0))

@@ -1,12 +1,13 @@
 #!/bin/bash
-# One GPU call: parity tests, bench line, conv probe with the debug switches, ncu --set full of the hand-written kernels.
+# One GPU call: parity tests, bench lines (both arms), conv probe with the debug switches, ncu --set full of the hand-written kernels.
 # Only text / csv summaries are kept (gpurun_out/ is capped at 64 MiB): .ncu-rep files are converted and deleted on the box.
 set -u
-O=gpurun_out/s5
+O=gpurun_out/${1:-s5}
 mkdir -p $O
-timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
+timeout 900 python -m pytest tests -m gpu -q -rs -s > $O/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $O/pytest_gpu.log
 timeout 600 python bench.py --steps 3 --warmup 3 > $O/bench.json 2> $O/bench.err
-for d in 0 1 2 4 5 6; do
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference.json 2> $O/bench_reference.err
+for d in 0 1 2 4; do
   RPE_CONV_DEBUG=$d timeout 300 python tools/conv_probe.py --n=22 > $O/probe_dbg$d.txt 2>&1
 done
 RPE_CONV_PAIR=0 timeout 300 python tools/conv_probe.py --n=22 > $O/probe_nopair.txt 2>&1
@@ -19,7 +20,7 @@ ncu -i $T/conv.ncu-rep --page source --csv --kernel-name regex:conv_bf16_pair --
 timeout 600 ncu --set full --clock-control none \
   -k regex:'corr_lookup_nhwc|pose_solve|corr_gemm|corr_pool|norm_act|instnorm_partial|im2col7s2|convex_upsample8|warp8_mask|depth_proj' \
   -s 30 -c 24 -o $T/own -f \
-  python bench.py --steps 1 --warmup 1 --pairs 11 --no-cpu-baseline > $O/ncu_own.log 2>&1
+  python bench.py --steps 1 --warmup 1 --pairs 11 --no-cpu-baseline --latency-frames 0 > $O/ncu_own.log 2>&1
 ncu -i $T/own.ncu-rep --page raw --csv > $O/ncu_own_bench_pairs11_raw.csv 2>/dev/null
 ncu -i $T/own.ncu-rep --page details --csv > $O/ncu_own_bench_pairs11_details.csv 2>/dev/null
 gzip -f $O/*_details.csv $O/ncu_conv_zr1_source.csv
