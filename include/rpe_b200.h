@@ -224,7 +224,11 @@ typedef struct rpe_conv_desc {
     int bf_ld, bf_offset;
     /* fused SepConvGRU epilogues (update.py:45-60); 0 = plain epilogue.
      *   mode 1 (z|r gates, activation sigmoid, cout = 2*hidden): z = out[:hidden] -> out_f32, planes <- r * h  (h = aux)
-     *   mode 2 (candidate, activation tanh, cout = hidden): h <- (1 - z) * h + z * q in place (h = aux, z = aux2), planes <- h */
+     *   mode 2 (candidate, activation tanh, cout = hidden): h <- (1 - z) * h + z * q in place (h = aux, z = aux2), planes <- h
+     * fused head of a following 3x3 convolution with 2 output channels (FlowHead, update.py:6-13):
+     *   mode 3 (tap projection, cout <= 256): the activated outputs y are not stored; out_f32 (f32_ld >= 36) receives two slots of
+     *           18 partial sums p[(ky*3+kx)*2 + o] = <y[half of the channels], w2[:, (ky*3+kx)*2 + o]>, w2 = aux2 as fp32 [cout][18];
+     *           rpe_tap_gather3x3 adds the nine shifted maps and the bias. */
     int mode;
     float *aux;          /* hidden state h, fp32 NHWC (N,OH,OW,aux_ld)                                */
     int aux_ld;
@@ -246,6 +250,7 @@ int rpe_nchw_to_nhwc_split(const float *x, void *hi, void *lo, float *f32, int n
 int rpe_nhwc_to_nchw(const float *x, float *out, int n, int C, int H, int W, int ld, int off, void *stream);
 int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi, void *col_lo, int col_ld, void *x_hi,
                   void *x_lo, int x_ld, int x_off, int n, int h, int w, void *stream);
+int rpe_tap_gather3x3(const float *part, int part_ld, const float *bias, float *out, int out_ld, int n, int h, int w, void *stream);
 int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *out_lo, int out_ld, int out_off,
                  long long npix, int mode, void *stream);
 

@@ -74,6 +74,7 @@ SIGNATURES = {
     "rpe_instnorm_workspace_bytes": (_Z, [_I, _I]),
     "rpe_instnorm_stats": (_I, [_P, _P, _I, _I, _I, _F, _P, _Z, _P]),
     "rpe_norm_act_split": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "rpe_tap_gather3x3": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_gru_gate": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_longlong, _I, _P]),
 }
 

@@ -4,6 +4,8 @@ Same arithmetic graph as ``update.update_forward`` (reference: /root/reference/c
 loop body of core/RAFT/core/raft.py:112-132) with every convolution evaluated as an error-compensated bf16x3 implicit
 GEMM on the tensor cores, NHWC activations, no materialised concatenations and the whole 12-iteration loop resident in
 pre-allocated device buffers (one set per batch shape)."""
+import os
+
 import torch
 
 from .... import _lib, ops
@@ -20,6 +22,7 @@ class UpdateTC:
         self.prefix = prefix
         self._packed = {}
         self._shapes = {}
+        self.fused_flow_head = os.environ.get("RPE_FUSED_FLOW_HEAD", "1") != "0"     # 0: plain conv1 -> conv2 plans (debug / A-B)
 
     # ---- weights ---------------------------------------------------------------------------------------
     def _w(self, name, c_lo, c_hi, cout_pad, transform=None):
@@ -57,7 +60,7 @@ class UpdateTC:
         # contribution to the six gate convolutions is evaluated once per refinement (pzr*/pq*) and enters as an addend
         st.update(corr=P(384), cor1=P(256), cf=P(256), col=P(128), flo1=P(128), inp=P(128), mot=P(128), hp=P(128), rh=P(128),
                   fh=P(256), mk=P(256), h=f32(128), z=f32(128), pzr1=f32(256), pzr2=f32(256), pq1=f32(128), pq2=f32(128),
-                  delta=f32(4), mask=f32(576), coords1=torch.zeros((n, 2, h, w), dtype=torch.float32, device=device))
+                  delta=f32(4), fpart=f32(36), mask=f32(576), coords1=torch.zeros((n, 2, h, w), dtype=torch.float32, device=device))
         W, pre = self.W, self.prefix
         zr_w = lambda half: (lambda: torch.cat((W[pre + f"gru.convz{half}.weight"], W[pre + f"gru.convr{half}.weight"]), 0))
         zr_b = lambda half: (lambda: torch.cat((W[pre + f"gru.convz{half}.bias"], W[pre + f"gru.convr{half}.bias"]), 0))
@@ -78,8 +81,17 @@ class UpdateTC:
                                          mode=1, aux=st["h"])
             pl["q" + half] = self._plan(st, "gru.convq" + half, [(st["rh"], 0, 128, 0), (st["mot"], 0, 128, 256)], kh, kw, 128, "tanh",
                                         out_planes=st["hp"], use_bias=False, pre=st["pq" + half], mode=2, aux=st["h"], aux2=st["z"])
-        pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["fh"])
-        pl["fh2"] = self._plan(st, "flow_head.conv2", [(st["fh"], 0, 256, 0)], 3, 3, 2, "none", out_f32=st["delta"])
+        if self.fused_flow_head:
+            # FlowHead (update.py:6-13): conv2 has 2 output channels -> its per-pixel part (18 dot products of length 256) runs in
+            # fp32 inside conv1's epilogue (conv.cu mode 3) and rpe_tap_gather3x3 adds the nine shifted maps; relu(conv1) is never stored
+            key = ("fh2_proj",)
+            if key not in self._packed:
+                self._packed[key] = W[pre + "flow_head.conv2.weight"].float().permute(1, 2, 3, 0).reshape(256, 18).contiguous()
+            pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_f32=st["fpart"], mode=3,
+                                   aux2=self._packed[key])
+        else:
+            pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["fh"])
+            pl["fh2"] = self._plan(st, "flow_head.conv2", [(st["fh"], 0, 256, 0)], 3, 3, 2, "none", out_f32=st["delta"])
         pl["mask0"] = self._plan(st, "mask.0", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["mk"])
         pl["mask2"] = self._plan(st, "mask.2", [(st["mk"], 0, 256, 0)], 1, 1, 576, "none", out_f32=st["mask"], scale=0.25)
         st["plans"] = pl
@@ -116,8 +128,14 @@ class UpdateTC:
                 check(l.rpe_flow_step(_p(coords1), _p(st["delta"]) if it > 0 else None, 4, _p(st["col"].hi), _p(st["col"].lo), 128,
                                       _p(st["mot"].hi), _p(st["mot"].lo), 128, 126, B, h, w, s), "rpe_flow_step")
             ops.corr_lookup_planes(corr_pyr, coords1, st["corr"])
-            for name in ("convc1", "convc2", "convf1", "convf2", "conv", "zr1", "q1", "zr2", "q2", "fh1", "fh2"):
+            for name in ("convc1", "convc2", "convf1", "convf2", "conv", "zr1", "q1", "zr2", "q2", "fh1"):
                 self._run(st, name)
+            if self.fused_flow_head:
+                with _timed("tap_gather", B):
+                    check(l.rpe_tap_gather3x3(_p(st["fpart"]), 36, _p(self._bias("flow_head.conv2")), _p(st["delta"]), 4, B, h, w, s),
+                          "rpe_tap_gather3x3")
+            else:
+                self._run(st, "fh2")
         coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))
         flow_lo = coords1 - grid[None]
         flow_up = None

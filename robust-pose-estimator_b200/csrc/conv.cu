@@ -230,6 +230,27 @@ __device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const floa
         if ((inside_mask >> it) & 1u) cv_epilogue_group(P, acc[it], sd[it], sbias, co, pix[it]);
 }
 
+// mode 3 ("tap projection"): the activated outputs y[c] of a pixel are not stored; instead the epilogue evaluates the
+// per-pixel part of a FOLLOWING 3x3 convolution with few output channels, p[t] = sum_c y[c] * w2[c][t] (t = tap * 2 + o,
+// 18 values), in fp32 on the CUDA cores under the shadow of the next tile's MMAs.  rpe_tap_gather3x3 then adds the nine
+// shifted p maps.  Used for RAFT's flow head (update.py:6-13: conv2(relu(conv1(x))), 256 -> 2 channels), whose second
+// convolution would otherwise run as an N = 16 tensor-core GEMM at ~1 % utilisation.
+constexpr int kCvProj = 18;
+__device__ __forceinline__ void cv_project_chunk(const ConvParams &P, const uint32_t *v, const float *sbias, const float *w2s, int co,
+                                                 float *acc) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float y = cv_activate_rt(__uint_as_float(v[j]) + sbias[co + j], P.act) * P.scale;
+        const float2 *w = reinterpret_cast<const float2 *>(w2s + (co + j) * kCvProj);
+#pragma unroll
+        for (int k = 0; k < kCvProj / 2; ++k) {
+            const float2 wk = w[k];
+            acc[2 * k] = fmaf(y, wk.x, acc[2 * k]);
+            acc[2 * k + 1] = fmaf(y, wk.y, acc[2 * k + 1]);
+        }
+    }
+}
+
 struct CvTile {
     int nb, img, omin0, omaj0;
     bool ghost;                                        // pair mode: padding tile of an odd tile count (computed, never stored)
@@ -273,6 +294,27 @@ __device__ __forceinline__ void cv_commit(uint64_t *bar) {
     else umma_commit(bar);
 }
 
+__device__ __forceinline__ void cv_tmem_load16(uint32_t *v, uint32_t taddr) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    tmem_ld_wait();
+}
+// the warp has read everything it needs from the accumulator stage: hand it back to the MMA issuer
+template <bool kPair>
+__device__ __forceinline__ void cv_release_acc(uint64_t *bar, uint32_t cluster_addr, int lane) {
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+        if (kPair) mbar_arrive_cluster(cluster_addr);
+        else mbar_arrive(bar);
+    }
+}
+
 // In pair mode (cta_group::2) two CTAs of a cluster own two adjacent pixel tiles: each loads its own activations and HALF of
 // the weight tile, the leader (rank 0) issues M = 256 MMAs that read both shared memories and write both tensor memories,
 // and every TMA load of either CTA counts its bytes on the leader's "full" barrier; the MMA commits are multicast to the
@@ -294,6 +336,10 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
     float *sbias = reinterpret_cast<float *>(smem + kCvSmemData + 512);
     float *sstage = reinterpret_cast<float *>(smem + kCvSmemData + 512 + kCvMaxCout * 4);
     for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
+    // mode 3: projection weights [cout <= 256][18] fp32 behind the bias (rest of the bias area + the unused staging tiles)
+    float *w2s = sbias + 256;
+    if (P.mode == 3)
+        for (int i = threadIdx.x; i < P.cout * kCvProj; i += kCvThreads) w2s[i] = P.aux2[i];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = kPair ? (int)cluster_ctarank() : 0;
@@ -511,47 +557,51 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 if (y < P.OH && x < P.OW && !t.ghost) inside_mask |= 1u << it;
                 pix[it] = ((size_t)t.img * P.OH + y) * P.OW + x;
             }
-            mbar_wait(&tmem_full[acc], acc_phase);
-            tcgen05_fence_after();
-            const uint32_t empty_addr = kPair ? mapa_shared(smem_u32(&tmem_empty[acc]), 0) : 0u;
             const int n_chunks = P.bn / 16;
             const int c_begin = chalf * ((n_chunks + 1) / 2), c_end = chalf == 0 ? (n_chunks + 1) / 2 : n_chunks;
-            if (c_begin >= c_end) {                                // nothing to drain (bn = 16): just release the accumulator
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (kPair) mbar_arrive_cluster(empty_addr);
-                    else mbar_arrive(&tmem_empty[acc]);
-                }
-            }
-            for (int c = c_begin; c < c_end; ++c) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kCvMaxBN + c * 16);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr)
-                    : "memory");
-                tmem_ld_wait();
-                if (c + 1 == c_end) {
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (kPair) mbar_arrive_cluster(empty_addr);
-                        else mbar_arrive(&tmem_empty[acc]);
-                    }
-                }
-                if (P.dbg & 4) continue;
-                __syncwarp();                                      // previous chunk's reads of the staging tile are done
+            const uint32_t empty_addr = kPair ? mapa_shared(smem_u32(&tmem_empty[acc]), 0) : 0u;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kCvMaxBN);
+            if (P.mode == 3) {
+                // ---- tap projection: lane = accumulator row = pixel, no transposition, nothing but 18 partial sums is stored
+                float proj[kCvProj];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
-                        make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-                __syncwarp();
-                const int co = t.nb * P.bn + c * 16 + ((lane & 3) << 2);
-                cv_epilogue_half(P, stage, sbias, co, pix, inside_mask, lane);
+                for (int k = 0; k < kCvProj; ++k) proj[k] = 0.0f;
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t v[16];
+                    cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
+                    if (c + 1 == c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);
+                    if (!(P.dbg & 4)) cv_project_chunk(P, v, sbias, w2s, t.nb * P.bn + c * 16, proj);
+                }
+                const int m = wq * 32 + lane;
+                const int gi = m >> 3, mi = m & 7;
+                const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
+                const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
+                if (y < P.OH && x < P.OW && !t.ghost && !(P.dbg & 4)) {
+                    float2 *dst = reinterpret_cast<float2 *>(P.out_f32 + (((size_t)t.img * P.OH + y) * P.OW + x) * P.f32_ld + P.f32_off +
+                                                             chalf * kCvProj);
+#pragma unroll
+                    for (int k = 0; k < kCvProj / 2; ++k) dst[k] = make_float2(proj[2 * k], proj[2 * k + 1]);
+                }
+            } else {
+                const int co_lane = t.nb * P.bn + ((lane & 3) << 2);
+                mbar_wait(&tmem_full[acc], acc_phase);
+                tcgen05_fence_after();
+                if (c_begin >= c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);   // nothing to drain (bn = 16)
+                for (int c = c_begin; c < c_end; ++c) {
+                    uint32_t v[16];
+                    cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
+                    if (c + 1 == c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);
+                    if (P.dbg & 4) continue;
+                    __syncwarp();                                  // previous chunk's reads of the staging tile are done
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
+                            make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    __syncwarp();
+                    cv_epilogue_half(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane);
+                }
             }
             if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
         }
@@ -740,9 +790,14 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     }
     if (p.mode != 0) {
         // GRU epilogues: channel groups of 4 never straddle the z|r boundary; state tensors must be 16-byte addressable
-        const bool ok = (p.mode == 1 || p.mode == 2) && d->aux && aligned16(d->aux) && (d->aux_ld % 4) == 0 && d->out_hi && d->out_lo &&
-                        (d->cout % 8) == 0 && n_blocks == 1 &&
-                        (p.mode == 1 ? (d->out_f32 != nullptr) : (d->aux2 != nullptr && aligned16(d->aux2) && (d->aux2_ld % 4) == 0));
+        bool ok;
+        if (p.mode == 3)        // tap projection: partial sums only, 2 x 18 floats per pixel; weights [cout][18] fp32 in aux2
+            ok = d->aux2 && d->out_f32 && !d->out_hi && !d->pre && !d->res && n_blocks == 1 && d->cout <= 256 && bn >= 32 &&
+                 d->cout == d->cout_pad && (d->f32_ld % 2) == 0 && (d->f32_offset % 2) == 0 && d->f32_ld >= d->f32_offset + 2 * kCvProj;
+        else
+            ok = (p.mode == 1 || p.mode == 2) && d->aux && aligned16(d->aux) && (d->aux_ld % 4) == 0 && d->out_hi && d->out_lo &&
+                 (d->cout % 8) == 0 && n_blocks == 1 &&
+                 (p.mode == 1 ? (d->out_f32 != nullptr) : (d->aux2 != nullptr && aligned16(d->aux2) && (d->aux2_ld % 4) == 0));
         if (!ok) {
             delete pl;
             return RPE_ERR_INVALID_ARG;

@@ -138,6 +138,34 @@ __global__ void __launch_bounds__(256) gru_gate_kernel(const float *__restrict__
     *reinterpret_cast<uint2 *>(o_lo + pix * o_ld + o_off + c) = *reinterpret_cast<uint2 *>(ll);
 }
 
+// Second half of a 3x3 convolution whose per-pixel part ran in the epilogue of the preceding convolution (conv.cu mode 3):
+// part (n,h,w,ld) holds two slots (one per half of the contracted channels) of p[t*2 + o] = <y(pixel), W[o][:, t]>, t = ky*3 + kx;
+// out[y][x][o] = bias[o] + sum_t p_t[y + ky - 1][x + kx - 1][o] with zero padding (update.py:6-13, FlowHead.conv2).
+__global__ void __launch_bounds__(256) tap_gather3x3_kernel(const float *__restrict__ part, int ld, const float *__restrict__ bias,
+                                                            float *__restrict__ out, int out_ld, int h, int w, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const long long img = i / ((long long)w * h);
+    float a0 = bias ? __ldg(bias) : 0.0f, a1 = bias ? __ldg(bias + 1) : 0.0f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yy = y + ky - 1;
+        if (yy < 0 || yy >= h) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xx = x + kx - 1;
+            if (xx < 0 || xx >= w) continue;
+            const float *p = part + ((img * h + yy) * w + xx) * ld + (ky * 3 + kx) * 2;
+            const float2 u = __ldg(reinterpret_cast<const float2 *>(p)), v = __ldg(reinterpret_cast<const float2 *>(p + 18));
+            a0 += u.x + v.x;
+            a1 += u.y + v.y;
+        }
+    }
+    *reinterpret_cast<float2 *>(out + i * out_ld) = make_float2(a0, a1);
+}
+
 }  // namespace rpe
 
 extern "C" {
@@ -176,6 +204,16 @@ int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi
     rpe::flow_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
         total);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_tap_gather3x3(const float *part, int part_ld, const float *bias, float *out, int out_ld, int n, int h, int w, void *stream) {
+    if (!part || !out || n <= 0 || h <= 0 || w <= 0 || part_ld < 36 || (part_ld % 2) || (out_ld % 2) || out_ld < 2 ||
+        (reinterpret_cast<uintptr_t>(part) & 7u) || (reinterpret_cast<uintptr_t>(out) & 7u))
+        return RPE_ERR_INVALID_ARG;
+    const long long total = (long long)n * h * w;
+    rpe::tap_gather3x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(part, part_ld, bias, out, out_ld, h, w, total);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

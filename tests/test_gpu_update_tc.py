@@ -115,6 +115,63 @@ def test_update_operator_vs_torch_trunk(ops):
     assert epe_ref.mean().item() < 1e-2                                    # north-star flow gate vs the reference itself
 
 
+@pytest.mark.parametrize("H,W", [(64, 80), (44, 52)])
+def test_flow_head_tap_projection_vs_torch_fp32(ops, H, W):
+    """FlowHead conv2(relu(conv1(x))) with conv2 evaluated as a per-pixel projection in conv1's epilogue (conv.cu mode 3)
+    plus rpe_tap_gather3x3, against torch fp32 convolutions (update.py:6-13).  44x52: ragged tiles and an odd tile count."""
+    import ctypes as C
+    from rpe_b200 import _lib, tc
+    from rpe_b200.ops import _p, _stream, check
+    n = 3
+    x = dev(det_uniform((n, 128, H, W), 31, -1, 1))
+    w1 = dev(det_uniform((256, 128, 3, 3), 32, -1, 1)) / (128 * 9) ** 0.5
+    b1 = dev(det_uniform((256,), 33, -0.5, 0.5))
+    w2 = dev(det_uniform((2, 256, 3, 3), 34, -1, 1)) / (256 * 9) ** 0.5
+    b2 = dev(det_uniform((2,), 35, -0.5, 0.5))
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref = F.conv2d(torch.relu(F.conv2d(x.double(), w1.double(), b1.double(), padding=1)), w2.double(), b2.double(), padding=1).float()
+    planes = tc.Planes(n, H, W, 128, x.device)
+    tc.nchw_to_planes(x, planes)
+    part = torch.full((n, H, W, 36), float("nan"), dtype=torch.float32, device=x.device)
+    proj = w2.permute(1, 2, 3, 0).reshape(256, 18).contiguous()
+    plan = tc.ConvPlan("fh1", [(planes, 0, 128, tc.pack_weight(w1, 0, 128, 256))], (n, H, W), 3, 3, 256, "relu", bias=b1.contiguous(),
+                       out_f32=part, mode=3, aux2=proj)
+    plan.run()
+    delta = torch.zeros((n, H, W, 4), dtype=torch.float32, device=x.device)
+    check(_lib.lib().rpe_tap_gather3x3(_p(part), 36, _p(b2.contiguous()), _p(delta), 4, n, H, W, _stream()), "rpe_tap_gather3x3")
+    torch.cuda.synchronize()
+    assert not torch.isnan(part).any()
+    got = delta[..., :2].permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item()
+    print(f"fused flow head {H}x{W}: max abs err {err:.2e} (|ref| max {ref.abs().max().item():.2f})")
+    assert err < 5e-5 and float(delta[..., 2:].abs().max()) == 0.0
+
+
+def test_update_operator_fused_vs_plain_flow_head(ops, monkeypatch):
+    """The whole 12-iteration update operator with the fused flow head equals the plain conv1 -> conv2 plans."""
+    if not os.path.isfile(CKPT) or not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz")):
+        pytest.skip("checkpoint / full golden not shipped")
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_net import PoseNet
+    g = np.load(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz"))
+    ck = torch.load(CKPT, map_location="cpu", weights_only=False)
+    i1 = dev(g["imgs_l"][1:3].astype(np.float32))
+    i2 = torch.cat((dev(g["imgs_l"][2:3].astype(np.float32)), dev(g["imgs_r"][2:3].astype(np.float32))))
+    outs = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("RPE_FUSED_FLOW_HEAD", flag)
+        cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision="bf16x3")
+        model = PoseNet(cfg)
+        model.load_state_dict(ck["state_dict"])
+        model = model.cuda().eval()
+        preds, net, inp = model.flow(i1, i2)
+        assert model.flow._tc.fused_flow_head == (flag == "1")
+        outs[flag] = preds[-1].clone()
+    epe = (outs["1"] - outs["0"]).pow(2).sum(1).sqrt()
+    print(f"fused vs plain flow head: flow EPE mean {epe.mean().item():.2e} max {epe.max().item():.2e}")
+    assert epe.mean().item() < 1e-4 and epe.max().item() < 5e-3
+
+
 @pytest.mark.parametrize("which", ["fnet", "cnet"])
 def test_encoder_tc_vs_torch_fp32(ops, which):
     """Feature / context encoder on the tensor-core path (instance-norm statistics, folded batch norm, strided TMA
