@@ -304,8 +304,29 @@ def main():
             evs.append((a, b))
         torch.cuda.synchronize()
         lat = np.array([a.elapsed_time(b) for a, b in evs[1 + min(5, nlat // 4):]])   # frame 0 has no pair; skip warm-up pairs
-        latency = {"p50_ms_per_pair": float(np.percentile(lat, 50)), "p90_ms_per_pair": float(np.percentile(lat, 90)),
-                   "pairs": int(lat.size), "call": "PoseEstimator.forward, batch 1, device-resident frame, CUDA events"}
+        eager = {"p50_ms_per_pair": float(np.percentile(lat, 50)), "p90_ms_per_pair": float(np.percentile(lat, 90)),
+                 "pairs": int(lat.size), "call": "PoseEstimator.forward, batch 1, device-resident frame, CUDA events"}
+        latency = dict(eager)
+        try:
+            # the same call with config['cuda_graph']: the per-frame device work replayed as one captured CUDA graph
+            est.config = dict(est.config, cuda_graph=True)
+            est.frame = est.last_frame = None
+            evs = []
+            for k in range(nlat + 1):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                est(dL[k:k + 1], dR[k:k + 1], dM[k:k + 1].clone())
+                b.record()
+                evs.append((a, b))
+            torch.cuda.synchronize()
+            lat = np.array([a.elapsed_time(b) for a, b in evs[1 + min(5, nlat // 4):]])   # pair 1 captures the graph
+            latency = {"p50_ms_per_pair": float(np.percentile(lat, 50)), "p90_ms_per_pair": float(np.percentile(lat, 90)),
+                       "pairs": int(lat.size),
+                       "call": "PoseEstimator.forward with config cuda_graph=True, batch 1, device-resident frame, CUDA events",
+                       "eager": eager}
+        except Exception as exc:                                   # keep the bench line; report why the graph leg is missing
+            latency["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
+        est.config = dict(est.config, cuda_graph=False)
     t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

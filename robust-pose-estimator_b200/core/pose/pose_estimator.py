@@ -22,7 +22,8 @@ class PoseEstimator(torch.nn.Module):
         """
         :param config: the ``slam`` section of configuration/infer_f2f.yaml (+ optional keys
                        ``precision`` fp32|bf16x3|tf32|bf16|fp16, ``solver`` lbfgs_ref|gn, ``residuals`` 2d3d|3d|2d,
-                       ``sync_guard``)
+                       ``sync_guard``, ``cuda_graph``: replay the whole per-frame device work of ``forward`` as one CUDA
+                       graph -- the latency path; ``flow`` / ``weights`` are then not returned)
         :param intrinsics: rectified camera intrinsics (3,3)
         :param baseline: stereo baseline x focal length in pixel * mm ("bf")
         :param checkpoint: path of a reference checkpoint (trained/*.pth), or a dict {state_dict, config},
@@ -78,6 +79,8 @@ class PoseEstimator(torch.nn.Module):
     def forward(self, limg, rimg, mask):
         """limg, rimg (1,3,H,W) float 0..255, mask (1,1,H,W) bool -> (pose SE3 in mm, None, flow, weights)."""
         self.last_pose = self.last_pose.to(limg.device)
+        if self.config.get("cuda_graph", False):
+            return self._forward_graphed(limg, rimg, mask)
         self.last_frame = self.frame
         self.frame = Frame(limg, rimg, mask=mask)
         rel_pose, ret_frame, flow, weights = self.get_pose_f2f()
@@ -93,6 +96,31 @@ class PoseEstimator(torch.nn.Module):
         rel_pose = rel_pose.scale(1 / self.scale)                  # de-normalise depth scaling
         self.last_pose = self.last_pose * rel_pose.inv()           # chain transforms
         return self.last_pose, self.scene, flow, weights
+
+    def _forward_graphed(self, limg, rimg, mask):
+        """Latency path: the same per-frame step through ``F2FEngine`` with one frame per chunk, captured once and replayed
+        as a single CUDA graph (features / context / stereo depth of the previous frame are the carried state, as in
+        ``Frame``).  Guard, de-normalisation and chaining as in ``forward`` (pose_estimator.py:81-91)."""
+        from ...engine import F2FEngine
+        eng = getattr(self, "_stream_engine", None)
+        if eng is None:
+            eng = self._stream_engine = F2FEngine(self, 1, True)
+        if self.frame is None:                                     # new sequence
+            eng.reset()
+        self.last_frame = self.frame
+        self.frame = Frame(limg, rimg, mask=mask)
+        rel, log, _ = eng.infer_sequence(limg, rimg, mask)
+        ident = SE3.IdentityLike(self.last_pose)
+        if rel.shape[0] == 0:                                      # first frame: stereo depth only
+            return self.last_pose, self.scene, None, None
+        bad = torch.isnan(rel).any() | (torch.abs(log) > 1.0e-1).any()
+        rel_pose = SE3(torch.where(bad, ident.data, rel.to(ident.dtype)))
+        self.failure_flags.append(bad)
+        if self.config.get("sync_guard", False) and bool(bad):
+            warnings.warn("pose estimation not converged, skip.", RuntimeWarning)
+        rel_pose = rel_pose.scale(1 / self.scale)
+        self.last_pose = self.last_pose * rel_pose.inv()
+        return self.last_pose, self.scene, None, None
 
     def get_pose_f2f(self):
         flow = None

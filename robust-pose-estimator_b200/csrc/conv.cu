@@ -103,6 +103,10 @@ __device__ __forceinline__ float cv_activate_rt(float v, int act) {
     return v;
 }
 
+// sigmoid / tanh on the hardware exponential and reciprocal (ex2.approx, rcp.approx): saturate correctly at +-inf
+__device__ __forceinline__ float cv_sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float cv_tanh_fast(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+
 // fp32 x4 -> bf16 hi / lo planes (hi = bf16(v), lo = bf16(v - hi)), packed conversions
 __device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, size_t o, const float *v) {
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
@@ -145,12 +149,13 @@ struct CvSide {
     float4 pre, a, z;
 };
 
+template <int kMode>
 __device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, int co, size_t pix) {
     if (co + 3 >= P.cout) return;
     if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
-    if (P.mode == 0) {
+    if (kMode == 0) {
         if (P.res) sd.a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
-    } else if (P.mode == 1) {
+    } else if (kMode == 1) {
         const int half = P.cout >> 1;
         if (co >= half) sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + pix * P.aux_ld + (co - half)));
     } else {
@@ -160,6 +165,7 @@ __device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, in
 }
 
 // One group of 4 consecutive output channels of one pixel: bias / addend / activation / scale / residual / stores.
+template <int kMode>
 __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const float4 acc, const CvSide &sd, const float *sbias, int co,
                                                   size_t pix) {
     if (co >= P.cout) return;
@@ -168,7 +174,15 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
         const float4 b = *reinterpret_cast<const float4 *>(sbias + co);
         o[0] = acc.x + b.x, o[1] = acc.y + b.y, o[2] = acc.z + b.z, o[3] = acc.w + b.w;
         if (P.pre) o[0] += sd.pre.x, o[1] += sd.pre.y, o[2] += sd.pre.z, o[3] += sd.pre.w;
-        if (P.act == 1) {
+        // GRU modes fix the activation (z|r: sigmoid, q: tanh) and use the hardware exponential / reciprocal (abs. error
+        // < 5e-7, far below the 2^-16 of the split operands): the epilogue shares its issue slots with the MMA issuer
+        if (kMode == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = cv_sigmoid_fast(o[k]);
+        } else if (kMode == 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o[k] = cv_tanh_fast(o[k]);
+        } else if (P.act == 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.0f);
         } else if (P.act == 2) {
@@ -182,14 +196,14 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] *= P.scale;
         }
-        if (P.mode == 0) {
+        if (kMode == 0) {
             if (P.res) {
                 o[0] = fmaxf(o[0] + sd.a.x, 0.0f), o[1] = fmaxf(o[1] + sd.a.y, 0.0f);
                 o[2] = fmaxf(o[2] + sd.a.z, 0.0f), o[3] = fmaxf(o[3] + sd.a.w, 0.0f);
             }
             if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
             if (P.out_hi) cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
-        } else if (P.mode == 1) {
+        } else if (kMode == 1) {
             // SepConvGRU gates (update.py:45-50, 53-58): channels [0, cout/2) = z -> fp32; [cout/2, cout) = r -> planes of r * h
             const int half = P.cout >> 1;
             if (co < half) {
@@ -215,6 +229,7 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
 // 16 accumulator columns of the warp's 32 pixels, already transposed through shared memory: lane = (pixel row it*8 + lane/4,
 // channel group lane%4), i.e. 4 lanes cover 64 contiguous bytes of one pixel and a warp instruction touches 8 pixels.
 // stage: [32 rows][4 chunks of 16 B], chunk k of row r stored at k ^ ((r >> 1) & 3) (conflict-free both ways).
+template <int kMode>
 __device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const float *stage, const float *sbias, int co, const size_t *pix,
                                                  uint32_t inside_mask, int lane) {
     CvSide sd[4];
@@ -223,11 +238,11 @@ __device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const floa
     for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2);
         acc[it] = *reinterpret_cast<const float4 *>(stage + r * 16 + (((lane & 3) ^ ((r >> 1) & 3)) << 2));
-        if ((inside_mask >> it) & 1u) cv_side_load(P, sd[it], co, pix[it]);
+        if ((inside_mask >> it) & 1u) cv_side_load<kMode>(P, sd[it], co, pix[it]);
     }
 #pragma unroll
     for (int it = 0; it < 4; ++it)
-        if ((inside_mask >> it) & 1u) cv_epilogue_group(P, acc[it], sd[it], sbias, co, pix[it]);
+        if ((inside_mask >> it) & 1u) cv_epilogue_group<kMode>(P, acc[it], sd[it], sbias, co, pix[it]);
 }
 
 // mode 3 ("tap projection"): the activated outputs y[c] of a pixel are not stored; instead the epilogue evaluates the
@@ -288,6 +303,55 @@ __device__ __forceinline__ void cv_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
         umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
     }
 }
+// ---- issuer-side helpers on raw shared-memory addresses (no generic-pointer arithmetic on the critical path) ----
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+    const long long t0 = clock64();
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (!ok && clock64() - t0 > 4000000000LL) {
+            printf("rpe_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    } while (!ok);
+}
+template <bool kPair>
+__device__ __forceinline__ void cv_commit_u32(uint32_t bar) {
+    if (kPair)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                     "h"((uint16_t)3)
+                     : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major, 128-byte swizzle, 8-row groups 1024 bytes apart: constant upper word of the shared-memory descriptor
+constexpr uint32_t kCvDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t cv_desc(uint32_t lo) { return ((uint64_t)kCvDescHi << 32) | (uint64_t)lo; }
+// `ksteps` (1..4) MMAs of 16 channels each over one 64-channel K block; consecutive K steps are 32 bytes apart
+template <bool kPair>
+__device__ __forceinline__ void cv_mma_k(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate, int ksteps) {
+    if (ksteps == kCvBK / 16) {
+        cv_mma<kPair>(d_tmem, cv_desc(a_lo), cv_desc(b_lo), idesc, accumulate);
+        cv_mma<kPair>(d_tmem, cv_desc(a_lo + 2u), cv_desc(b_lo + 2u), idesc, 1u);
+        cv_mma<kPair>(d_tmem, cv_desc(a_lo + 4u), cv_desc(b_lo + 4u), idesc, 1u);
+        cv_mma<kPair>(d_tmem, cv_desc(a_lo + 6u), cv_desc(b_lo + 6u), idesc, 1u);
+    } else {
+        for (int k = 0; k < ksteps; ++k) {
+            cv_mma<kPair>(d_tmem, cv_desc(a_lo + 2u * k), cv_desc(b_lo + 2u * k), idesc, accumulate);
+            accumulate = 1u;
+        }
+    }
+}
 template <bool kPair>
 __device__ __forceinline__ void cv_commit(uint64_t *bar) {
     if (kPair) umma_commit_pair(bar, 3);
@@ -319,7 +383,7 @@ __device__ __forceinline__ void cv_release_acc(uint64_t *bar, uint32_t cluster_a
 // the weight tile, the leader (rank 0) issues M = 256 MMAs that read both shared memories and write both tensor memories,
 // and every TMA load of either CTA counts its bytes on the leader's "full" barrier; the MMA commits are multicast to the
 // "empty" / "accumulator full" barriers of both CTAs.
-template <bool kPair>
+template <bool kPair, int kMode>
 __device__ __forceinline__ void conv_body(const ConvParams &P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -338,10 +402,11 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
     for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
     // mode 3: projection weights [cout <= 256][18] fp32 behind the bias (rest of the bias area + the unused staging tiles)
     float *w2s = sbias + 256;
-    if (P.mode == 3)
+    if (kMode == 3)
         for (int i = threadIdx.x; i < P.cout * kCvProj; i += kCvThreads) w2s[i] = P.aux2[i];
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int rank = kPair ? (int)cluster_ctarank() : 0;
     const int px_tiles = P.N * P.tiles_min * P.tiles_maj;
     const int num_units = (kPair ? (px_tiles + 1) / 2 : px_tiles) * P.n_blocks;
@@ -461,80 +526,85 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         }
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (the leader CTA in pair mode) =====================
-        if (elect_one()) {
-            // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128 (256 across a CTA pair)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
-                                   ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            bool b_ready = (P.dbg & 1) != 0;
-            const bool no_load = (P.dbg & 1) != 0, no_mma = (P.dbg & 2) != 0;
-            for (int u = u_first; u < num_units; u += u_step) {
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kCvMaxBN);
-                uint32_t accumulate = 0;
-                for (int s = 0; s < P.n_src; ++s)
-                    for (int cb = 0; cb < P.cblocks[s]; ++cb) {
-                        const int ksteps = (cb == P.cblocks[s] - 1) ? P.ksteps_last[s] : kCvBK / 16;
-                        for (int tm = 0; tm < P.kmin; ++tm)
-                            for (int tj = 0; tj < P.kmaj; ++tj) {
-                                if ((!P.reuse || tj == 0) && !no_load) {
-                                    mbar_wait(&a_full[sa], pa);
+        // The WHOLE warp walks the loop nest, so that every address / descriptor / barrier computation is warp-uniform (uniform
+        // registers, which is where tcgen05.mma takes its descriptors from); only the MMAs and commits are predicated on one
+        // elected lane.  The issuer's instruction stream is the critical path of the kernel: one 128-cycle MMA per ~20 issue slots.
+        const bool leader = elect_one();
+        // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128 (256 across a CTA pair)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+                               ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
+        const bool no_load = (P.dbg & 1) != 0, no_mma = (P.dbg & 2) != 0;
+        const bool planes2 = P.n_planes == 2, reuse = P.reuse != 0, resident = P.resident_b != 0;
+        // shared-memory descriptors = constant upper word | (address >> 4); ring positions advance the low word only
+        const uint32_t a_base16 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16), b_base16 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+        const uint32_t a_stage16 = P.a_stage_bytes >> 4, a_plane16 = P.a_plane_bytes >> 4, b_plane16 = P.b_plane_bytes >> 4;
+        const uint32_t a_full_u = smem_u32(a_full), a_empty_u = smem_u32(a_empty), b_full_u = smem_u32(b_full), b_empty_u = smem_u32(b_empty);
+        const uint32_t t_full_u = smem_u32(tmem_full), t_empty_u = smem_u32(tmem_empty);
+        const int n_a = P.n_a_stages, n_b = P.n_b_stages, kmin = P.kmin, kmaj = P.kmaj, taps = P.kmin * P.kmaj;
+        uint32_t sa = 0, sb = 0, pa = 0, pb = 0, acc = 0, acc_phase = 0;
+        bool b_ready = no_load;
+        for (int u = u_first; u < num_units; u += u_step) {
+            mbar_wait_u32(t_empty_u + acc * 8u, acc_phase ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)kCvMaxBN;
+            uint32_t accumulate = 0;
+            for (int s = 0; s < P.n_src; ++s) {
+                const int ncb = P.cblocks[s];
+                for (int cb = 0; cb < ncb; ++cb) {
+                    const int ksteps = (cb == ncb - 1) ? P.ksteps_last[s] : kCvBK / 16;
+                    for (int tm = 0; tm < kmin; ++tm)
+                        for (int tj = 0; tj < kmaj; ++tj) {
+                            if ((!reuse || tj == 0) && !no_load) mbar_wait_u32(a_full_u + sa * 8u, pa);
+                            const uint32_t a_hi = a_base16 + sa * a_stage16 + (reuse ? (uint32_t)tj * 64u : 0u);   // tap shift: 1024 B
+                            if (resident) {
+                                if (!b_ready) {
+                                    mbar_wait_u32(b_full_u, 0);
+                                    b_ready = true;
                                 }
-                                const uint32_t a0 = smem_u32(sA + (size_t)sa * P.a_stage_bytes) + (P.reuse ? (uint32_t)tj * 1024u : 0u);
-                                const uint64_t da_hi = cv_sw128_desc(a0);
-                                if (P.resident_b) {
-                                    if (!b_ready) {
-                                        mbar_wait(&b_full[0], 0);
-                                        b_ready = true;
+                                tcgen05_fence_after();
+                                const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
+                                const uint32_t b_hi = b_base16 + (uint32_t)(((P.cb_base[s] + cb) * taps + tap) * P.n_planes) * b_plane16;
+                                if (leader && !no_mma) {
+                                    cv_mma_k<kPair>(d_tmem, a_hi, b_hi, idesc, accumulate, ksteps);
+                                    if (planes2) {
+                                        cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
+                                        cv_mma_k<kPair>(d_tmem, a_hi, b_hi + b_plane16, idesc, 1u, ksteps);
                                     }
-                                    tcgen05_fence_after();
-                                    const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
-                                    const uint32_t b0 = smem_u32(sB) + (uint32_t)(((P.cb_base[s] + cb) * (P.kmin * P.kmaj) + tap) * P.n_planes) * P.b_plane_bytes;
-                                    const uint64_t db_hi = cv_sw128_desc(b0);
-                                    for (int k = 0; k < ksteps; ++k) {
-                                        if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
-                                        accumulate = 1;
-                                    }
-                                    if (P.n_planes == 2) {
-                                        const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes), db_lo = cv_sw128_desc(b0 + P.b_plane_bytes);
-                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
-                                    }
-                                } else {
-                                    if (!no_load) mbar_wait(&b_full[sb], pb);
-                                    tcgen05_fence_after();
-                                    const uint64_t db_hi = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
-                                    for (int k = 0; k < ksteps; ++k) {
-                                        if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, accumulate);
-                                        accumulate = 1;
-                                    }
-                                    if (P.n_planes == 2) {
-                                        const uint64_t da_lo = cv_sw128_desc(a0 + P.a_plane_bytes);
-                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_lo + (uint64_t)(2 * k), db_hi + (uint64_t)(2 * k), idesc, 1u);
-                                        if (!no_load) cv_commit<kPair>(&b_empty[sb]);
-                                        if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
-                                        if (!no_load) mbar_wait(&b_full[sb], pb);
-                                        tcgen05_fence_after();
-                                        const uint64_t db_lo = cv_sw128_desc(smem_u32(sB + (size_t)sb * P.b_plane_bytes));
-                                        for (int k = 0; k < ksteps; ++k) if (!no_mma) cv_mma<kPair>(d_tmem, da_hi + (uint64_t)(2 * k), db_lo + (uint64_t)(2 * k), idesc, 1u);
-                                    }
-                                    if (!no_load) cv_commit<kPair>(&b_empty[sb]);
-                                    if (++sb == P.n_b_stages) sb = 0, pb ^= 1;
                                 }
-                                if (!P.reuse || tj == P.kmaj - 1) {
-                                    if (!no_load) cv_commit<kPair>(&a_empty[sa]);
-                                    if (++sa == P.n_a_stages) sa = 0, pa ^= 1;
+                            } else {
+                                if (!no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
+                                tcgen05_fence_after();
+                                const uint32_t b_hi = b_base16 + sb * b_plane16;
+                                if (leader) {
+                                    if (!no_mma) {
+                                        cv_mma_k<kPair>(d_tmem, a_hi, b_hi, idesc, accumulate, ksteps);
+                                        if (planes2) cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
+                                    }
+                                    if (!no_load) cv_commit_u32<kPair>(b_empty_u + sb * 8u);
+                                }
+                                if (++sb == (uint32_t)n_b) sb = 0, pb ^= 1u;
+                                if (planes2) {
+                                    if (!no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
+                                    tcgen05_fence_after();
+                                    if (leader) {
+                                        if (!no_mma) cv_mma_k<kPair>(d_tmem, a_hi, b_base16 + sb * b_plane16, idesc, 1u, ksteps);
+                                        if (!no_load) cv_commit_u32<kPair>(b_empty_u + sb * 8u);
+                                    }
+                                    if (++sb == (uint32_t)n_b) sb = 0, pb ^= 1u;
                                 }
                             }
-                    }
-                cv_commit<kPair>(&tmem_full[acc]);
-                if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
+                            accumulate = 1;
+                            if (!reuse || tj == kmaj - 1) {
+                                if (leader && !no_load) cv_commit_u32<kPair>(a_empty_u + sa * 8u);
+                                if (++sa == (uint32_t)n_a) sa = 0, pa ^= 1u;
+                            }
+                        }
+                }
             }
+            if (leader) cv_commit_u32<kPair>(t_full_u + acc * 8u);
+            if (++acc == (uint32_t)kCvAcc) acc = 0, acc_phase ^= 1u;
         }
+        __syncwarp();
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         // TMEM lane = pixel row of the tile.  Every 16 accumulator columns are transposed through a 2 KB per-warp staging
@@ -561,7 +631,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
             const int c_begin = chalf * ((n_chunks + 1) / 2), c_end = chalf == 0 ? (n_chunks + 1) / 2 : n_chunks;
             const uint32_t empty_addr = kPair ? mapa_shared(smem_u32(&tmem_empty[acc]), 0) : 0u;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kCvMaxBN);
-            if (P.mode == 3) {
+            if (kMode == 3) {
                 // ---- tap projection: lane = accumulator row = pixel, no transposition, nothing but 18 partial sums is stored
                 float proj[kCvProj];
 #pragma unroll
@@ -600,7 +670,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                         *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                     __syncwarp();
-                    cv_epilogue_half(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane);
+                    cv_epilogue_half<kMode>(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane);
                 }
             }
             if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
@@ -615,10 +685,36 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
     }
 }
 
-__global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_constant__ ConvParams P) { conv_body<false>(P); }
+// One instantiation per epilogue mode: each kernel carries only its own epilogue (the instruction footprint of the three
+// concurrently running roles has to stay inside the instruction cache).
+template <int kMode>
+__global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_constant__ ConvParams P) {
+    conv_body<false, kMode>(P);
+}
 
+template <int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_bf16_pair_kernel(const __grid_constant__ ConvParams P) {
-    conv_body<true>(P);
+    conv_body<true, kMode>(P);
+}
+
+template <int kMode>
+static cudaError_t cv_launch(const ConvParams &p, int grid, bool pair, cudaStream_t stream, bool set_attr) {
+    if (set_attr) {
+        cudaError_t e = cudaFuncSetAttribute(conv_bf16_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_bf16_pair_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
+        return e;
+    }
+    if (pair) conv_bf16_pair_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
+    else conv_bf16_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
+    return cudaSuccess;
+}
+static cudaError_t cv_dispatch(const ConvParams &p, int grid, bool pair, cudaStream_t stream, bool set_attr) {
+    switch (p.mode) {
+        case 1: return cv_launch<1>(p, grid, pair, stream, set_attr);
+        case 2: return cv_launch<2>(p, grid, pair, stream, set_attr);
+        case 3: return cv_launch<3>(p, grid, pair, stream, set_attr);
+        default: return cv_launch<0>(p, grid, pair, stream, set_attr);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -795,7 +891,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
             ok = d->aux2 && d->out_f32 && !d->out_hi && !d->pre && !d->res && n_blocks == 1 && d->cout <= 256 && bn >= 32 &&
                  d->cout == d->cout_pad && (d->f32_ld % 2) == 0 && (d->f32_offset % 2) == 0 && d->f32_ld >= d->f32_offset + 2 * kCvProj;
         else
-            ok = (p.mode == 1 || p.mode == 2) && d->aux && aligned16(d->aux) && (d->aux_ld % 4) == 0 && d->out_hi && d->out_lo &&
+            ok = (p.mode == 1 || p.mode == 2) && d->activation == (p.mode == 1 ? 2 : 3) && d->aux && aligned16(d->aux) && (d->aux_ld % 4) == 0 && d->out_hi && d->out_lo &&
                  (d->cout % 8) == 0 && n_blocks == 1 &&
                  (p.mode == 1 ? (d->out_f32 != nullptr) : (d->aux2 != nullptr && aligned16(d->aux2) && (d->aux2_ld % 4) == 0));
         if (!ok) {
@@ -814,15 +910,18 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         pl->grid = sm_count() < tiles ? sm_count() : tiles;
         if (pl->grid < 1) pl->grid = 1;
     }
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
+    static bool attr[4] = {false, false, false, false};
+    if (p.mode < 0 || p.mode > 3) {
+        delete pl;
+        return RPE_ERR_INVALID_ARG;
+    }
+    if (!attr[p.mode]) {
+        cudaError_t e = cv_dispatch(p, 0, false, nullptr, true);
         if (e != cudaSuccess) {
             delete pl;
             return cuda_fail(e);
         }
-        attr = true;
+        attr[p.mode] = true;
     }
     *plan_out = pl;
     return RPE_OK;
@@ -832,8 +931,7 @@ int rpe_conv_plan_run(void *plan, void *stream) {
     using namespace rpe;
     if (!plan) return RPE_ERR_INVALID_ARG;
     ConvPlan *pl = reinterpret_cast<ConvPlan *>(plan);
-    if (pl->pair) conv_bf16_pair_kernel<<<pl->grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(pl->p);
-    else conv_bf16_kernel<<<pl->grid, kCvThreads, kCvSmem, (cudaStream_t)stream>>>(pl->p);
+    cv_dispatch(pl->p, pl->grid, pl->pair, (cudaStream_t)stream, false);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

@@ -177,6 +177,34 @@ def test_gauss_newton_solver_mode(golden_dir):
     assert rot < 5e-3 and trans < 5e-2
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_graphed_streaming_tracker_matches_reference(golden_dir, precision):
+    """config['cuda_graph']: PoseEstimator.forward replays one captured CUDA graph per frame (latency path).  Same trajectory
+    as the reference, and as the eager per-frame tracker, frame by frame; a second sequence on the same estimator re-uses
+    the captured graph."""
+    _need_ckpt()
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_estimator import PoseEstimator
+    from rpe_b200.lie import SE3
+    g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
+    W, H = [int(v) for v in g["size"]]
+    _, eager, _ = _run_tracker(g, precision=precision)
+    est = PoseEstimator(dict(SLAM, precision=precision, cuda_graph=True), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    for rep in range(2):
+        est.frame = est.last_frame = None
+        est.last_pose = SE3.Identity(1, device="cuda")
+        for i in range(g["imgs_l"].shape[0]):
+            limg = torch.from_numpy(g["imgs_l"][i].astype(np.float32))[None].cuda()
+            rimg = torch.from_numpy(g["imgs_r"][i].astype(np.float32))[None].cuda()
+            mask = torch.from_numpy(unpack(g["masks_in"][i], (1, 1, H, W))).cuda()
+            pose = est(limg, rimg, mask)[0].vec().cpu().numpy().reshape(7)
+            rot, trans = _pose_err(pose, g["traj"][i]) if i else (0.0, 0.0)
+            rot_e, trans_e = _pose_err(pose, eager[i]) if i else (0.0, 0.0)
+            print(f"graphed/{precision} pass {rep} frame {i}: vs reference rot {rot:.2e} trans {trans:.2e}; vs eager rot {rot_e:.2e} trans {trans_e:.2e}")
+            assert rot < 1e-4 and trans < 1e-4 and rot_e < 1e-5 and trans_e < 1e-5
+    assert not est.check_failures()
+
+
 @pytest.mark.parametrize("chunk,graphs", [(1, False), (2, False), (2, True)])
 def test_batched_engine_matches_reference(golden_dir, chunk, graphs):
     """PoseEstimator.infer_sequence (chunked engine, feature reuse, optional CUDA graph, host composition through
