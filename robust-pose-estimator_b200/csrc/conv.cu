@@ -107,14 +107,21 @@ __device__ __forceinline__ float cv_activate_rt(float v, int act) {
 __device__ __forceinline__ float cv_sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float cv_tanh_fast(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
 
+// Kernel kinds (template parameter kK): the epilogue of each is compiled for exactly the tensors it touches, because the epilogue
+// warps share their issue slots with the MMA issuer and the instruction cache with both producers.
+//   0 generic mode 0 (every optional tensor tested at run time)      1 GRU z|r gates (mode 1)      2 GRU candidate + state (mode 2)
+//   3 tap projection (mode 3)      4 mode 0, split planes only (no addend / residual / fp32 copy)      5 mode 0, fp32 only
+constexpr int kKGeneric = 0, kKGates = 1, kKState = 2, kKProj = 3, kKPlanes = 4, kKF32 = 5;
+
 // fp32 x4 -> bf16 hi / lo planes (hi = bf16(v), lo = bf16(v - hi)), packed conversions
-__device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, size_t o, const float *v) {
+template <bool kLo>
+__device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, uint32_t o, const float *v) {
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
     uint2 hv;
     hv.x = *reinterpret_cast<const uint32_t *>(&h01);
     hv.y = *reinterpret_cast<const uint32_t *>(&h23);
     *reinterpret_cast<uint2 *>(P.out_hi + o) = hv;
-    if (P.out_lo) {
+    if (kLo) {
         const float r0 = v[0] - __uint_as_float(hv.x << 16), r1 = v[1] - __uint_as_float(hv.x & 0xffff0000u);
         const float r2 = v[2] - __uint_as_float(hv.y << 16), r3 = v[3] - __uint_as_float(hv.y & 0xffff0000u);
         const __nv_bfloat162 l01 = __floats2bfloat162_rn(r0, r1), l23 = __floats2bfloat162_rn(r2, r3);
@@ -125,92 +132,102 @@ __device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, size_t o, c
     }
 }
 
-// Ragged tail (1..3 channels) of an output-channel count that is not a multiple of 4.
+// Ragged tail (1..3 channels) of an output-channel count that is not a multiple of 4 (mode 0 only).
 __device__ __noinline__ void cv_epilogue_tail(const ConvParams &P, int act, float a0, float a1, float a2, const float *sbias, int co,
-                                              size_t pix) {
+                                              uint32_t pix) {
     const float acc[3] = {a0, a1, a2};
     for (int k = 0; k < 3 && co + k < P.cout; ++k) {
         float r = acc[k] + sbias[co + k];
-        if (P.pre) r += __ldg(P.pre + pix * P.pre_ld + co + k);
+        if (P.pre) r += __ldg(P.pre + (size_t)pix * P.pre_ld + co + k);
         r = cv_activate_rt(r, act) * P.scale;
-        if (P.res) r = fmaxf(r + __ldg(P.res + pix * P.res_ld + co + k), 0.0f);
-        if (P.out_f32) P.out_f32[pix * P.f32_ld + P.f32_off + co + k] = r;
+        if (P.res) r = fmaxf(r + __ldg(P.res + (size_t)pix * P.res_ld + co + k), 0.0f);
+        if (P.out_f32) P.out_f32[(size_t)pix * P.f32_ld + P.f32_off + co + k] = r;
         if (P.out_hi) {
             const __nv_bfloat16 h = __float2bfloat16_rn(r);
-            P.out_hi[pix * P.bf_ld + P.bf_off + co + k] = h;
-            if (P.out_lo) P.out_lo[pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(r - __bfloat162float(h));
+            P.out_hi[(size_t)pix * P.bf_ld + P.bf_off + co + k] = h;
+            if (P.out_lo) P.out_lo[(size_t)pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(r - __bfloat162float(h));
         }
     }
 }
 
-// Side inputs of one group of 4 channels (addend, residual / hidden state, update gate); loaded for several groups at once
-// so that their latencies overlap.  Every element is read at most once before any write to it.
+// Side inputs of one group of 4 channels (addend, residual / hidden state, update gate).  They do not depend on the
+// accumulators, so they are requested one 16-column chunk ahead.  Every element is read at most once before any write to it.
+// Element offsets are 32-bit (the plan rejects tensors of 2^32 elements or more).
 struct CvSide {
     float4 pre, a, z;
 };
 
-template <int kMode>
-__device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, int co, size_t pix) {
+template <int kK>
+__device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, int co, uint32_t pix) {
+    if (kK == kKPlanes || kK == kKF32 || kK == kKProj) return;
     if (co + 3 >= P.cout) return;
-    if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + pix * P.pre_ld + co));
-    if (kMode == 0) {
-        if (P.res) sd.a = __ldg(reinterpret_cast<const float4 *>(P.res + pix * P.res_ld + co));
-    } else if (kMode == 1) {
+    if (kK == kKGeneric) {
+        if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
+        if (P.res) sd.a = __ldg(reinterpret_cast<const float4 *>(P.res + (pix * (uint32_t)P.res_ld + co)));
+    } else if (kK == kKGates) {
+        sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
         const int half = P.cout >> 1;
-        if (co >= half) sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + pix * P.aux_ld + (co - half)));
+        if (co >= half) sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + (co - half))));
     } else {
-        sd.z = __ldg(reinterpret_cast<const float4 *>(P.aux2 + pix * P.aux2_ld + co));
-        sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + pix * P.aux_ld + co));
+        sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
+        sd.z = __ldg(reinterpret_cast<const float4 *>(P.aux2 + (pix * (uint32_t)P.aux2_ld + co)));
+        sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co)));
     }
 }
 
 // One group of 4 consecutive output channels of one pixel: bias / addend / activation / scale / residual / stores.
-template <int kMode>
-__device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const float4 acc, const CvSide &sd, const float *sbias, int co,
-                                                  size_t pix) {
+template <int kK>
+__device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const float4 acc, const CvSide &sd, const float4 b, const float *sbias,
+                                                  int co, uint32_t pix) {
     if (co >= P.cout) return;
     float o[4];
     if (co + 3 < P.cout) {
-        const float4 b = *reinterpret_cast<const float4 *>(sbias + co);
         o[0] = acc.x + b.x, o[1] = acc.y + b.y, o[2] = acc.z + b.z, o[3] = acc.w + b.w;
-        if (P.pre) o[0] += sd.pre.x, o[1] += sd.pre.y, o[2] += sd.pre.z, o[3] += sd.pre.w;
-        // GRU modes fix the activation (z|r: sigmoid, q: tanh) and use the hardware exponential / reciprocal (abs. error
-        // < 5e-7, far below the 2^-16 of the split operands): the epilogue shares its issue slots with the MMA issuer
-        if (kMode == 1) {
+        if (kK == kKGates || kK == kKState || (kK == kKGeneric && P.pre)) o[0] += sd.pre.x, o[1] += sd.pre.y, o[2] += sd.pre.z, o[3] += sd.pre.w;
+        // GRU kinds fix the activation (z|r: sigmoid, q: tanh) and use the hardware exponential / reciprocal (abs. error
+        // < 5e-7, far below the 2^-16 of the split operands); planes / fp32 kinds only know relu / none (checked by the plan)
+        if (kK == kKGates) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = cv_sigmoid_fast(o[k]);
-        } else if (kMode == 2) {
+        } else if (kK == kKState) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = cv_tanh_fast(o[k]);
         } else if (P.act == 1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.0f);
-        } else if (P.act == 2) {
+        } else if (kK == kKGeneric && P.act == 2) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = 1.0f / (1.0f + expf(-o[k]));
-        } else if (P.act == 3) {
+        } else if (kK == kKGeneric && P.act == 3) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] = tanhf(o[k]);
         }
-        if (P.scale != 1.0f) {
+        if ((kK == kKGeneric || kK == kKF32) && P.scale != 1.0f) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) o[k] *= P.scale;
         }
-        if (kMode == 0) {
+        if (kK == kKGeneric) {
             if (P.res) {
                 o[0] = fmaxf(o[0] + sd.a.x, 0.0f), o[1] = fmaxf(o[1] + sd.a.y, 0.0f);
                 o[2] = fmaxf(o[2] + sd.a.z, 0.0f), o[3] = fmaxf(o[3] + sd.a.w, 0.0f);
             }
-            if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
-            if (P.out_hi) cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
-        } else if (kMode == 1) {
+            if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + (pix * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
+            if (P.out_hi) {
+                if (P.out_lo) cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+                else cv_store_bf16x4<false>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+            }
+        } else if (kK == kKPlanes) {
+            cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+        } else if (kK == kKF32) {
+            *reinterpret_cast<float4 *>(P.out_f32 + (pix * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
+        } else if (kK == kKGates) {
             // SepConvGRU gates (update.py:45-50, 53-58): channels [0, cout/2) = z -> fp32; [cout/2, cout) = r -> planes of r * h
             const int half = P.cout >> 1;
             if (co < half) {
-                *reinterpret_cast<float4 *>(P.out_f32 + pix * P.f32_ld + P.f32_off + co) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4 *>(P.out_f32 + (pix * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
                 o[0] *= sd.a.x, o[1] *= sd.a.y, o[2] *= sd.a.z, o[3] *= sd.a.w;
-                cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + (co - half), o);
+                cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + (co - half), o);
             }
         } else {
             // candidate state q = tanh(.) and the state update h = (1 - z) * h + z * q, fp32 in place + planes
@@ -218,31 +235,38 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
             o[1] = (1.0f - sd.z.y) * sd.a.y + sd.z.y * o[1];
             o[2] = (1.0f - sd.z.z) * sd.a.z + sd.z.z * o[2];
             o[3] = (1.0f - sd.z.w) * sd.a.w + sd.z.w * o[3];
-            *reinterpret_cast<float4 *>(P.aux + pix * P.aux_ld + co) = make_float4(o[0], o[1], o[2], o[3]);
-            cv_store_bf16x4(P, pix * P.bf_ld + P.bf_off + co, o);
+            *reinterpret_cast<float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co)) = make_float4(o[0], o[1], o[2], o[3]);
+            cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
         }
-    } else {                                           // ragged tail of a channel count that is not a multiple of 4
+    } else if (kK == kKGeneric || kK == kKPlanes || kK == kKF32) {      // ragged tail of a channel count that is not a multiple of 4
         cv_epilogue_tail(P, P.act, acc.x, acc.y, acc.z, sbias, co, pix);
     }
+}
+
+// Side inputs of the warp's 32 pixels for one 16-column chunk (issued a chunk ahead of their use).
+template <int kK>
+__device__ __forceinline__ void cv_side_load4(const ConvParams &P, CvSide *sd, int co, const uint32_t *pix, uint32_t inside_mask) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+        if ((inside_mask >> it) & 1u) cv_side_load<kK>(P, sd[it], co, pix[it]);
 }
 
 // 16 accumulator columns of the warp's 32 pixels, already transposed through shared memory: lane = (pixel row it*8 + lane/4,
 // channel group lane%4), i.e. 4 lanes cover 64 contiguous bytes of one pixel and a warp instruction touches 8 pixels.
 // stage: [32 rows][4 chunks of 16 B], chunk k of row r stored at k ^ ((r >> 1) & 3) (conflict-free both ways).
-template <int kMode>
-__device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const float *stage, const float *sbias, int co, const size_t *pix,
-                                                 uint32_t inside_mask, int lane) {
-    CvSide sd[4];
+template <int kK>
+__device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const float *stage, const float *sbias, int co, const uint32_t *pix,
+                                                 uint32_t inside_mask, int lane, const CvSide *sd) {
     float4 acc[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2);
         acc[it] = *reinterpret_cast<const float4 *>(stage + r * 16 + (((lane & 3) ^ ((r >> 1) & 3)) << 2));
-        if ((inside_mask >> it) & 1u) cv_side_load<kMode>(P, sd[it], co, pix[it]);
     }
+    const float4 b = *reinterpret_cast<const float4 *>(sbias + co);          // the bias area is padded to bn * n_blocks floats
 #pragma unroll
     for (int it = 0; it < 4; ++it)
-        if ((inside_mask >> it) & 1u) cv_epilogue_group<kMode>(P, acc[it], sd[it], sbias, co, pix[it]);
+        if ((inside_mask >> it) & 1u) cv_epilogue_group<kK>(P, acc[it], sd[it], b, sbias, co, pix[it]);
 }
 
 // mode 3 ("tap projection"): the activated outputs y[c] of a pixel are not stored; instead the epilogue evaluates the
@@ -383,7 +407,7 @@ __device__ __forceinline__ void cv_release_acc(uint64_t *bar, uint32_t cluster_a
 // the weight tile, the leader (rank 0) issues M = 256 MMAs that read both shared memories and write both tensor memories,
 // and every TMA load of either CTA counts its bytes on the leader's "full" barrier; the MMA commits are multicast to the
 // "empty" / "accumulator full" barriers of both CTAs.
-template <bool kPair, int kMode>
+template <bool kPair, int kK>
 __device__ __forceinline__ void conv_body(const ConvParams &P) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -402,7 +426,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
     for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
     // mode 3: projection weights [cout <= 256][18] fp32 behind the bias (rest of the bias area + the unused staging tiles)
     float *w2s = sbias + 256;
-    if (kMode == 3)
+    if (kK == kKProj)
         for (int i = threadIdx.x; i < P.cout * kCvProj; i += kCvThreads) w2s[i] = P.aux2[i];
 
     // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops in uniform registers
@@ -616,7 +640,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         uint32_t acc_phase = 0;
         for (int u = u_first; u < num_units; u += u_step) {
             const CvTile t = cv_decode<kPair>(P, u, rank);
-            size_t pix[4];
+            uint32_t pix[4];
             uint32_t inside_mask = 0;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
@@ -625,13 +649,13 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
                 const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
                 if (y < P.OH && x < P.OW && !t.ghost) inside_mask |= 1u << it;
-                pix[it] = ((size_t)t.img * P.OH + y) * P.OW + x;
+                pix[it] = (uint32_t)((t.img * P.OH + y) * P.OW + x);
             }
             const int n_chunks = P.bn / 16;
             const int c_begin = chalf * ((n_chunks + 1) / 2), c_end = chalf == 0 ? (n_chunks + 1) / 2 : n_chunks;
             const uint32_t empty_addr = kPair ? mapa_shared(smem_u32(&tmem_empty[acc]), 0) : 0u;
             const uint32_t taddr0 = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * kCvMaxBN);
-            if (kMode == 3) {
+            if (kK == kKProj) {
                 // ---- tap projection: lane = accumulator row = pixel, no transposition, nothing but 18 partial sums is stored
                 float proj[kCvProj];
 #pragma unroll
@@ -656,6 +680,9 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 }
             } else {
                 const int co_lane = t.nb * P.bn + ((lane & 3) << 2);
+                // side inputs of the first chunk are requested before the accumulator is even complete
+                CvSide sd[4], sd_next[4];
+                if (c_begin < c_end && !(P.dbg & 4)) cv_side_load4<kK>(P, sd, co_lane + c_begin * 16, pix, inside_mask);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tcgen05_fence_after();
                 if (c_begin >= c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);   // nothing to drain (bn = 16)
@@ -664,13 +691,18 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                     cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
                     if (c + 1 == c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);
                     if (P.dbg & 4) continue;
+                    if (c + 1 < c_end) cv_side_load4<kK>(P, sd_next, co_lane + (c + 1) * 16, pix, inside_mask);
                     __syncwarp();                                  // previous chunk's reads of the staging tile are done
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                     __syncwarp();
-                    cv_epilogue_half<kMode>(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane);
+                    cv_epilogue_half<kK>(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane, sd);
+                    if (kK == kKGeneric || kK == kKGates || kK == kKState) {
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) sd[it] = sd_next[it];
+                    }
                 }
             }
             if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
@@ -708,12 +740,14 @@ static cudaError_t cv_launch(const ConvParams &p, int grid, bool pair, cudaStrea
     else conv_bf16_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
     return cudaSuccess;
 }
-static cudaError_t cv_dispatch(const ConvParams &p, int grid, bool pair, cudaStream_t stream, bool set_attr) {
-    switch (p.mode) {
-        case 1: return cv_launch<1>(p, grid, pair, stream, set_attr);
-        case 2: return cv_launch<2>(p, grid, pair, stream, set_attr);
-        case 3: return cv_launch<3>(p, grid, pair, stream, set_attr);
-        default: return cv_launch<0>(p, grid, pair, stream, set_attr);
+static cudaError_t cv_dispatch(int kind, const ConvParams &p, int grid, bool pair, cudaStream_t stream, bool set_attr) {
+    switch (kind) {
+        case kKGates: return cv_launch<kKGates>(p, grid, pair, stream, set_attr);
+        case kKState: return cv_launch<kKState>(p, grid, pair, stream, set_attr);
+        case kKProj: return cv_launch<kKProj>(p, grid, pair, stream, set_attr);
+        case kKPlanes: return cv_launch<kKPlanes>(p, grid, pair, stream, set_attr);
+        case kKF32: return cv_launch<kKF32>(p, grid, pair, stream, set_attr);
+        default: return cv_launch<kKGeneric>(p, grid, pair, stream, set_attr);
     }
 }
 
@@ -736,6 +770,7 @@ struct ConvPlan {
     ConvParams p;
     int grid;
     bool pair;             // CTA-pair kernel (cta_group::2)
+    int kind;              // kernel kind (kK*): which epilogue instantiation runs
     double flops;          // real multiply-adds x 2 of one run (all products of the split arithmetic)
 };
 
@@ -910,18 +945,34 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         pl->grid = sm_count() < tiles ? sm_count() : tiles;
         if (pl->grid < 1) pl->grid = 1;
     }
-    static bool attr[4] = {false, false, false, false};
     if (p.mode < 0 || p.mode > 3) {
         delete pl;
         return RPE_ERR_INVALID_ARG;
     }
-    if (!attr[p.mode]) {
-        cudaError_t e = cv_dispatch(p, 0, false, nullptr, true);
+    {   // 32-bit element offsets in the epilogue: no tensor row index times leading dimension may reach 2^32
+        int max_ld = d->f32_ld > d->bf_ld ? d->f32_ld : d->bf_ld;
+        const int lds[4] = {d->pre ? d->pre_ld : 0, d->res ? d->res_ld : 0, d->aux ? d->aux_ld : 0, (d->aux2 && p.mode == 2) ? d->aux2_ld : 0};
+        for (int k = 0; k < 4; ++k) max_ld = lds[k] > max_ld ? lds[k] : max_ld;
+        if ((double)d->N * OH * OW * (double)max_ld >= 4294967296.0) {
+            delete pl;
+            return RPE_ERR_INVALID_ARG;
+        }
+    }
+    // kernel kind: the GRU / projection modes have their own epilogues; mode 0 runs a lean epilogue when it only writes split
+    // planes or only fp32 (the convolutions of the motion encoder and of the instance-norm encoder), else the generic one
+    pl->kind = p.mode;
+    if (p.mode == 0 && !d->pre && !d->res && d->activation <= 1 && !getenv("RPE_CONV_GENERIC")) {
+        if (d->out_hi && d->out_lo && !d->out_f32 && d->out_scale == 1.0f) pl->kind = kKPlanes;
+        else if (d->out_f32 && !d->out_hi) pl->kind = kKF32;
+    }
+    static bool attr[6] = {false, false, false, false, false, false};
+    if (!attr[pl->kind]) {
+        cudaError_t e = cv_dispatch(pl->kind, p, 0, false, nullptr, true);
         if (e != cudaSuccess) {
             delete pl;
             return cuda_fail(e);
         }
-        attr[p.mode] = true;
+        attr[pl->kind] = true;
     }
     *plan_out = pl;
     return RPE_OK;
@@ -931,7 +982,7 @@ int rpe_conv_plan_run(void *plan, void *stream) {
     using namespace rpe;
     if (!plan) return RPE_ERR_INVALID_ARG;
     ConvPlan *pl = reinterpret_cast<ConvPlan *>(plan);
-    cv_dispatch(pl->p, pl->grid, pl->pair, (cudaStream_t)stream, false);
+    cv_dispatch(pl->kind, pl->p, pl->grid, pl->pair, (cudaStream_t)stream, false);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
