@@ -123,7 +123,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} consecutive pairs, oracle/pipeline_ref.py (torch CPU fp32 + numpy fp64 L-BFGS)"},
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def _state_dict(torch):
@@ -170,7 +170,25 @@ ALG_BYTES = {
 }
 
 
+def _emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else that libraries print to fd 1 (the NCCL
+    version banner, torchrun notices) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+_REAL_STDOUT = None
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                                  # fd 1 -> stderr for the whole run (C libraries included)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -179,7 +197,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "tf32", "fp16", "bf16"],
                     help="bf16x3 (default): whole trunk on the hand-written tcgen05 kernels, fp32-equivalent split arithmetic "
                          "(parity-gated); fp32: cuDNN fp32 trunk; tf32 / fp16 / bf16: cuDNN reduced precision (not parity-gated)")
-    ap.add_argument("--chunk", type=int, default=11, help="frames per engine chunk (11 -> 880 conv tiles = 5.95 waves of 148 SMs)")
+    ap.add_argument("--chunk", type=int, default=32, help="frames per engine chunk (measured on B200: 11 -> 318, 22 -> 330, 32 -> 334 pairs/s; fewer, larger launches)")
     ap.add_argument("--pairs", type=int, default=64)
     ap.add_argument("--graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -398,7 +416,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cb, _ = cpu_baseline(L, R, M, seq)
         line["cpu_baseline"] = cb
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
