@@ -387,8 +387,16 @@ def main():
         flops_exec = sum(stage[k]["units"] for k in conv)
         n_launch = sum(stage[k]["launches"] for k in conv)
         achieved = flops_exec / split / (conv_ms * 1e-3) / 1e12
-        roofline = {"kernel": "conv_bf16_kernel", "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tc_peak, "traffic": None, "peak_source": peak_src,
+        traffic = None                              # DRAM bytes per conv launch from the committed ncu capture of this configuration
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+            if tr["config"]["chunk"] == args.chunk and tr["config"]["precision"] == args.precision and args.pairs >= args.chunk:
+                traffic = float(tr["dram_bytes_per_launch"])
+        except (OSError, KeyError, ValueError):
+            pass
+        roofline = {"kernel": "conv_bf16_pair_kernel", "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tc_peak, "traffic": traffic, "traffic_source": "profiles/conv_traffic.json (ncu, launch-weighted mean)" if traffic else None,
+                    "peak_source": peak_src,
                     "avg_launch_us": 1e3 * conv_ms / n_launch, "algorithmic_flops_per_launch": flops_exec / split / n_launch,
                     "executed_tflops": flops_exec / (conv_ms * 1e-3) / 1e12, "executed_frac": flops_exec / (conv_ms * 1e-3) / 1e12 / tc_peak,
                     "note": "algorithmic = fp32-equivalent convolution flops; the bf16x3 split executes 3 bf16 MMAs per multiply-add, "

@@ -159,7 +159,9 @@ int rpe_compose_trajectory_host(const float *rel_host, const float *log_host, in
 
 typedef enum rpe_corr_precision {
     RPE_CORR_TF32 = 0,     /* one tcgen05 kind::tf32 pass (inputs rounded to tf32)                  */
-    RPE_CORR_TF32X3 = 1    /* split hi/lo: hi*hi + lo*hi + hi*lo, fp32-class accuracy               */
+    RPE_CORR_TF32X3 = 1,   /* split hi/lo: hi*hi + lo*hi + hi*lo, fp32-class accuracy               */
+    RPE_CORR_BF16X3 = 2    /* same split on bf16 planes, full-rate kind::f16 MMAs (16 mantissa bits
+                              per operand, the arithmetic of the bf16x3 convolution trunk)          */
 } rpe_corr_precision;
 
 /* Replaces CorrBlock.__init__ / CorrBlock.corr (/root/reference/core/RAFT/core/corr.py:13-27, 52-60):

@@ -9,7 +9,7 @@ _lib = None
 
 POSE_OUT_STRIDE = 64
 SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = 0, 1, 2
-CORR_TF32, CORR_TF32X3 = 0, 1
+CORR_TF32, CORR_TF32X3, CORR_BF16X3 = 0, 1, 2
 
 
 class RpeError(RuntimeError):

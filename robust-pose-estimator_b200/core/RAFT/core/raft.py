@@ -123,7 +123,10 @@ class RAFT(nn.Module):
     def refine(self, fmap1, fmap2, net, inp, iters=12, flow_init=None, upsample=True, all_predictions=False):
         """Correlation pyramid + `iters` GRU updates + convex up-sampling."""
         B, _, h, w = fmap1.shape
-        corr_prec = ops.CORR_TF32X3 if self.precision in ("fp32", "bf16x3") else ops.CORR_TF32
+        # fp32: 3xTF32 split; bf16x3: the same split on bf16 planes (full-rate kind::f16 MMAs, the trunk's own arithmetic)
+        corr_prec = {"fp32": ops.CORR_TF32X3, "bf16x3": ops.CORR_BF16X3}.get(self.precision, ops.CORR_TF32)
+        if fmap1.shape[1] % 64 != 0 and corr_prec == ops.CORR_BF16X3:
+            corr_prec = ops.CORR_TF32X3
         corr_fn = CorrBlock(fmap1, fmap2, radius=self.config["corr_radius"], precision=corr_prec)
         if self.precision == "bf16x3" and not all_predictions:
             if self._tc is None:

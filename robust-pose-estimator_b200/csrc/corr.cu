@@ -31,6 +31,36 @@ __device__ __forceinline__ float to_tf32(float x) {
     return __uint_as_float(r);
 }
 
+// bf16 variant (RPE_CORR_BF16X3): the same [hi | lo | hi] x [hi | hi | lo] arrangement with hi = bf16(x), lo = bf16(x - hi), for the
+// full-rate kind::f16 MMAs (16 mantissa bits per operand, like the convolution trunk's bf16x3 arithmetic).
+__global__ void __launch_bounds__(256) corr_prep_bf16_kernel(const float *__restrict__ fmap, __nv_bfloat16 *__restrict__ out, int C, int Q,
+                                                             int which) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int Kp = 3 * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = c0 + ty + 8 * j, q = q0 + tx;
+        tile[ty + 8 * j][tx] = (c < C && q < Q) ? __ldg(fmap + ((size_t)b * C + c) * Q + q) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int q = q0 + ty + 8 * j, c = c0 + tx;
+        if (q < Q && c < C) {
+            const float x = tile[tx][ty + 8 * j];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+            __nv_bfloat16 *o = out + ((size_t)b * Q + q) * Kp;
+            o[c] = hi;
+            o[C + c] = which == 0 ? lo : hi;
+            o[2 * C + c] = which == 0 ? hi : lo;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) corr_prep_kernel(const float *__restrict__ fmap, float *__restrict__ out, int C, int Q,
                                                         int split, int which) {
     __shared__ float tile[32][33];
@@ -82,6 +112,16 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13),
 // a/b K-major (0), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+// bf16 operands (a/b_format BF16 = 1), kind::f16: K = 16 per instruction, 64 elements per 128-byte swizzle row
+constexpr uint32_t kInstrDescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+__device__ __forceinline__ void umma_bf16_1cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 
 struct GemmShape {
     int B, Q, Kp;      // batch, queries (= targets), padded contraction length
@@ -89,6 +129,7 @@ struct GemmShape {
     float scale;       // 1 / sqrt(C)
 };
 
+template <bool kBf16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     corr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, GemmShape s) {
@@ -105,7 +146,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = s.B * s.m_tiles * s.n_tiles;
-    const int num_kb = s.Kp / kBK;
+    constexpr int kBKe = kBf16 ? 2 * kBK : kBK;          // elements per 128-byte K block (stage bytes are the same)
+    const int num_kb = s.Kp / kBKe;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -144,8 +186,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
-                    tma_load_3d(sA + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBK, m_blk * kBM, b);
-                    tma_load_3d(sB + stage * kBBytes, &tmap_b, &full_bar[stage], kb * kBK, n_blk * kBN, b);
+                    tma_load_3d(sA + stage * kABytes, &tmap_a, &full_bar[stage], kb * kBKe, m_blk * kBM, b);
+                    tma_load_3d(sB + stage * kBBytes, &tmap_b, &full_bar[stage], kb * kBKe, n_blk * kBN, b);
                     if (++stage == kStages) stage = 0, phase ^= 1;
                 }
             }
@@ -169,7 +211,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
                         // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) start address
-                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+                        if (kBf16) umma_bf16_1cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDescBf16, (kb | k) != 0 ? 1u : 0u);
+                        else umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -479,12 +522,13 @@ static int load_encode() {
 
 // 3-D fp32 tensor (inner, rows, batch) with a (box_inner x box_rows x 1) box, SWIZZLE_128B.
 static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint64_t batch, uint32_t box_inner,
-                    uint32_t box_rows) {
+                    uint32_t box_rows, bool bf16 = false) {
+    const uint64_t es = bf16 ? 2 : 4;
     cuuint64_t dims[3] = {inner, rows, batch};
-    cuuint64_t strides[2] = {inner * 4, inner * rows * 4};
+    cuuint64_t strides[2] = {inner * es, inner * rows * es};
     cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -528,8 +572,9 @@ size_t rpe_corr_pyramid_bytes(int B, int h, int w, int num_levels) {
 }
 
 size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision) {
-    const size_t Kp = precision == RPE_CORR_TF32X3 ? 3 * (size_t)C : (size_t)C;
-    return 2 * (((size_t)B * h * w * Kp * sizeof(float) + 1023) & ~(size_t)1023);
+    const size_t Kp = precision == RPE_CORR_TF32 ? (size_t)C : 3 * (size_t)C;
+    const size_t es = precision == RPE_CORR_BF16X3 ? 2 : sizeof(float);
+    return 2 * (((size_t)B * h * w * Kp * es + 1023) & ~(size_t)1023);
 }
 
 int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B, int C, int h, int w, int num_levels,
@@ -538,7 +583,9 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     if (!fmap1 || !fmap2 || !pyramid || !workspace) return RPE_ERR_INVALID_ARG;
     if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4) return RPE_ERR_INVALID_ARG;
     if (C % 32 != 0) return RPE_ERR_INVALID_ARG;
-    if (precision != RPE_CORR_TF32 && precision != RPE_CORR_TF32X3) return RPE_ERR_INVALID_ARG;
+    if (precision != RPE_CORR_TF32 && precision != RPE_CORR_TF32X3 && precision != RPE_CORR_BF16X3) return RPE_ERR_INVALID_ARG;
+    const bool bf16 = precision == RPE_CORR_BF16X3;
+    if (bf16 && (3 * C) % 64 != 0) return RPE_ERR_INVALID_ARG;
     if ((h >> (num_levels - 1)) < 1 || (w >> (num_levels - 1)) < 1) return RPE_ERR_INVALID_ARG;
     const int Q = h * w;
     if (Q % 4 != 0) return RPE_ERR_INVALID_ARG;     // TMA global strides must be multiples of 16 bytes
@@ -547,21 +594,28 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     int rc = load_encode();
     if (rc != RPE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int split = precision == RPE_CORR_TF32X3;
+    const int split = precision != RPE_CORR_TF32;
     const int Kp = split ? 3 * C : C;
     float *opA = reinterpret_cast<float *>(workspace);
     float *opB = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + rpe_corr_workspace_bytes(B, C, h, w, precision) / 2);
 
     dim3 pgrid((Q + 31) / 32, C / 32, B);
-    corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap1, opA, C, Q, split, 0);
-    RPE_LAUNCH_CHECK();
-    corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap2, opB, C, Q, split, 1);
-    RPE_LAUNCH_CHECK();
+    if (bf16) {
+        corr_prep_bf16_kernel<<<pgrid, 256, 0, st>>>(fmap1, reinterpret_cast<__nv_bfloat16 *>(opA), C, Q, 0);
+        RPE_LAUNCH_CHECK();
+        corr_prep_bf16_kernel<<<pgrid, 256, 0, st>>>(fmap2, reinterpret_cast<__nv_bfloat16 *>(opB), C, Q, 1);
+        RPE_LAUNCH_CHECK();
+    } else {
+        corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap1, opA, C, Q, split, 0);
+        RPE_LAUNCH_CHECK();
+        corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap2, opB, C, Q, split, 1);
+        RPE_LAUNCH_CHECK();
+    }
 
     PyrDims d = pyr_dims(B, h, w, num_levels);
     CUtensorMap ma, mb, mc;
-    if ((rc = make_map(&ma, opA, Kp, Q, B, kBK, kBM)) != RPE_OK) return rc;
-    if ((rc = make_map(&mb, opB, Kp, Q, B, kBK, kBN)) != RPE_OK) return rc;
+    if ((rc = make_map(&ma, opA, Kp, Q, B, bf16 ? 2 * kBK : kBK, kBM, bf16)) != RPE_OK) return rc;
+    if ((rc = make_map(&mb, opB, Kp, Q, B, bf16 ? 2 * kBK : kBK, kBN, bf16)) != RPE_OK) return rc;
     if ((rc = make_map(&mc, pyramid + d.off[0], Q, Q, B, kEpiCols, kBM)) != RPE_OK) return rc;
 
     GemmShape s;
@@ -571,13 +625,15 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     s.scale = 1.0f / sqrtf((float)C);
     static bool attr_set = false;
     if (!attr_set) {
-        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         attr_set = true;
     }
     int grid = sm_count();
     const int tiles = s.B * s.m_tiles * s.n_tiles;
     if (grid > tiles) grid = tiles;
-    corr_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
+    if (bf16) corr_gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
+    else corr_gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
     RPE_LAUNCH_CHECK();
 
     if (num_levels > 1) {

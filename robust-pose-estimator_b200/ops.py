@@ -9,10 +9,10 @@ from . import _lib
 from ._lib import RpeError, check
 
 __all__ = ["depth_proj", "proj", "warp8_mask", "downsample8_cat", "pose_solve", "PoseSolution", "CorrPyramid",
-           "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3"]
+           "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3", "CORR_BF16X3"]
 
 SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = _lib.SOLVER_LBFGS_REF, _lib.SOLVER_GN, _lib.SOLVER_EVAL_ONLY
-CORR_TF32, CORR_TF32X3 = _lib.CORR_TF32, _lib.CORR_TF32X3
+CORR_TF32, CORR_TF32X3, CORR_BF16X3 = _lib.CORR_TF32, _lib.CORR_TF32X3, _lib.CORR_BF16X3
 
 
 def _stream():
