@@ -54,39 +54,56 @@ class F2FEngine:
         st.depth, st.sflow, st.mask = depth, preds[-1], m
         return st
 
-    def _chunk_body(self, prev, limg, rimg, mask):
-        """C new frames given the state of the frame before them -> (pose (C,7), log (C,6), evals (C,), new state)."""
-        C = limg.shape[0]
+    def _chunk_body(self, prev, limg, rimg, mask, sequence_start=True):
+        """C new frames given the state of the frame before them -> (pose (C,7), log (C,6), evals (C,), new state).
+        ``prev is None``: ``limg[0]`` is the first frame of the (shard of the) sequence and rides along in the same batch --
+        its stereo pair is one more RAFT sample of this chunk instead of a batch-1 pass of its own; C = len(limg) - 1."""
+        first = prev is None
+        n_img = limg.shape[0]
+        C = n_img - 1 if first else n_img
         raft, model, est = self.model.flow, self.model, self.est
-        H, W = limg.shape[-2:]
         fL, fR, net0, inp = raft.encode(limg, rimg)
-        fL_prev = torch.cat((prev.fmap, fL[:-1]), 0)
-        net_prev = torch.cat((prev.net, net0[:-1]), 0)
-        inp_prev = torch.cat((prev.inp, inp[:-1]), 0)
-        # samples [0, C): temporal pairs (k-1 -> k); samples [C, 2C): stereo pairs of the new frames
-        preds, gru, ctx, _ = raft.refine(torch.cat((fL_prev, fL), 0).contiguous(), torch.cat((fL, fR), 0).contiguous(),
+        if first:
+            fL_prev, net_prev, inp_prev, fL_new = fL[:-1], net0[:-1], inp[:-1], fL[1:]
+        else:
+            fL_prev = torch.cat((prev.fmap, fL[:-1]), 0)
+            net_prev = torch.cat((prev.net, net0[:-1]), 0)
+            inp_prev = torch.cat((prev.inp, inp[:-1]), 0)
+            fL_new = fL
+        # samples [0, C): temporal pairs (k-1 -> k); samples [C, C + n_img): stereo pairs of the frames of this batch
+        preds, gru, ctx, _ = raft.refine(torch.cat((fL_prev, fL), 0).contiguous(), torch.cat((fL_new, fR), 0).contiguous(),
                                          torch.cat((net_prev, net0), 0), torch.cat((inp_prev, inp), 0))
         time_flow = preds[-1][:C].contiguous()
-        sflow = preds[-1][C:].contiguous()
-        K = est.intrinsics.float().expand(C, 3, 3).contiguous()
-        bl = (est.baseline * est.scale).float().reshape(1).expand(C).contiguous()
-        mask2 = mask.clone()
-        depth2, _, pcl2 = ops.depth_proj(sflow, bl, K, mask2)                       # mask2 &= stereo validity
-        depth_prev = torch.cat((prev.depth, depth2[:-1]), 0).contiguous()
-        pcl1 = ops.proj(depth_prev, K, rescale=self._scale)                  # (d / scale) * scale round trip
-        img_prev = torch.cat((prev.img, limg[:-1]), 0).contiguous()
-        sflow_prev = torch.cat((prev.sflow, sflow[:-1]), 0).contiguous()
-        mask1 = torch.cat((prev.mask, mask2[:-1]), 0).contiguous()
-        conf1, conf2, pcl2w, mask2w = model.get_weight_maps(pcl1, pcl2, img_prev, limg, mask2, time_flow, sflow_prev,
+        sflow_all = preds[-1][C:].contiguous()
+        K = est.intrinsics.float().expand(n_img, 3, 3).contiguous()
+        bl = (est.baseline * est.scale).float().reshape(1).expand(n_img).contiguous()
+        mask_all = mask.clone()
+        keep0 = mask_all[0:1].clone() if (first and sequence_start) else None
+        depth_all, _, pcl_all = ops.depth_proj(sflow_all, bl, K, mask_all)          # mask &= stereo validity
+        if keep0 is not None:
+            mask_all[0:1] = keep0              # the first frame of the SEQUENCE keeps its input mask (SURVEY A.6)
+        if first:
+            limg_new, mask2, depth2, pcl2, sflow = limg[1:], mask_all[1:].contiguous(), depth_all[1:], pcl_all[1:].contiguous(), sflow_all[1:].contiguous()
+            depth_prev, img_prev = depth_all[:-1].contiguous(), limg[:-1].contiguous()
+            sflow_prev, mask1 = sflow_all[:-1].contiguous(), mask_all[:-1].contiguous()
+        else:
+            limg_new, mask2, depth2, pcl2, sflow = limg, mask_all, depth_all, pcl_all, sflow_all
+            depth_prev = torch.cat((prev.depth, depth2[:-1]), 0).contiguous()
+            img_prev = torch.cat((prev.img, limg[:-1]), 0).contiguous()
+            sflow_prev = torch.cat((prev.sflow, sflow[:-1]), 0).contiguous()
+            mask1 = torch.cat((prev.mask, mask2[:-1]), 0).contiguous()
+        Kc = K[:C].contiguous()
+        pcl1 = ops.proj(depth_prev, Kc, rescale=self._scale)                 # (d / scale) * scale round trip
+        conf1, conf2, pcl2w, mask2w = model.get_weight_maps(pcl1, pcl2, img_prev, limg_new.contiguous(), mask2, time_flow, sflow_prev,
                                                             sflow, gru[:C], ctx[:C])
         lw = model.loss_weight[None, :].float().expand(C, 2).contiguous()
         head = model.pose_head.problem
         mode = ops.SOLVER_GN if head.solver == "gn" else ops.SOLVER_LBFGS_REF
         iters = head.gn_iters if head.solver == "gn" else head.lbgfs_iters
-        sol = ops.pose_solve(time_flow, pcl1, pcl2w, conf1, conf2, mask1, mask2w, K, lw, mode=mode, max_iter=iters)
+        sol = ops.pose_solve(time_flow, pcl1, pcl2w, conf1, conf2, mask1, mask2w, Kc, lw, mode=mode, max_iter=iters)
         st = _FrameState()
         st.img, st.fmap, st.net, st.inp = limg[-1:], fL[-1:].contiguous(), net0[-1:], inp[-1:]
-        st.depth, st.sflow, st.mask = depth2[-1:], sflow[-1:], mask2[-1:]
+        st.depth, st.sflow, st.mask = depth_all[-1:], sflow_all[-1:], mask_all[-1:]
         return sol.pose, sol.log, sol.n_evals, st
 
     # ------------------------------------------------------------------------------------------------
@@ -132,8 +149,13 @@ class F2FEngine:
         with torch.no_grad():
             start = 0
             if self.prev is None:
-                self.prev = self._first_frame(limgs[0:1], rimgs[0:1], masks[0:1], sequence_start)
-                start = 1
+                if T == 1:
+                    self.prev = self._first_frame(limgs[0:1], rimgs[0:1], masks[0:1], sequence_start)
+                    start = 1
+                else:                      # the first frame joins the first chunk (no batch-1 stereo pass of its own)
+                    start = min(1 + self.chunk, T)
+                    p, l, e, self.prev = self._chunk_body(None, limgs[0:start], rimgs[0:start], masks[0:start], sequence_start)
+                    poses.append(p), logs.append(l), evals.append(e)
             for a in range(start, T, self.chunk):
                 b = min(a + self.chunk, T)
                 args = (self.prev, limgs[a:b], rimgs[a:b], masks[a:b])

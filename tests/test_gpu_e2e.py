@@ -205,8 +205,9 @@ def test_graphed_streaming_tracker_matches_reference(golden_dir, precision):
     assert not est.check_failures()
 
 
-@pytest.mark.parametrize("chunk,graphs", [(1, False), (2, False), (2, True)])
-def test_batched_engine_matches_reference(golden_dir, chunk, graphs):
+@pytest.mark.parametrize("chunk,graphs,precision", [(1, False, "fp32"), (2, False, "fp32"), (2, True, "fp32"), (2, False, "bf16x3"),
+                                                    (3, True, "bf16x3")])
+def test_batched_engine_matches_reference(golden_dir, chunk, graphs, precision):
     """PoseEstimator.infer_sequence (chunked engine, feature reuse, optional CUDA graph, host composition through
     rpe_compose_trajectory_host) reproduces the reference trajectory."""
     _need_ckpt()
@@ -214,7 +215,7 @@ def test_batched_engine_matches_reference(golden_dir, chunk, graphs):
     from rpe_b200.core.pose.pose_estimator import PoseEstimator
     g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
     W, H = [int(v) for v in g["size"]]
-    est = PoseEstimator(dict(SLAM), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    est = PoseEstimator(dict(SLAM, precision=precision), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
     L = torch.from_numpy(g["imgs_l"].astype(np.float32)).cuda()
     R = torch.from_numpy(g["imgs_r"].astype(np.float32)).cuda()
     M = torch.from_numpy(np.stack([unpack(g["masks_in"][i], (1, H, W)) for i in range(3)])).cuda()
@@ -225,4 +226,5 @@ def test_batched_engine_matches_reference(golden_dir, chunk, graphs):
     for k in range(1, 3):
         rot, trans = _pose_err(traj[k].numpy(), g["traj"][k])
         assert rot < 1e-4 and trans < 1e-4, f"frame {k}: rot {rot:.2e} trans {trans:.2e}"
-    assert est.last_evals[:2].tolist() == [len(g["pair0_eval_pose"]), len(g["pair1_eval_pose"])]
+    if precision == "fp32":                 # identical evaluation count of the reference's L-BFGS run
+        assert est.last_evals[:2].tolist() == [len(g["pair0_eval_pose"]), len(g["pair1_eval_pose"])]
