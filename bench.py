@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=32, help="frames per engine chunk (measured on B200: 11 -> 318, 22 -> 330, 32 -> 334 pairs/s; fewer, larger launches)")
     ap.add_argument("--pairs", type=int, default=64)
     ap.add_argument("--graphs", action="store_true")
+    ap.add_argument("--pose-groups", type=int, default=0, help="concurrently solved pairs in rpe_pose_solve (0 = library default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency-frames", type=int, default=40, help="batch-1 latency leg (config 2): pairs timed one by one; 0 = off")
     args = ap.parse_args()
@@ -231,6 +232,8 @@ def main():
     if world > 1:
         dist.barrier()
     lib = _lib.lib()
+    if args.pose_groups > 0:
+        _lib.check(lib.rpe_pose_set_groups(args.pose_groups), "rpe_pose_set_groups")
 
     # rank r owns pairs [r*P, (r+1)*P) of one global (N*P + 1)-frame sequence: frames [r*P, (r+1)*P] (one halo frame)
     T = args.pairs + 1

@@ -236,10 +236,15 @@ typedef struct rpe_conv_desc {
     int aux_ld;
     const float *aux2;   /* update gate z, fp32 NHWC (N,OH,OW,aux2_ld)                                */
     int aux2_ld;
+    /* instance-norm partial sums fused into an fp32-only epilogue (mode 0, no pre / res / planes, cout % 16 == 0), or NULL:
+     * fp32 [N * tiles_per_image * 4][cout_pad][2] = (sum, sum of squares) of the outputs of 32 pixels each; slots of pixels
+     * outside the image hold zeros.  rpe_instnorm_stats_from_partials reduces them (extractor.py:23-56 nn.InstanceNorm2d). */
+    float *stat_partials;
 } rpe_conv_desc;
 
 int rpe_conv_plan_create(const rpe_conv_desc *desc, void **plan_out);   /* encodes the TMA descriptors once */
 int rpe_conv_plan_run(void *plan, void *stream);
+int rpe_conv_plan_tiles_per_image(void *plan); /* 128-pixel tiles per image (4 stat_partials slots each)   */
 double rpe_conv_plan_flops(void *plan);      /* tensor-core flops of one run (x3 for the split arithmetic) */
 int rpe_conv_plan_destroy(void *plan);
 
@@ -266,6 +271,10 @@ int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int
 size_t rpe_instnorm_workspace_bytes(int n, int C);
 int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float eps, void *workspace, size_t workspace_bytes,
                        void *stream);
+/* The same statistics from the partial sums a convolution wrote through rpe_conv_desc.stat_partials
+ * ([n * slots_per_image][ld][2] fp32, slots_per_image = 4 * rpe_conv_plan_tiles_per_image): no second pass over the tensor. */
+int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n, int slots_per_image, int C, int ld, int HW, float eps,
+                                     void *stream);
 int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
                        void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream);
 

@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
                 ("activation", C.c_int), ("out_scale", C.c_float), ("out_f32", C.c_void_p), ("f32_ld", C.c_int),
                 ("f32_offset", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("bf_ld", C.c_int),
                 ("bf_offset", C.c_int), ("mode", C.c_int), ("aux", C.c_void_p), ("aux_ld", C.c_int), ("aux2", C.c_void_p),
-                ("aux2_ld", C.c_int)]
+                ("aux2_ld", C.c_int), ("stat_partials", C.c_void_p)]
 
 
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -65,6 +65,8 @@ SIGNATURES = {
     "rpe_conv_plan_create": (_I, [C.POINTER(ConvDesc), C.POINTER(C.c_void_p)]),
     "rpe_conv_plan_run": (_I, [_P, _P]),
     "rpe_conv_plan_flops": (C.c_double, [_P]),
+    "rpe_conv_plan_tiles_per_image": (_I, [_P]),
+    "rpe_instnorm_stats_from_partials": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "rpe_conv_plan_destroy": (_I, [_P]),
     "rpe_corr_lookup_nhwc_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_nchw_to_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -8,6 +8,8 @@ Same arithmetic graph as ``extractor.encoder_forward`` (reference: /root/referen
   * cnet (eval-mode BatchNorm2d): the affine map is folded into the convolution weights and the relu / residual run in the
     convolution epilogue.
 All buffers and plans are created once per input shape."""
+import os
+
 import torch
 
 from .... import _lib
@@ -75,10 +77,21 @@ class EncoderTC:
         l = _lib.lib()
         ws = torch.empty(l.rpe_instnorm_workspace_bytes(n, 128), dtype=torch.uint8, device=device) if inst else None
         st["keep"].append(ws)
+        # instance-norm statistics from partial sums written by the convolution epilogue (conv.cu kind 6) instead of a second
+        # pass over the raw tensor; one buffer sized for the largest layer (stem / layer1).  RPE_FUSED_INSTNORM=0: two-pass path.
+        fused_stats = inst and os.environ.get("RPE_FUSED_INSTNORM", "1") != "0"
+        tiles_of = lambda oh, ow: ((ow + 7) // 8) * ((oh + 15) // 16)
+        part = torch.zeros((n * tiles_of(h, w) * 4 * 64 * 2,), dtype=torch.float32, device=device) if fused_stats else None
+        st["keep"].append(part)
+        pending = {}                                            # raw tensor -> the plan that fills `part` for it
 
         def stats_of(raw, c, hw):
             s = torch.empty((n, c, 2), dtype=torch.float32, device=device)
-            st["steps"].append(("stats", raw, s, hw, c, ws))
+            plan = pending.pop(raw.data_ptr(), None)
+            if plan is not None:
+                st["steps"].append(("stats_tiles", part, s, 4 * plan.tiles_per_image, hw, c))
+            else:
+                st["steps"].append(("stats", raw, s, hw, c, ws))
             return s
 
         def norm_act(a, sa, relu_a, b, sb, out, planes, hw, c):
@@ -87,8 +100,14 @@ class EncoderTC:
         def conv(name, bn, src, dims, k, cout, act, stride=1, out_f32=None, out_planes=None, res=None):
             (wts, bias) = self._wb(name, bn)
             cin = src.c if name != "conv1" else STEM_K
+            oh, ow = (dims[1] - 1) // stride + 1, (dims[2] - 1) // stride + 1
+            want_stats = (fused_stats and out_f32 is not None and out_planes is None and res is None and act == "none" and cout % 16 == 0
+                          and n * tiles_of(oh, ow) * 4 * cout * 2 <= part.numel())
             plan = ConvPlan(self.prefix + name, [(src, 0, min(cin, wts[0].shape[-1]), wts)], dims, k, k, cout, act, bias=bias, stride=stride,
-                            out_f32=out_f32, out_planes=out_planes, res=res)
+                            out_f32=out_f32, out_planes=out_planes, res=res, stat_partials=part if want_stats else None)
+            if want_stats:
+                assert plan.tiles_per_image == tiles_of(oh, ow), (plan.tiles_per_image, oh, ow)
+                pending[out_f32.data_ptr()] = plan
             st["steps"].append(("conv", plan))
             return plan
 
@@ -170,6 +189,10 @@ class EncoderTC:
             kind = step[0]
             if kind == "conv":
                 step[1].run("conv_tc_enc")
+            elif kind == "stats_tiles":
+                _, part, stats, slots, hw, c = step
+                with _timed("instnorm_stats", n):
+                    check(l.rpe_instnorm_stats_from_partials(_p(part), _p(stats), n, slots, c, c, hw, 1e-5, s), "rpe_instnorm_stats_from_partials")
             elif kind == "stats":
                 _, raw, stats, hw, c, ws = step
                 with _timed("instnorm_stats", n):

@@ -71,6 +71,7 @@ struct alignas(64) ConvParams {
     int aux_ld;
     const float *aux2;                                // mode 2: update gate z (fp32 NHWC)
     int aux2_ld;
+    float *stat_part;                                 // kind 6: per (pixel tile, lane quarter) sums of out and out^2, [slot][cout_pad][2]
     int dbg;                                          // RPE_CONV_DEBUG bits (probe only): 1 no loads, 2 no MMAs, 4 no epilogue memory traffic
 };
 
@@ -111,7 +112,8 @@ __device__ __forceinline__ float cv_tanh_fast(float v) { return 1.0f - __fdivide
 // warps share their issue slots with the MMA issuer and the instruction cache with both producers.
 //   0 generic mode 0 (every optional tensor tested at run time)      1 GRU z|r gates (mode 1)      2 GRU candidate + state (mode 2)
 //   3 tap projection (mode 3)      4 mode 0, split planes only (no addend / residual / fp32 copy)      5 mode 0, fp32 only
-constexpr int kKGeneric = 0, kKGates = 1, kKState = 2, kKProj = 3, kKPlanes = 4, kKF32 = 5;
+//   6 = 5 + instance-norm partial sums: every epilogue warp reduces its 32 pixels and writes sum / sum of squares per channel
+constexpr int kKGeneric = 0, kKGates = 1, kKState = 2, kKProj = 3, kKPlanes = 4, kKF32 = 5, kKF32Stats = 6;
 
 // fp32 x4 -> bf16 hi / lo planes (hi = bf16(v), lo = bf16(v - hi)), packed conversions
 template <bool kLo>
@@ -159,7 +161,7 @@ struct CvSide {
 
 template <int kK>
 __device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, int co, uint32_t pix) {
-    if (kK == kKPlanes || kK == kKF32 || kK == kKProj) return;
+    if (kK == kKPlanes || kK == kKF32 || kK == kKF32Stats || kK == kKProj) return;
     if (co + 3 >= P.cout) return;
     if (kK == kKGeneric) {
         if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
@@ -269,6 +271,43 @@ __device__ __forceinline__ void cv_epilogue_half(const ConvParams &P, const floa
         if ((inside_mask >> it) & 1u) cv_epilogue_group<kK>(P, acc[it], sd[it], b, sbias, co, pix[it]);
 }
 
+// fp32-only output + instance-norm partial sums (kind 6; cout is a multiple of 16, activation none / relu, no scale):
+// the lane sums its 4 pixels per channel, the 8 lanes that hold the same channel group are combined with shuffles, and lanes
+// 0..3 write (sum, sum of squares) of 4 channels each into this warp's slot -- no atomics, deterministic.
+__device__ __forceinline__ void cv_epilogue_half_stats(const ConvParams &P, const float *stage, const float *sbias, int co, const uint32_t *pix,
+                                                       uint32_t inside_mask, int lane, float *slot) {
+    const float4 b = *reinterpret_cast<const float4 *>(sbias + co);
+    float s[4] = {0.0f, 0.0f, 0.0f, 0.0f}, q[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        const float4 acc = *reinterpret_cast<const float4 *>(stage + r * 16 + (((lane & 3) ^ ((r >> 1) & 3)) << 2));
+        if (((inside_mask >> it) & 1u) && co < P.cout) {
+            float o[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
+            if (P.act == 1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.0f);
+            }
+            *reinterpret_cast<float4 *>(P.out_f32 + (pix[it] * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s[k] += o[k], q[k] = fmaf(o[k], o[k], q[k]);
+        }
+    }
+#pragma unroll
+    for (int m = 4; m < 32; m <<= 1) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            s[k] += __shfl_xor_sync(0xffffffffu, s[k], m);
+            q[k] += __shfl_xor_sync(0xffffffffu, q[k], m);
+        }
+    }
+    if (lane < 4 && co < P.cout) {
+        float4 *dst = reinterpret_cast<float4 *>(slot + 2 * co);
+        dst[0] = make_float4(s[0], q[0], s[1], q[1]);
+        dst[1] = make_float4(s[2], q[2], s[3], q[3]);
+    }
+}
+
 // mode 3 ("tap projection"): the activated outputs y[c] of a pixel are not stored; instead the epilogue evaluates the
 // per-pixel part of a FOLLOWING 3x3 convolution with few output channels, p[t] = sum_c y[c] * w2[c][t] (t = tap * 2 + o,
 // 18 values), in fp32 on the CUDA cores under the shadow of the next tile's MMAs.  rpe_tap_gather3x3 then adds the nine
@@ -291,7 +330,7 @@ __device__ __forceinline__ void cv_project_chunk(const ConvParams &P, const uint
 }
 
 struct CvTile {
-    int nb, img, omin0, omaj0;
+    int nb, img, omin0, omaj0, lin;                    // lin: pixel-tile index over the whole batch
     bool ghost;                                        // pair mode: padding tile of an odd tile count (computed, never stored)
 };
 // Work unit u of CTA `rank`: a single tile, or (pair mode) one of two adjacent pixel tiles that share the weight block nb.
@@ -306,6 +345,7 @@ __device__ __forceinline__ CvTile cv_decode(const ConvParams &P, int u, int rank
         t2 = 2 * t2 + rank;
         if (t2 >= P.N * per_img) t2 = P.N * per_img - 1, t.ghost = true;
     }
+    t.lin = t2;
     t.img = t2 / per_img;
     const int tr = t2 - t.img * per_img;
     const int tj = tr / P.tiles_min;
@@ -698,7 +738,13 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                         *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                     __syncwarp();
-                    cv_epilogue_half<kK>(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane, sd);
+                    if (kK == kKF32Stats) {
+                        // ghost tiles (pair padding) have inside_mask = 0 and alias the last real tile: they must not write a slot
+                        float *slot = P.stat_part + ((size_t)t.lin * 4 + wq) * (size_t)(2 * P.bn * P.n_blocks);
+                        if (!t.ghost) cv_epilogue_half_stats(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane, slot);
+                    } else {
+                        cv_epilogue_half<kK>(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane, sd);
+                    }
                     if (kK == kKGeneric || kK == kKGates || kK == kKState) {
 #pragma unroll
                         for (int it = 0; it < 4; ++it) sd[it] = sd_next[it];
@@ -747,6 +793,7 @@ static cudaError_t cv_dispatch(int kind, const ConvParams &p, int grid, bool pai
         case kKProj: return cv_launch<kKProj>(p, grid, pair, stream, set_attr);
         case kKPlanes: return cv_launch<kKPlanes>(p, grid, pair, stream, set_attr);
         case kKF32: return cv_launch<kKF32>(p, grid, pair, stream, set_attr);
+        case kKF32Stats: return cv_launch<kKF32Stats>(p, grid, pair, stream, set_attr);
         default: return cv_launch<kKGeneric>(p, grid, pair, stream, set_attr);
     }
 }
@@ -771,6 +818,7 @@ struct ConvPlan {
     int grid;
     bool pair;             // CTA-pair kernel (cta_group::2)
     int kind;              // kernel kind (kK*): which epilogue instantiation runs
+    int tiles_per_image;   // 128-pixel tiles per image (instance-norm partial sums: 4 slots per tile)
     double flops;          // real multiply-adds x 2 of one run (all products of the split arithmetic)
 };
 
@@ -965,7 +1013,17 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         if (d->out_hi && d->out_lo && !d->out_f32 && d->out_scale == 1.0f) pl->kind = kKPlanes;
         else if (d->out_f32 && !d->out_hi) pl->kind = kKF32;
     }
-    static bool attr[6] = {false, false, false, false, false, false};
+    p.stat_part = d->stat_partials;
+    if (d->stat_partials) {      // instance-norm partial sums ride on the fp32-only epilogue
+        if (p.mode != 0 || d->pre || d->res || d->activation > 1 || !d->out_f32 || d->out_hi || d->out_scale != 1.0f || (d->cout % 16) ||
+            !aligned16(d->stat_partials)) {
+            delete pl;
+            return RPE_ERR_INVALID_ARG;
+        }
+        pl->kind = kKF32Stats;
+    }
+    pl->tiles_per_image = p.tiles_min * p.tiles_maj;
+    static bool attr[7] = {false, false, false, false, false, false, false};
     if (!attr[pl->kind]) {
         cudaError_t e = cv_dispatch(pl->kind, p, 0, false, nullptr, true);
         if (e != cudaSuccess) {
@@ -985,6 +1043,11 @@ int rpe_conv_plan_run(void *plan, void *stream) {
     cv_dispatch(pl->kind, pl->p, pl->grid, pl->pair, (cudaStream_t)stream, false);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
+}
+
+int rpe_conv_plan_tiles_per_image(void *plan) {
+    if (!plan) return 0;
+    return reinterpret_cast<rpe::ConvPlan *>(plan)->tiles_per_image;
 }
 
 double rpe_conv_plan_flops(void *plan) {

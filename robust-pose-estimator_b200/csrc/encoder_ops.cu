@@ -116,6 +116,36 @@ __global__ void instnorm_final_kernel(const double *__restrict__ partial, float 
     }
 }
 
+// Statistics from the per-tile partial sums that the convolution epilogue writes (conv.cu kind 6): partial
+// [n * slots][ld][2] fp32 (sum, sum of squares over 32 pixels each).  One CTA per sample, fixed summation order, fp64.
+__global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float *__restrict__ partial, float *__restrict__ stats, int slots,
+                                                                     int C, int ld, int HW, float eps) {
+    __shared__ double sred[256][2];
+    const int n = blockIdx.x;
+    const int rows = 256 / C;                            // C <= 256 (checked by the host)
+    const int c = threadIdx.x % C, r = threadIdx.x / C;
+    double a = 0, b = 0;
+    if (r < rows) {
+        const float2 *base = reinterpret_cast<const float2 *>(partial) + (size_t)n * slots * ld + c;
+        for (int sl = r; sl < slots; sl += rows) {
+            const float2 v = __ldg(base + (size_t)sl * ld);
+            a += (double)v.x;
+            b += (double)v.y;
+        }
+    }
+    sred[threadIdx.x][0] = a, sred[threadIdx.x][1] = b;
+    __syncthreads();
+    if (threadIdx.x < C) {
+        a = 0, b = 0;
+        for (int rr = 0; rr < rows; ++rr) a += sred[rr * C + threadIdx.x][0], b += sred[rr * C + threadIdx.x][1];
+        const double mean = a / HW;
+        double var = b / HW - mean * mean;
+        if (var < 0) var = 0;
+        stats[((size_t)n * C + threadIdx.x) * 2] = (float)mean;
+        stats[((size_t)n * C + threadIdx.x) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 //   ya = stats_a ? (a - mean_a) * rstd_a : a;   if relu_a: ya = max(ya, 0)
 //   y  = b ? max(ya + (stats_b ? (b - mean_b) * rstd_b : b), 0) : ya
@@ -191,6 +221,15 @@ int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float
     rpe::instnorm_partial_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, (double *)workspace, HW, C, C);
     RPE_LAUNCH_CHECK();
     rpe::instnorm_final_kernel<<<n, 128, 0, (cudaStream_t)stream>>>((const double *)workspace, stats, HW, C, eps);
+    RPE_LAUNCH_CHECK();
+    return RPE_OK;
+}
+
+int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n, int slots_per_image, int C, int ld, int HW, float eps,
+                                     void *stream) {
+    if (!partials || !stats || n <= 0 || slots_per_image <= 0 || C <= 0 || C > 256 || ld < C || HW <= 0) return RPE_ERR_INVALID_ARG;
+    if (reinterpret_cast<uintptr_t>(partials) & 7u) return RPE_ERR_ALIGNMENT;
+    rpe::instnorm_from_partials_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(partials, stats, slots_per_image, C, ld, HW, eps);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

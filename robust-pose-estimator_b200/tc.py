@@ -44,11 +44,13 @@ class ConvPlan:
     """One convolution bound to its input / output buffers.  ``inputs``: [(Planes, c_offset, c_count, (w_hi, w_lo))]."""
 
     def __init__(self, name, inputs, dims, kh, kw, cout, act="none", bias=None, stride=1, out_f32=None, f32_off=0, out_planes=None,
-                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None):
+                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None, stat_partials=None):
         n, h, w = dims
         cout_pad = (cout + 15) // 16 * 16
         d = _lib.ConvDesc()
-        self._keep = [bias, pre, res, out_f32, out_planes, aux, aux2]
+        self._keep = [bias, pre, res, out_f32, out_planes, aux, aux2, stat_partials]
+        if stat_partials is not None:               # instance-norm partial sums (conv.cu kind 6), fp32 [N * tiles * 4][cout_pad][2]
+            d.stat_partials = stat_partials.data_ptr()
         d.mode = mode
         if aux is not None:
             d.aux, d.aux_ld = aux.data_ptr(), aux.shape[-1]
@@ -80,6 +82,7 @@ class ConvPlan:
         self._h = C.c_void_p()
         check(_lib.lib().rpe_conv_plan_create(C.byref(d), C.byref(self._h)), f"rpe_conv_plan_create({name})")
         self.flops = float(_lib.lib().rpe_conv_plan_flops(self._h))
+        self.tiles_per_image = int(_lib.lib().rpe_conv_plan_tiles_per_image(self._h))
 
     def run(self, stage="conv_tc"):
         with _timed(stage, self.flops):

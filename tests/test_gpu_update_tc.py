@@ -70,6 +70,44 @@ def test_conv_strided_and_partial_blocks(ops, cin, cout, k, stride, H, W):
     assert err < 3e-5 * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", [(64, 64, 3, 1, 44, 52), (64, 96, 3, 2, 50, 70), (64, 96, 1, 2, 50, 70), (176, 64, 1, 1, 40, 24)])
+def test_conv_instnorm_partial_sums(ops, cin, cout, k, stride, H, W):
+    """conv.cu kind 6: the fp32-only epilogue also writes per-(tile, lane quarter) sums / sums of squares; reduced by
+    rpe_instnorm_stats_from_partials they equal InstanceNorm2d's statistics of the convolution output (extractor.py:23-56).
+    Ragged sizes: pixel rows outside the image and the ghost tile of an odd tile count contribute nothing."""
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib, tc
+    from rpe_b200.ops import _p, _stream, check
+    n = 3
+    x = dev(det_uniform((n, cin, H, W), 131, -2.0, 2.0))
+    w = dev(det_uniform((cout, cin, k, k), 132, -1.0, 1.0)) * (1.0 / np.sqrt(cin * k * k))
+    b = dev(det_uniform((cout,), 133, -0.5, 0.5))
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=k // 2)
+    OH, OW = ref.shape[-2:]
+    planes = tc.Planes(n, H, W, cin, x.device)
+    tc.nchw_to_planes(x, planes)
+    wts = tc.pack_weight(w.float(), 0, cin, cout)
+    out = torch.zeros((n, OH, OW, cout), dtype=torch.float32, device=x.device)
+    tiles = ((OW + 7) // 8) * ((OH + 15) // 16)
+    part = torch.full((n * tiles * 4, cout, 2), float("nan"), dtype=torch.float32, device=x.device)
+    plan = tc.ConvPlan("stats", [(planes, 0, cin, wts)], (n, H, W), k, k, cout, "none", bias=b.float().contiguous(), stride=stride,
+                       out_f32=out, stat_partials=part)
+    assert plan.tiles_per_image == tiles
+    plan.run()
+    stats = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().rpe_instnorm_stats_from_partials(_p(part), _p(stats), n, 4 * tiles, cout, cout, OH * OW, 1e-5, _stream()),
+          "rpe_instnorm_stats_from_partials")
+    torch.cuda.synchronize()
+    assert (out.permute(0, 3, 1, 2).double() - ref).abs().max().item() < 3e-5 * max(1.0, ref.abs().max().item())
+    assert torch.isfinite(part).all()                                   # every slot of every real tile was written
+    o64 = out.double().reshape(n, OH * OW, cout)
+    mean, var = o64.mean(1), o64.var(1, unbiased=False)
+    err_m = (stats[..., 0].double() - mean).abs().max().item()
+    err_r = (stats[..., 1].double() * torch.sqrt(var + 1e-5) - 1.0).abs().max().item()
+    print(f"fused instnorm stats {cin}->{cout} {k}x{k}/{stride} {H}x{W}: mean err {err_m:.2e}, rstd rel err {err_r:.2e}")
+    assert err_m < 1e-6 and err_r < 1e-5
+
+
 def test_conv_addend_residual_and_single_pass(ops):
     n, cin, cout, H, W = 2, 128, 128, 32, 40
     x = dev(det_uniform((n, cin, H, W), 121, -2.0, 2.0))
