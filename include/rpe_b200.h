@@ -274,7 +274,7 @@ int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float
 /* The same statistics from the partial sums a convolution wrote through rpe_conv_desc.stat_partials
  * ([n * slots_per_image][ld][2] fp32, slots_per_image = 4 * rpe_conv_plan_tiles_per_image): no second pass over the tensor. */
 int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n, int slots_per_image, int C, int ld, int HW, float eps,
-                                     void *stream);
+                                     void *workspace, size_t workspace_bytes, void *stream);   /* rpe_instnorm_workspace_bytes(n, C) */
 int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
                        void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream);
 

@@ -66,7 +66,7 @@ SIGNATURES = {
     "rpe_conv_plan_run": (_I, [_P, _P]),
     "rpe_conv_plan_flops": (C.c_double, [_P]),
     "rpe_conv_plan_tiles_per_image": (_I, [_P]),
-    "rpe_instnorm_stats_from_partials": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "rpe_instnorm_stats_from_partials": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _Z, _P]),
     "rpe_conv_plan_destroy": (_I, [_P]),
     "rpe_corr_lookup_nhwc_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_nchw_to_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -89,7 +89,7 @@ class EncoderTC:
             s = torch.empty((n, c, 2), dtype=torch.float32, device=device)
             plan = pending.pop(raw.data_ptr(), None)
             if plan is not None:
-                st["steps"].append(("stats_tiles", part, s, 4 * plan.tiles_per_image, hw, c))
+                st["steps"].append(("stats_tiles", part, s, 4 * plan.tiles_per_image, hw, c, ws))
             else:
                 st["steps"].append(("stats", raw, s, hw, c, ws))
             return s
@@ -190,9 +190,10 @@ class EncoderTC:
             if kind == "conv":
                 step[1].run("conv_tc_enc")
             elif kind == "stats_tiles":
-                _, part, stats, slots, hw, c = step
+                _, part, stats, slots, hw, c, ws = step
                 with _timed("instnorm_stats", n):
-                    check(l.rpe_instnorm_stats_from_partials(_p(part), _p(stats), n, slots, c, c, hw, 1e-5, s), "rpe_instnorm_stats_from_partials")
+                    check(l.rpe_instnorm_stats_from_partials(_p(part), _p(stats), n, slots, c, c, hw, 1e-5, _p(ws), ws.numel(), s),
+                          "rpe_instnorm_stats_from_partials")
             elif kind == "stats":
                 _, raw, stats, hw, c, ws = step
                 with _timed("instnorm_stats", n):

@@ -22,16 +22,19 @@ __device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
 // a 1x1 convolution: k = ky*24 + kx*3 + c (21 real values per filter row, padded to 24 so that every row is three aligned
 // 16-byte stores per plane).  img NCHW fp32 (n,3,H,W) -> planes (n, H/2, W/2, ld).  One thread = one (pixel, ky).
 // ------------------------------------------------------------------------------------------------
+// idx_t: unsigned whenever the element count fits (32-bit divisions; with 64-bit ones the index arithmetic, not HBM, was the bound)
+template <typename idx_t>
 __global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ hi,
                                                         __nv_bfloat16 *__restrict__ lo, int H, int W, int OH, int OW, int ld,
                                                         long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
+    if ((long long)i >= total) return;
     const int ky = (int)(i % 7);
-    const long long pix = i / 7;
-    const int ox = (int)(pix % OW);
-    const int oy = (int)((pix / OW) % OH);
-    const int n = (int)(pix / ((long long)OW * OH));
+    const idx_t pix = i / 7;
+    const idx_t row = pix / (idx_t)OW;
+    const int ox = (int)(pix - row * (idx_t)OW);
+    const int n = (int)(row / (idx_t)OH);
+    const int oy = (int)(row - (idx_t)n * (idx_t)OH);
     const int y = 2 * oy + ky - 3;
     float v[24];
 #pragma unroll
@@ -117,17 +120,18 @@ __global__ void instnorm_final_kernel(const double *__restrict__ partial, float 
 }
 
 // Statistics from the per-tile partial sums that the convolution epilogue writes (conv.cu kind 6): partial
-// [n * slots][ld][2] fp32 (sum, sum of squares over 32 pixels each).  One CTA per sample, fixed summation order, fp64.
-__global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float *__restrict__ partial, float *__restrict__ stats, int slots,
-                                                                     int C, int ld, int HW, float eps) {
+// [n * slots][ld][2] fp32 (sum, sum of squares over 32 pixels each).  First level of a fixed-order fp64 reduction: block
+// (blk, n) sums the slots blk, blk + kStatBlocks, ... into the same [n][kStatBlocks][C][2] layout instnorm_final_kernel reads.
+__global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float *__restrict__ partial, double *__restrict__ blocks, int slots,
+                                                                     int C, int ld) {
     __shared__ double sred[256][2];
-    const int n = blockIdx.x;
+    const int n = blockIdx.y, blk = blockIdx.x;
     const int rows = 256 / C;                            // C <= 256 (checked by the host)
     const int c = threadIdx.x % C, r = threadIdx.x / C;
     double a = 0, b = 0;
     if (r < rows) {
         const float2 *base = reinterpret_cast<const float2 *>(partial) + (size_t)n * slots * ld + c;
-        for (int sl = r; sl < slots; sl += rows) {
+        for (int sl = blk + kStatBlocks * r; sl < slots; sl += kStatBlocks * rows) {
             const float2 v = __ldg(base + (size_t)sl * ld);
             a += (double)v.x;
             b += (double)v.y;
@@ -138,11 +142,8 @@ __global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float
     if (threadIdx.x < C) {
         a = 0, b = 0;
         for (int rr = 0; rr < rows; ++rr) a += sred[rr * C + threadIdx.x][0], b += sred[rr * C + threadIdx.x][1];
-        const double mean = a / HW;
-        double var = b / HW - mean * mean;
-        if (var < 0) var = 0;
-        stats[((size_t)n * C + threadIdx.x) * 2] = (float)mean;
-        stats[((size_t)n * C + threadIdx.x) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+        blocks[(((size_t)n * kStatBlocks + blk) * C + threadIdx.x) * 2] = a;
+        blocks[(((size_t)n * kStatBlocks + blk) * C + threadIdx.x) * 2 + 1] = b;
     }
 }
 
@@ -151,16 +152,17 @@ __global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float
 //   y  = b ? max(ya + (stats_b ? (b - mean_b) * rstd_b : b), 0) : ya
 // a, b fp32 NHWC with C channels (dense); y -> optional fp32 NHWC (dense) and / or split planes with channel pitch ld.
 // ------------------------------------------------------------------------------------------------
+template <typename idx_t>
 __global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__ a, const float *__restrict__ sa, int relu_a,
                                                        const float *__restrict__ b, const float *__restrict__ sb, float *__restrict__ out,
                                                        __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int ld, int HW, int C,
                                                        long long total4) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total4) return;
+    const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
+    if ((long long)i >= total4) return;
     const int c4n = C / 4;
-    const int c = (int)(i % c4n) * 4;
-    const long long pix = i / c4n;
-    const int n = (int)(pix / HW);
+    const idx_t pix = i / (idx_t)c4n;
+    const int c = (int)(i - pix * (idx_t)c4n) * 4;
+    const int n = (int)(pix / (idx_t)HW);
     const float4 av = __ldg(reinterpret_cast<const float4 *>(a + pix * C + c));
     float y[4] = {av.x, av.y, av.z, av.w};
     if (sa) {
@@ -201,8 +203,12 @@ int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int
     if ((reinterpret_cast<uintptr_t>(out_hi) & 15u) || (reinterpret_cast<uintptr_t>(out_lo) & 15u)) return RPE_ERR_ALIGNMENT;
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
     const long long total = (long long)n * OH * OW * 7;
-    rpe::im2col7s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16 *)out_hi,
-                                                                                           (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld, total);
+    if (total + 256 < (1ll << 32))
+        rpe::im2col7s2_kernel<unsigned><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            img, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld, total);
+    else
+        rpe::im2col7s2_kernel<unsigned long long><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            img, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld, total);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
@@ -226,10 +232,15 @@ int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float
 }
 
 int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n, int slots_per_image, int C, int ld, int HW, float eps,
-                                     void *stream) {
-    if (!partials || !stats || n <= 0 || slots_per_image <= 0 || C <= 0 || C > 256 || ld < C || HW <= 0) return RPE_ERR_INVALID_ARG;
-    if (reinterpret_cast<uintptr_t>(partials) & 7u) return RPE_ERR_ALIGNMENT;
-    rpe::instnorm_from_partials_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(partials, stats, slots_per_image, C, ld, HW, eps);
+                                     void *workspace, size_t workspace_bytes, void *stream) {
+    if (!partials || !stats || !workspace || n <= 0 || slots_per_image <= 0 || C <= 0 || C > 256 || ld < C || HW <= 0)
+        return RPE_ERR_INVALID_ARG;
+    if (workspace_bytes < rpe_instnorm_workspace_bytes(n, C)) return RPE_ERR_WORKSPACE;
+    if ((reinterpret_cast<uintptr_t>(partials) & 7u) || (reinterpret_cast<uintptr_t>(workspace) & 7u)) return RPE_ERR_ALIGNMENT;
+    dim3 grid(rpe::kStatBlocks, n);
+    rpe::instnorm_from_partials_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(partials, (double *)workspace, slots_per_image, C, ld);
+    RPE_LAUNCH_CHECK();
+    rpe::instnorm_final_kernel<<<n, 128, 0, (cudaStream_t)stream>>>((const double *)workspace, stats, HW, C, eps);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
@@ -241,8 +252,14 @@ int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const f
     if (out_hi && (ld < C || (ld % 4))) return RPE_ERR_INVALID_ARG;
     if (!rpe::aligned16(a) || (b && !rpe::aligned16(b)) || (out_f32 && !rpe::aligned16(out_f32))) return RPE_ERR_ALIGNMENT;
     const long long total4 = (long long)n * HW * (C / 4);
-    rpe::norm_act_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        a, stats_a, relu_a, b, stats_b, out_f32, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, ld, HW, C, total4);
+    // 32-bit element offsets when every tensor has fewer than 2^32 elements (pix * max(C, ld) below)
+    const long long elems = (long long)n * HW * (long long)(ld > C ? ld : C);
+    if (elems + 1024 < (1ll << 32))
+        rpe::norm_act_kernel<unsigned><<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            a, stats_a, relu_a, b, stats_b, out_f32, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, ld, HW, C, total4);
+    else
+        rpe::norm_act_kernel<unsigned long long><<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            a, stats_a, relu_a, b, stats_b, out_f32, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, ld, HW, C, total4);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

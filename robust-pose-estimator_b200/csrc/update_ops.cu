@@ -72,17 +72,19 @@ __global__ void __launch_bounds__(256) coords_add_kernel(float *__restrict__ coo
 // flow = coords1 - coords0 with coords0 = pixel grid; writes (i) the 7x7 im2col of the flow (98 of `col_ld` channels,
 // tap-major: ch = (ky*7+kx)*2 + c) as split planes and (ii) the flow itself into 2 channels at `x_off` of the GRU input
 // tensor.  One thread = one (pixel, tap): consecutive threads write consecutive 4-byte (fx, fy) pairs.
+// idx_t = unsigned for every realistic size (32-bit divisions; the 64-bit ones made this kernel instruction-bound).
+template <typename idx_t>
 __global__ void __launch_bounds__(256) flow_im2col_kernel(const float *__restrict__ coords1, __nv_bfloat16 *__restrict__ col_hi,
                                                           __nv_bfloat16 *__restrict__ col_lo, int col_ld, __nv_bfloat16 *__restrict__ x_hi,
                                                           __nv_bfloat16 *__restrict__ x_lo, int x_ld, int x_off, int h, int w,
                                                           long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
+    const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
+    if ((long long)i >= total) return;
     const int tap = (int)(i % 49);
-    const long long pix = i / 49;
+    const idx_t pix = i / 49;
     const int hw = h * w;
-    const int n = (int)(pix / hw);
-    const int p = (int)(pix - (long long)n * hw);
+    const int n = (int)(pix / (idx_t)hw);
+    const int p = (int)(pix - (idx_t)n * (idx_t)hw);
     const int y = p / w, x = p - y * w;
     const int ky = tap / 7, kx = tap - ky * 7;
     const int yy = y + ky - 3, xx = x + kx - 3;
@@ -201,9 +203,14 @@ int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi
         RPE_LAUNCH_CHECK();
     }
     const long long total = (long long)n * h * w * 49;
-    rpe::flow_im2col_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
-        total);
+    if (total + 256 < (1ll << 32))
+        rpe::flow_im2col_kernel<unsigned><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
+            total);
+    else
+        rpe::flow_im2col_kernel<unsigned long long><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
+            total);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

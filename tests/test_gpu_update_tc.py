@@ -95,8 +95,9 @@ def test_conv_instnorm_partial_sums(ops, cin, cout, k, stride, H, W):
     assert plan.tiles_per_image == tiles
     plan.run()
     stats = torch.empty((n, cout, 2), dtype=torch.float32, device=x.device)
-    check(_lib.lib().rpe_instnorm_stats_from_partials(_p(part), _p(stats), n, 4 * tiles, cout, cout, OH * OW, 1e-5, _stream()),
-          "rpe_instnorm_stats_from_partials")
+    ws = torch.empty(_lib.lib().rpe_instnorm_workspace_bytes(n, cout), dtype=torch.uint8, device=x.device)
+    check(_lib.lib().rpe_instnorm_stats_from_partials(_p(part), _p(stats), n, 4 * tiles, cout, cout, OH * OW, 1e-5, _p(ws), ws.numel(),
+                                                      _stream()), "rpe_instnorm_stats_from_partials")
     torch.cuda.synchronize()
     assert (out.permute(0, 3, 1, 2).double() - ref).abs().max().item() < 3e-5 * max(1.0, ref.abs().max().item())
     assert torch.isfinite(part).all()                                   # every slot of every real tile was written
