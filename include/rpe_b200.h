@@ -263,7 +263,8 @@ int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *
 
 /* Encoder companions (reference: /root/reference/core/RAFT/core/extractor.py:118-192, raft.py:82-83).
  * rpe_im2col7s2_split: 7x7 / stride 2 / pad 3 windows of the normalised image 2*(v/255)-1 as the K axis of a 1x1 convolution,
- *   k = ky*24 + kx*3 + c (168 of `ld` channels); img NCHW fp32 (n,3,H,W) -> bf16 split planes (n, H/2, W/2, ld).
+ *   k = ky*24 + kx*3 + c (168 of `ld` = 176 channels, the last 8 written as zeros); img NCHW fp32 (n,3,H,W) -> bf16 split
+ *   planes (n, H/2, W/2, 176).
  * rpe_instnorm_stats: InstanceNorm2d statistics (biased variance) of an NHWC fp32 tensor (n,HW,C): stats (n,C,2) = mean, rstd.
  * rpe_norm_act_split: y = [relu]((a - mean_a) * rstd_a), optionally y = relu(y + (b - mean_b) * rstd_b) (stats may be NULL =
  *   identity); writes fp32 NHWC and / or bf16 split planes with channel pitch ld. */

@@ -22,42 +22,57 @@ __device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
 // a 1x1 convolution: k = ky*24 + kx*3 + c (21 real values per filter row, padded to 24 so that every row is three aligned
 // 16-byte stores per plane).  img NCHW fp32 (n,3,H,W) -> planes (n, H/2, W/2, ld).  One thread = one (pixel, ky).
 // ------------------------------------------------------------------------------------------------
-// idx_t: unsigned whenever the element count fits (32-bit divisions; with 64-bit ones the index arithmetic, not HBM, was the bound)
-template <typename idx_t>
+// CTA = 32 consecutive output pixels of one output row: the 7 input rows x 3 channels x 69 columns they need are staged in
+// shared memory with coalesced loads (normalised on the way in, zeros outside the image), then thread (pixel, ky) assembles
+// its 24 values in a second shared tile and the CTA copies its contiguous 32 x 352-byte output range in 16-byte chunks.
+constexpr int kStemPx = 32, kStemCols = 2 * kStemPx + 5, kStemPitch = 72, kStemLd = 176;
 __global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ hi,
-                                                        __nv_bfloat16 *__restrict__ lo, int H, int W, int OH, int OW, int ld,
-                                                        long long total) {
-    const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
-    if ((long long)i >= total) return;
-    const int ky = (int)(i % 7);
-    const idx_t pix = i / 7;
-    const idx_t row = pix / (idx_t)OW;
-    const int ox = (int)(pix - row * (idx_t)OW);
-    const int n = (int)(row / (idx_t)OH);
-    const int oy = (int)(row - (idx_t)n * (idx_t)OH);
-    const int y = 2 * oy + ky - 3;
-    float v[24];
-#pragma unroll
-    for (int k = 0; k < 24; ++k) v[k] = 0.0f;
-    if (y >= 0 && y < H) {
-        const float *base = img + (size_t)n * 3 * H * W + (size_t)y * W;
+                                                        __nv_bfloat16 *__restrict__ lo, int H, int W, int OH, int OW, int ld) {
+    __shared__ float tile[7][3][kStemPitch];
+    const int ox0 = blockIdx.x * kStemPx, oy = blockIdx.y, n = blockIdx.z;
+    const int x0 = 2 * ox0 - 3, y0 = 2 * oy - 3;
+    const float *base = img + (size_t)n * 3 * H * W;
+    for (int i = threadIdx.x; i < 7 * 3 * kStemPitch; i += blockDim.x) {
+        const int col = i % kStemPitch, rc = i / kStemPitch;
+        const int c = rc % 3, r = rc / 3;
+        const int y = y0 + r, x = x0 + col;
+        float v = 0.0f;
+        if (col < kStemCols && y >= 0 && y < H && x >= 0 && x < W) v = 2.0f * (__ldg(base + ((size_t)c * H + y) * W + x) / 255.0f) - 1.0f;
+        tile[r][c][col] = v;
+    }
+    __syncthreads();
+    // assemble the (pixel, ky) rows in shared memory, then copy the CTA's contiguous output range with 16-byte chunks
+    __shared__ __align__(16) __nv_bfloat16 s_hi[kStemPx][kStemLd], s_lo[kStemPx][kStemLd];
+    const int npx = min(kStemPx, OW - ox0);
+    if (threadIdx.x < kStemPx * 7) {
+        const int ky = threadIdx.x % 7, p = threadIdx.x / 7;
+        float v[24];
 #pragma unroll
         for (int kx = 0; kx < 7; ++kx) {
-            const int x = 2 * ox + kx - 3;
-            if (x >= 0 && x < W) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) v[kx * 3 + c] = 2.0f * (__ldg(base + (size_t)c * H * W + x) / 255.0f) - 1.0f;
-            }
+            for (int c = 0; c < 3; ++c) v[kx * 3 + c] = tile[ky][c][2 * p + kx];
+        }
+        v[21] = v[22] = v[23] = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 6; ++g) {
+            uint2 h, l;
+            split4(v + g * 4, h, l);
+            *reinterpret_cast<uint2 *>(&s_hi[p][ky * 24 + g * 4]) = h;
+            *reinterpret_cast<uint2 *>(&s_lo[p][ky * 24 + g * 4]) = l;
+        }
+        if (ky == 0) {                                       // channels 168..175: padding of the K axis, kept at zero
+            *reinterpret_cast<uint4 *>(&s_hi[p][168]) = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4 *>(&s_lo[p][168]) = make_uint4(0, 0, 0, 0);
         }
     }
-    const size_t o = (size_t)pix * ld + ky * 24;
-#pragma unroll
-    for (int g = 0; g < 3; ++g) {
-        uint2 h0, l0, h1, l1;
-        split4(v + g * 8, h0, l0);
-        split4(v + g * 8 + 4, h1, l1);
-        *reinterpret_cast<uint4 *>(hi + o + g * 8) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-        *reinterpret_cast<uint4 *>(lo + o + g * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+    __syncthreads();
+    const size_t pix0 = ((size_t)n * OH + oy) * OW + ox0;
+    uint4 *ghi = reinterpret_cast<uint4 *>(hi + pix0 * kStemLd), *glo = reinterpret_cast<uint4 *>(lo + pix0 * kStemLd);
+    const uint4 *shi = reinterpret_cast<const uint4 *>(&s_hi[0][0]), *slo = reinterpret_cast<const uint4 *>(&s_lo[0][0]);
+    const int chunks = npx * (kStemLd * 2 / 16);
+    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+        ghi[i] = shi[i];
+        glo[i] = slo[i];
     }
 }
 
@@ -202,13 +217,9 @@ int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int
     if (!img || !out_hi || !out_lo || n <= 0 || H <= 0 || W <= 0 || ld < 168 || (ld % 8)) return RPE_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(out_hi) & 15u) || (reinterpret_cast<uintptr_t>(out_lo) & 15u)) return RPE_ERR_ALIGNMENT;
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
-    const long long total = (long long)n * OH * OW * 7;
-    if (total + 256 < (1ll << 32))
-        rpe::im2col7s2_kernel<unsigned><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            img, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld, total);
-    else
-        rpe::im2col7s2_kernel<unsigned long long><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            img, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld, total);
+    if (OH > 65535 || n > 65535 || ld != rpe::kStemLd) return RPE_ERR_INVALID_ARG;      // the staged copy assumes the 176-channel pitch
+    dim3 grid((OW + rpe::kStemPx - 1) / rpe::kStemPx, OH, n);
+    rpe::im2col7s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

@@ -109,6 +109,28 @@ def test_conv_instnorm_partial_sums(ops, cin, cout, k, stride, H, W):
     assert err_m < 1e-6 and err_r < 1e-5
 
 
+@pytest.mark.parametrize("H,W", [(50, 70), (64, 80), (33, 129)])
+def test_stem_im2col_vs_unfold(ops, H, W):
+    """rpe_im2col7s2_split: K axis k = ky*24 + kx*3 + c of the 7x7 / 2 windows of 2*(img/255)-1 (raft.py:82-83, extractor.py:124),
+    zero padding, odd sizes and output rows that do not fill a 32-pixel CTA."""
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.RAFT.core.encoder_tc import stem_planes
+    n = 2
+    img = dev(det_uniform((n, 3, H, W), 141, 0.0, 255.0))
+    pl = stem_planes(img)
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    x = 2.0 * (img / 255.0) - 1.0
+    cols = F.unfold(x, 7, padding=3, stride=2).reshape(n, 3, 7, 7, OH, OW)          # (n, c, ky, kx, oy, ox)
+    ref = torch.zeros((n, OH, OW, 7, 24), device=img.device)
+    ref[..., :21] = cols.permute(0, 4, 5, 2, 3, 1).reshape(n, OH, OW, 7, 21)
+    got = pl.float()[..., :168].reshape(n, OH, OW, 7, 24)
+    torch.cuda.synchronize()
+    err = (got - ref).abs().max().item()
+    print(f"stem im2col {H}x{W}: max abs err {err:.2e}")
+    assert err < 2e-5                                                               # 16-bit split of values in [-1, 1]
+    assert (pl.float()[..., 168:] == 0).all()
+
+
 def test_conv_addend_residual_and_single_pass(ops):
     n, cin, cout, H, W = 2, 128, 128, 32, 40
     x = dev(det_uniform((n, cin, H, W), 121, -2.0, 2.0))
