@@ -259,12 +259,12 @@ def main():
         return rel, log, evals, rec
 
     def e2e_step():
+        if world == 1:                                       # the public API call a user makes, fed from pinned host frames
+            est.last_pose = est.last_pose.__class__.Identity(1, device=dev)   # (uploads chunk k+1 while chunk k is solved)
+            return est.infer_sequence(hL, hR, hM, chunk=args.chunk, use_graphs=args.graphs)
         l = hL.to(dev, non_blocking=True).float()
         r = hR.to(dev, non_blocking=True).float()
         m = hM.to(dev, non_blocking=True)
-        if world == 1:                                                            # the public API call a user makes
-            est.last_pose = est.last_pose.__class__.Identity(1, device=dev)
-            return est.infer_sequence(l, r, m, chunk=args.chunk, use_graphs=args.graphs)
         rec = device_step(l, r, m)[3]
         if rank == 0:                                                             # host composition of the gathered poses
             return parallel.compose_trajectory(rec, [0, 0, 0, 0, 0, 0, 1.0], inv_scale)

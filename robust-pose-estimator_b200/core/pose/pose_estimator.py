@@ -139,7 +139,8 @@ class PoseEstimator(torch.nn.Module):
         return rel, self.last_frame, flow, weights
 
     def infer_sequence(self, limgs, rimgs, masks, chunk=8, use_graphs=False):
-        """Throughput path: a whole sequence (T,3,H,W) / (T,1,H,W) on the device -> absolute poses
+        """Throughput path: a whole sequence (T,3,H,W) / (T,1,H,W) on the device -- or in (pinned) host memory, then uploaded
+        chunk by chunk behind the compute of the previous chunk -- -> absolute poses
         (T,7) float32 on the HOST (mm; row 0 = initial pose, like the reference's trajectory list) and the
         per-pair failure flags (T-1,).  Pairs are solved in chunks by ``F2FEngine``; the trajectory is composed
         on the host with rpe_compose_trajectory_host (one device->host copy of (T-1) x 13 floats)."""
@@ -151,7 +152,10 @@ class PoseEstimator(torch.nn.Module):
         if getattr(self, "_engine_key", None) != key:
             self._engine, self._engine_key = F2FEngine(self, chunk, use_graphs), key
         self._engine.reset()
-        rel, log, evals = self._engine.infer_sequence(limgs, rimgs, masks)
+        if limgs.device.type == "cpu":
+            rel, log, evals = self._infer_from_host(limgs, rimgs, masks, chunk)
+        else:
+            rel, log, evals = self._engine.infer_sequence(limgs, rimgs, masks)
         n = rel.shape[0]
         host = torch.cat((rel, log), 1).cpu().contiguous()                      # the only device->host transfer
         rel_h, log_h = host[:, :7].contiguous(), host[:, 7:].contiguous()
@@ -166,6 +170,41 @@ class PoseEstimator(torch.nn.Module):
         self.last_pose = SE3(out[-1:].clone().to(self.last_pose.device))
         self.last_evals = evals
         return out, failed[:n].bool()
+
+    def _infer_from_host(self, limgs, rimgs, masks, chunk):
+        """``infer_sequence`` fed from HOST tensors (pinned uint8 / float frames, bool masks): the frames of engine chunk k+1
+        are uploaded on a copy stream while chunk k is being solved, so the host->device transfer is hidden behind compute."""
+        dev = self.baseline.device
+        T = limgs.shape[0]
+        bounds, a = [], 0
+        while a < T:
+            b = min(a + chunk + (1 if a == 0 else 0), T)              # the first chunk carries the first frame as well
+            bounds.append((a, b))
+            a = b
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        copy, main = self._copy_stream, torch.cuda.current_stream(dev)
+
+        def upload(a, b):
+            copy.wait_stream(main)                                    # buffers freed on the main stream may be reused here
+            with torch.cuda.stream(copy):
+                t = [x[a:b].to(dev, non_blocking=True) for x in (limgs, rimgs, masks)]
+                ev = torch.cuda.Event()
+                ev.record(copy)
+            return t, ev
+
+        nxt = upload(*bounds[0])
+        rel, log, evals = [], [], []
+        for i in range(len(bounds)):
+            (l, r, m), ev = nxt
+            if i + 1 < len(bounds):
+                nxt = upload(*bounds[i + 1])
+            main.wait_event(ev)
+            for x in (l, r, m):
+                x.record_stream(main)
+            p, lg, e = self._engine.infer_sequence(l.float(), r.float(), m.bool())
+            rel.append(p), log.append(lg), evals.append(e)
+        return torch.cat(rel), torch.cat(log), torch.cat(evals)
 
     def check_failures(self):
         """Synchronise and raise the reference's warning for every failed pair; returns their indices."""

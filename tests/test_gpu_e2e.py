@@ -205,6 +205,26 @@ def test_graphed_streaming_tracker_matches_reference(golden_dir, precision):
     assert not est.check_failures()
 
 
+def test_infer_sequence_from_pinned_host_frames(golden_dir):
+    """infer_sequence fed from pinned uint8 host frames (chunked uploads on a copy stream behind the compute) returns exactly
+    what the device-resident call returns."""
+    _need_ckpt()
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_estimator import PoseEstimator
+    from rpe_b200.lie import SE3
+    g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
+    W, H = [int(v) for v in g["size"]]
+    est = PoseEstimator(dict(SLAM, precision="bf16x3"), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    idx = [0, 1, 2, 1, 0, 2]
+    L8 = torch.from_numpy(np.clip(np.round(g["imgs_l"]), 0, 255).astype(np.uint8))[idx].contiguous().pin_memory()
+    R8 = torch.from_numpy(np.clip(np.round(g["imgs_r"]), 0, 255).astype(np.uint8))[idx].contiguous().pin_memory()
+    M = torch.from_numpy(np.stack([unpack(g["masks_in"][i], (1, H, W)) for i in range(3)]))[idx].contiguous().pin_memory()
+    ref, failed_ref = est.infer_sequence(L8.cuda().float(), R8.cuda().float(), M.cuda(), chunk=2)
+    est.last_pose = SE3.Identity(1, device="cuda")
+    got, failed = est.infer_sequence(L8, R8, M, chunk=2)
+    assert got.shape == (6, 7) and torch.equal(got, ref) and torch.equal(failed, failed_ref)
+
+
 @pytest.mark.parametrize("chunk,graphs,precision", [(1, False, "fp32"), (2, False, "fp32"), (2, True, "fp32"), (2, False, "bf16x3"),
                                                     (3, True, "bf16x3")])
 def test_batched_engine_matches_reference(golden_dir, chunk, graphs, precision):
