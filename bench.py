@@ -65,6 +65,17 @@ class ClockSampler:
         except OSError:
             self.p = None
 
+    def _rows(self):
+        try:
+            return [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        except OSError:
+            return []
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi was started earlier (its start-up can exceed a short timed region on a
+        multi-GPU box); only the rows written from here on are reported."""
+        self.begin = len(self._rows())
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
@@ -75,8 +86,14 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        rows = self._rows()
         os.unlink(self.f.name)
+        begin = getattr(self, "begin", 0)
+        if len(rows) > begin:
+            rows = rows[begin:]
+        elif rows:                                   # no sample landed inside a very short timed region: last warm-up samples
+            rows = rows[-3:]
+            out["window"] = "last warm-up steps (same load); the timed region was shorter than the sampling period"
         sm, reasons = [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -275,14 +292,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                  # nvidia-smi polls from the warm-up on; mark() opens the reported window
     for _ in range(args.warmup):
         device_step()
     # ---- timed region (device-resident inputs), CUDA events, per-stage timers on
-    sampler = ClockSampler(local_rank)
     timers = ops.enable_timers(True)
     sync_all()
     launches0 = lib.rpe_launch_count()
-    sampler.start()
+    sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     evals_total = 0

@@ -16,9 +16,14 @@
 // shifted along the major axis is the same slab advanced by 1024 bytes: one TMA load serves all kmaj taps of a filter column
 // (3x3: 3 loads instead of 9; 1x5 / 5x1: 1 load instead of 5).  Out-of-image coordinates are zero-filled by the TMA unit, which
 // IS the zero padding.  The hi and lo planes of a stage are loaded once and feed all three products.  Weights stream through
-// their own ring, one [bn][64] tile per tap.  Roles: warp 0 = activation TMA producer, warp 3 = weight TMA producer, warp 1 =
-// tcgen05.mma issuer (one elected thread), warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> bias / addend /
-// activation / residual -> fp32 and/or bf16 hi/lo NHWC stores) overlapped with the next tile through two TMEM accumulator stages.
+// their own ring, one [bn][64] tile per tap (or stay resident in shared memory when the whole set fits).  Roles: warp 0 =
+// activation TMA producer, warp 3 = weight TMA producer, warp 1 = tcgen05.mma issuer (the whole warp walks the loop nest so that
+// descriptors live in uniform registers; MMAs / commits are predicated on one elected lane), warp 2 = TMEM allocator, warps
+// 4-11 = epilogue (tcgen05.ld -> smem transposition -> bias / addend / activation / residual / GRU arithmetic -> coalesced fp32
+// and/or bf16 hi/lo NHWC stores) overlapped with the next tile through two TMEM accumulator stages.  CTA pairs (cta_group::2)
+// share every weight tile.  The kernel is instantiated once per epilogue KIND (kK* below) so that each instance carries only
+// the code of the tensors it touches: the epilogue warps share issue slots with the MMA issuer and the instruction cache with
+// both producers (profiles/README.md: the issuer, not the tensor pipe, was the bottleneck of the first version).
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>
 #include <math.h>
