@@ -1,8 +1,9 @@
 """RAFT optical flow with the reference's interface (/root/reference/core/RAFT/core/raft.py:24-137).
 
-The convolutional trunk runs through torch (cuDNN) from a functional weight table; the correlation
-volume, its lookup and the convex up-sampling are the hand-written sm_100a kernels.  Deviations that
-do not change the consumed result:
+With ``precision='bf16x3'`` the whole network runs on the hand-written sm_100a kernels: encoders and update
+operator on the tcgen05 implicit-GEMM convolution (encoder_tc.py, update_tc.py), correlation volume, lookup and
+convex up-sampling (csrc/corr.cu, upsample.cu).  The other precisions keep a torch (cuDNN) trunk built from the
+same functional weight table.  Deviations that do not change the consumed result:
   * only the final flow prediction is up-sampled unless ``all_predictions=True`` (the pose path
     reads ``flow_predictions[-1]`` only, pose_net.py:66-67);
   * ``precision``: "fp32" (cuDNN fp32, TF32 off, correlation TF32x3 split) |

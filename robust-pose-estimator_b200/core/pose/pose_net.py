@@ -1,6 +1,7 @@
 """PoseNet with the reference's interface (/root/reference/core/pose/pose_net.py:13-164) on the
-B200-native path: RAFT trunk through cuDNN, correlation / lookup / up-sampling, stereo-depth lifting,
-back-projection, flow warping, the 1/8 down-sampling and the SE(3) solve as sm_100a kernels.
+B200-native path: RAFT trunk (tcgen05 convolution kernels with precision 'bf16x3', a cuDNN trunk otherwise),
+correlation / lookup / up-sampling, stereo-depth lifting, back-projection, flow warping, the 1/8 down-sampling and
+the SE(3) solve as sm_100a kernels; only the two small confidence heads run through cuDNN.
 
 ``state_dict`` layout equals the reference's (loss_weight, flow.*, weight_head_2d.0.*, weight_head_3d.0.*),
 so trained/*.pth load unchanged.  CUDA only: CPU tensors raise (no fallback path)."""

@@ -3,9 +3,9 @@
 Frame pairs are independent in the f2f configuration, so a sequence is processed in
 chunks of C consecutive frames.  Per chunk (all on one CUDA stream, optionally replayed as one CUDA graph):
 
-  fnet over the 2C left/right images, cnet over the C left images          (cuDNN, once per image:
-                                                                             the reference recomputes the
-                                                                             features of frame k twice)
+  fnet over the 2C left/right images, cnet over the C left images          (once per image: the reference
+                                                                             recomputes the features of
+                                                                             frame k twice)
   one RAFT refinement over 2C samples: C temporal pairs (k-1 -> k) + C stereo pairs (left k -> right k)
       rpe_corr_build / 12 x rpe_corr_lookup / rpe_convex_upsample8          (sm_100a kernels)
   rpe_depth_proj, rpe_proj, rpe_warp8_mask, rpe_downsample8_cat, confidence heads, rpe_pose_solve (n = C)
@@ -13,7 +13,8 @@ chunks of C consecutive frames.  Per chunk (all on one CUDA stream, optionally r
 State carried between chunks = the last frame's features, context, normalised depth, stereo flow, mask and
 image, exactly what the reference keeps in ``Frame`` (pose_estimator.py:62-63,115-122).  The arithmetic per
 pair is the same as the per-frame tracker; only batch composition differs (eval-mode BatchNorm and
-InstanceNorm are per-sample, so this is exact up to cuDNN algorithm selection)."""
+InstanceNorm are per-sample, so results do not depend on how frames are grouped into chunks).  The first frame of a
+sequence rides in the first chunk (its stereo pair is one more RAFT sample)."""
 import torch
 
 from . import ops
