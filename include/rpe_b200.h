@@ -41,6 +41,17 @@ int rpe_device_sm_count(void);
 long long rpe_launch_count(void);               /* kernels launched by this library so far        */
 
 /* ------------------------------------------------------------------------------------------------
+ * Input pipeline ("next" row 8f-4 of SURVEY.md): the specularity mask of the reference's datasets.
+ * Replaces mask_specularities (/root/reference/dataset/stereo_dataset.py:12-16):
+ *   spec = img.sum(-1) < 3*255*spec_thr ; mask &= spec ; mask = cv2.erode(mask, ones((2r+1, 2r+1)))   (r = 5)
+ * img (n,3,H,W) u8 planar RGB on the device, mask_in (n,1,H,W) u8 or NULL (all valid), mask_out (n,1,H,W) u8 (0/1,
+ * must not alias mask_in).  max_sum = ceil(3*255*spec_thr) - 1 (= 734 for the reference's 0.96): the channel sum is an
+ * integer, so `sum < t` is `sum <= max_sum`.  Out-of-image pixels do not constrain the erosion (cv2's default border).
+ * ---------------------------------------------------------------------------------------------- */
+int rpe_mask_specularities(const uint8_t *img, const uint8_t *mask_in, uint8_t *mask_out, int n, int H, int W, int max_sum,
+                           int radius, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage 2 -- stereo depth lifting and pinhole back-projection (coalesced per-pixel kernels).
  * ---------------------------------------------------------------------------------------------- */
 

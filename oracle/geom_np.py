@@ -10,7 +10,11 @@ CPU fp32 run -- the parity oracle) of the per-pixel geometry and w
   ATen grid_sampler_2d (CPU, vectorised): unnormalize = (g + 1) * ((size-1)/2) for align_corners=True,
       bilinear corner weights from x - floor(x), zeros padding, nearest = round-half-even.
 
-Pinned by tests/golden/stages_small.npz and e2e_384x352.npz (outputs of the reference itself).
+  mask_specularities       /root/reference/dataset/stereo_dataset.py:12-16 (cv2.erode with a box kernel, default border:
+      out-of-image pixels do not constrain the minimum)
+
+Pinned by tests/golden/stages_small.npz and e2e_384x352.npz (outputs of the reference itself); mask_specularities by
+tests/golden/mask_specularities.npz (output of the reference function, oracle/make_golden.py --mask-spec).
 """
 import numpy as np
 
@@ -107,3 +111,18 @@ def downsample8(x):
     b = x[..., 4::8, :]
     r = (F32(0.5) * a + F32(0.5) * b).astype(F32)
     return (F32(0.5) * r[..., 3::8] + F32(0.5) * r[..., 4::8]).astype(F32)
+
+
+def mask_specularities(img_hwc, mask=None, spec_thr=0.96, radius=5):
+    """img (H,W,3) uint8, mask (H,W) bool or None -> (H,W) uint8 0/1.  stereo_dataset.py:12-16."""
+    img_hwc = np.asarray(img_hwc)
+    spec = img_hwc.sum(axis=-1) < (3 * 255 * spec_thr)
+    m = (np.asarray(mask, dtype=bool) & spec) if mask is not None else spec
+    H, W = m.shape
+    pad = np.ones((H + 2 * radius, W + 2 * radius), dtype=bool)           # cv2.erode default border: never the minimum
+    pad[radius:radius + H, radius:radius + W] = m
+    out = np.ones((H, W), dtype=bool)
+    for dy in range(2 * radius + 1):
+        for dx in range(2 * radius + 1):
+            out &= pad[dy:dy + H, dx:dx + W]
+    return out.astype(np.uint8)

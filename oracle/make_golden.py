@@ -361,6 +361,29 @@ def posehead_real_golden(rec, est, step=3):
     return g
 
 
+def mask_spec_golden():
+    """The reference's own mask_specularities (dataset/stereo_dataset.py:12-16, cv2.erode) on deterministic frames with
+    saturated blobs touching the borders; sizes that are not multiples of the CUDA tile."""
+    from dataset.stereo_dataset import mask_specularities                  # the unmodified reference function
+    from detrand import det_uniform                                      # oracle/ is on sys.path (HERE)
+    g = {}
+    for k, (H, W) in enumerate(((70, 90), (33, 129), (64, 64))):
+        img = det_uniform((H, W, 3), 900 + k, 0.0, 255.0).astype(np.uint8)
+        yy, xx = np.mgrid[0:H, 0:W]
+        for (cy, cx, rad) in ((0, 0, 9), (H - 1, W // 2, 7), (H // 2, W - 1, 12), (H // 3, W // 3, 5), (H // 2, W // 2, 1)):
+            img[(yy - cy) ** 2 + (xx - cx) ** 2 <= rad * rad] = 250 + (k % 3)        # saturated highlights (sum >= 750)
+        img[5, 7] = (245, 245, 244)                                                  # sum 734: just below the threshold
+        img[9, 11] = (245, 245, 245)                                                 # sum 735: just above
+        mask = det_uniform((H, W), 950 + k, 0.0, 1.0) > 0.002                        # a few isolated invalid pixels
+        mask[H - 4:, :6] = False
+        g[f"img{k}"] = img
+        g[f"mask{k}"] = np.packbits(mask)
+        g[f"shape{k}"] = np.array([H, W])
+        g[f"out{k}"] = np.packbits(mask_specularities(img, mask.copy()).astype(bool))
+        g[f"out_nomask{k}"] = np.packbits(mask_specularities(img).astype(bool))
+    return g
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also write the 640x512 dump to oracle/_ref")
@@ -368,8 +391,13 @@ def main():
     ap.add_argument("--variants", action="store_true",
                     help="BASELINE configs 4/5: infer_f2f_nw (no confidence heads) trajectory -> tests/golden, only3d 1280x1024 -> oracle/_ref")
     ap.add_argument("--skip-nw", action="store_true", help="with --variants: only the (git-ignored) only3d 1280x1024 golden")
+    ap.add_argument("--mask-spec", action="store_true", help="only tests/golden/mask_specularities.npz (reference dataset function)")
     args = ap.parse_args()
     assert os.path.isdir(REF), "reference not mounted"
+    if args.mask_spec:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mask_specularities.npz"), **mask_spec_golden())
+        print("tests/golden/mask_specularities.npz written")
+        return
     torch.manual_seed(0)
     torch.set_num_threads(8)
     gold = os.path.join(ROOT, "tests", "golden")

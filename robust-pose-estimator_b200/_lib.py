@@ -45,6 +45,7 @@ SIGNATURES = {
     "rpe_last_cuda_error": (_I, []),
     "rpe_device_sm_count": (_I, []),
     "rpe_launch_count": (C.c_longlong, []),
+    "rpe_mask_specularities": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_depth_proj": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "rpe_proj": (_I, [_P, _P, _P, _I, _F, _I, _I, _I, _P]),
     "rpe_warp8_mask": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

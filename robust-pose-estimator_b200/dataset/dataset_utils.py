@@ -20,6 +20,13 @@ class SyntheticStereoDataset(Dataset):
         return torch.from_numpy(limg), torch.from_numpy(rimg), torch.from_numpy(mask), n
 
 
+def mask_specularities(img, mask=None, spec_thr=0.96):
+    """The reference datasets' specularity mask (/root/reference/dataset/stereo_dataset.py:12-16) on frames that are already on
+    the device: img (n,3,H,W) uint8 RGB, mask (n,1,H,W) bool or None -> bool (n,1,H,W).  rpe_mask_specularities, bit-exact."""
+    from .. import ops
+    return ops.mask_specularities(img, mask, spec_thr=spec_thr, radius=5)
+
+
 class SequentialSubSampler(Sampler):
     def __init__(self, data_source, start=None, stop=None, step=1):
         n = len(data_source)

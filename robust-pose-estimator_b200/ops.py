@@ -9,7 +9,7 @@ from . import _lib
 from ._lib import RpeError, check
 
 __all__ = ["depth_proj", "proj", "warp8_mask", "downsample8_cat", "pose_solve", "PoseSolution", "CorrPyramid",
-           "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3", "CORR_BF16X3"]
+           "mask_specularities", "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3", "CORR_BF16X3"]
 
 SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = _lib.SOLVER_LBFGS_REF, _lib.SOLVER_GN, _lib.SOLVER_EVAL_ONLY
 CORR_TF32, CORR_TF32X3, CORR_BF16X3 = _lib.CORR_TF32, _lib.CORR_TF32X3, _lib.CORR_BF16X3
@@ -67,6 +67,24 @@ def _p(t):
 
 
 # ---------------------------------------------------------------------------------------------
+# input pipeline
+# ---------------------------------------------------------------------------------------------
+def mask_specularities(img, mask=None, spec_thr=0.96, radius=5):
+    """rpe_mask_specularities (reference dataset/stereo_dataset.py:12-16): img (n,3,H,W) uint8 RGB on the device, mask
+    (n,1,H,W) bool or None -> bool (n,1,H,W): valid & (R+G+B < 3*255*spec_thr), eroded with a (2r+1)^2 box."""
+    import math
+    n, _, H, W = img.shape
+    _chk(img, torch.uint8, "img", (n, 3, H, W))
+    if mask is not None:
+        _chk(mask, torch.bool, "mask", (n, 1, H, W))
+    out = torch.empty((n, 1, H, W), device=img.device, dtype=torch.bool)
+    max_sum = int(math.ceil(3 * 255 * spec_thr)) - 1            # integer sums: sum < t  <=>  sum <= ceil(t) - 1
+    with _timed("mask_specularities", n):
+        check(_lib.lib().rpe_mask_specularities(_p(img), _p(mask), _p(out), n, H, W, max_sum, int(radius), _stream()),
+              "rpe_mask_specularities")
+    return out
+
+
 # stage 2
 # ---------------------------------------------------------------------------------------------
 def depth_proj(stereo_flow, bf, K, mask=None, want_pcl=True):
