@@ -55,3 +55,31 @@ def test_ops_refuse_cpu_tensors():
     from rpe_b200._lib import RpeError
     with pytest.raises(RpeError):
         ops.proj(torch.ones(1, 1, 8, 8), torch.eye(3)[None])
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import, call or open anything under oracle/
+    (only tests/, __graft_entry__.smoke() and bench.py's CPU legs do)."""
+    pkg = os.path.join(ROOT, "robust-pose-estimator_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M) or "oracle/" in src.replace("oracle/_ref", ""):
+                    offenders.append(os.path.relpath(os.path.join(dirpath, f), ROOT))
+    assert not offenders, offenders
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback: if librpe_b200.so is missing, the first use raises instead of computing on the CPU."""
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib
+    from rpe_b200._lib import RpeError
+    loaded = _lib.lib()
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(RpeError, match="no CPU fallback"):
+        _lib.lib()
+    monkeypatch.undo()
+    assert _lib.lib() is loaded
