@@ -150,7 +150,7 @@ typedef struct rpe_pose_problem {
  *   trace    (n, trace_cap, 16) f64 or NULL: per evaluation [pose7 | grad6 | f | L2d | L3d]
  *   max_iter = lbgfs_iters (LBFGS) or GN iterations. */
 size_t rpe_pose_workspace_bytes(int n_pairs);
-/* Tuning: number of pairs solved concurrently by disjoint CTA groups (default 8, 1..256). */
+/* Tuning: upper bound on the pairs solved concurrently by disjoint CTA groups (default 16, 1..256). */
 int rpe_pose_set_groups(int groups);
 int rpe_pose_solve(const rpe_pose_problem *problem_host, int mode, int max_iter, int with_hessian,
                    double *out, float *pose_f32, float *log_f32, double *trace, int trace_cap,
@@ -185,6 +185,11 @@ size_t rpe_corr_level_offset(int B, int h, int w, int level);
 size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision);
 int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B, int C, int h, int w,
                    int num_levels, int precision, void *workspace, size_t workspace_bytes, void *stream);
+/* The RPE_CORR_BF16X3 build from feature maps that already are NHWC bf16 split planes (B,h,w,C), C % 64 == 0 -- what the
+ * feature encoder's last convolution writes: one tcgen05 kernel (CTA pairs, M = 256 queries x N = 16x16 target block) whose
+ * epilogue emits level 0 AND the 2x2 / 4x4 / 8x8 mean-pooled levels from the accumulators (corr.py:25-27 avg_pool2d order). */
+int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_hi, const void *f2_lo, float *pyramid, int B, int C,
+                          int h, int w, int num_levels, void *stream);
 
 /* Replaces CorrBlock.__call__ + bilinear_sampler (/root/reference/core/RAFT/core/corr.py:29-50,
  * core/RAFT/core/utils/utils.py:57-71): coords (B,2,h,w) f32 (channel 0 = x) ->

@@ -57,7 +57,19 @@ class Recorder:
         self.stage = {}
 
 
-def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True, loss_weight_mask=None):
+class FixedFrames:
+    """Minimal stand-in for SyntheticStereoSequence over given uint8 frames (config 1: the reference's own fixtures)."""
+
+    def __init__(self, L, R, M, K, bf):
+        self.L, self.R, self.M = L, R, M
+        self.calib = {"intrinsics": {"left": np.asarray(K, np.float64)}, "bf": float(bf)}
+        self.rel_xi = np.zeros((len(L) - 1, 6))
+
+    def __getitem__(self, i):
+        return self.L[i].astype(np.float32), self.R[i].astype(np.float32), self.M[i].copy(), i
+
+
+def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True, loss_weight_mask=None, seq=None, quiet=False):
     """Run the reference tracker over a synthetic sequence and record every stage of the last pair."""
     from core.pose.pose_estimator import PoseEstimator
     import core.pose.pose_net as pose_net_mod
@@ -65,8 +77,9 @@ def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True,
     from core.RAFT.core.corr import CorrBlock
     from lietorch import SE3
 
-    synth = _load_synth()
-    seq = synth.SyntheticStereoSequence(n_frames, size, seed=seed, holes=holes)
+    if seq is None:
+        synth = _load_synth()
+        seq = synth.SyntheticStereoSequence(n_frames, size, seed=seed, holes=holes)
     with open(os.path.join(REF, "configuration", "infer_f2f.yaml")) as f:
         config = yaml.load(f, Loader=yaml.SafeLoader)
     config["slam"]["conf_weighing"] = conf
@@ -141,6 +154,15 @@ def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True,
     frames = []
     poses = []
     rel = []
+    rel_pose = []                       # PoseNet.infer's own return value per pair (normalised units, before the guard)
+    orig_infer = model.infer
+
+    def infer_hook(*a, **k):
+        r = orig_infer(*a, **k)
+        rel_pose.append((r[0] if isinstance(r, tuple) else r).vec().detach().clone().numpy().reshape(7))
+        return r
+
+    model.infer = infer_hook
     try:
         with torch.no_grad():
             for i in range(n_frames):
@@ -153,7 +175,8 @@ def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True,
                 if i > 0:
                     xs = rec.stage["xs"]
                     rel.append(dict(evals=[(p.numpy().copy(), g.numpy().copy()) for p, g in rec.lbfgs]))
-                print(f"  frame {i}: pose {poses[-1]}  evals {len(rec.lbfgs)}")
+                if not quiet or i % 8 == 0:
+                    print(f"  frame {i}: pose {poses[-1]}  evals {len(rec.lbfgs)}", flush=True)
     finally:
         raft_mod.CorrBlock = CorrBlock
         torch.nn.utils.clip_grad_norm_ = orig_clip
@@ -163,6 +186,7 @@ def run_sequence(size, seed, n_frames, ckpt, rec_corr=False, holes=2, conf=True,
     out["imgs_r"] = np.stack([f[1] for f in frames])
     out["masks_in"] = np.stack([pack(f[2]) for f in frames])
     out["traj"] = np.stack(poses)
+    out["rel_pose"] = np.stack(rel_pose) if rel_pose else np.zeros((0, 7), np.float32)
     for k, r in enumerate(rel):
         out[f"pair{k}_eval_pose"] = np.stack([e[0] for e in r["evals"]])
         out[f"pair{k}_eval_grad"] = np.stack([e[1] for e in r["evals"]])
@@ -384,8 +408,60 @@ def mask_spec_golden():
     return g
 
 
+def tartan_frames(size=(640, 512), mm_per_unit=60.0, bf=2200.0):
+    """BASELINE config 1: stereo frames from the reference's OWN fixtures tests/test_data/tartan_air
+    (000000/000001 _left.png + _left_depth.npy; real rendered texture).  The left image and its depth go through the
+    reference's ResizeStereo (dataset/transforms.py:20-39) to 640x512; the fixtures hold no right view, so it is synthesised
+    from the depth: disparity = bf / depth_mm, forward-splatted into the right view with a z-buffer (nearest surface wins,
+    holes take the farther neighbour), then the left image is sampled at x + disparity.  Images are quantised to uint8."""
+    import cv2
+    from dataset.transforms import ResizeStereo
+    d = os.path.join(REF, "tests", "test_data", "tartan_air")
+    tr = ResizeStereo(size)
+    L, R = [], []
+    for name in ("000000", "000001"):
+        left = cv2.cvtColor(cv2.imread(os.path.join(d, name + "_left.png")), cv2.COLOR_BGR2RGB)
+        depth = np.load(os.path.join(d, name + "_left_depth.npy")).astype(np.float32)
+        lt, dt, _ = tr(torch.from_numpy(left).permute(2, 0, 1).float(), torch.from_numpy(depth)[None], None)
+        left_u8 = np.clip(np.rint(lt.numpy()), 0, 255).astype(np.uint8)                # (3,H,W)
+        disp = bf / (dt.numpy()[0].astype(np.float64) * mm_per_unit)                   # (H,W) pixels
+        H, W = disp.shape
+        cols = np.arange(W)[None, :].repeat(H, 0)
+        xr = np.rint(cols - disp).astype(np.int64)
+        ok = (xr >= 0) & (xr < W)
+        order = np.argsort(disp, axis=None, kind="stable")                             # ascending: larger disparity written last
+        order = order[ok.ravel()[order]]
+        disp_r = np.full(H * W, np.nan)
+        rows = (order // W)
+        disp_r[rows * W + xr.ravel()[order]] = disp.ravel()[order]
+        disp_r = disp_r.reshape(H, W)
+        fl, fr = disp_r.copy(), disp_r.copy()
+        for x in range(1, W):                                                          # nearest valid neighbour from each side
+            m = np.isnan(fl[:, x])
+            fl[m, x] = fl[m, x - 1]
+        for x in range(W - 2, -1, -1):
+            m = np.isnan(fr[:, x])
+            fr[m, x] = fr[m, x + 1]
+        disp_r = np.fmin(fl, fr)                                                       # the farther surface fills a hole
+        disp_r[np.isnan(disp_r)] = np.nanmedian(disp)
+        xs = np.clip(cols + disp_r, 0, W - 1)
+        x0 = np.clip(np.floor(xs).astype(np.int64), 0, W - 2)
+        a = (xs - x0)[None]
+        rr = np.arange(H)[:, None]
+        lf = left_u8.astype(np.float64)
+        right = (1 - a) * lf[:, rr, x0] + a * lf[:, rr, x0 + 1]
+        L.append(left_u8)
+        R.append(np.clip(np.rint(right), 0, 255).astype(np.uint8))
+    K = np.array([[320.0, 0, 320], [0, 320.0, 256], [0, 0, 1]])
+    return np.stack(L), np.stack(R), K, bf
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--config1", action="store_true",
+                    help="only tests/golden/e2e_cfg1_tartan.npz: the reference run on its own tests/test_data/tartan_air fixtures")
+    ap.add_argument("--bench64", action="store_true",
+                    help="only tests/golden/bench64_poses.npz: the reference's poses of the 64 frame pairs bench.py times")
     ap.add_argument("--full", action="store_true", help="also write the 640x512 dump to oracle/_ref")
     ap.add_argument("--skip-small", action="store_true")
     ap.add_argument("--variants", action="store_true",
@@ -410,6 +486,38 @@ def main():
             shutil.copyfile(os.path.join(REF, "trained", name), dst)
     ckpt = os.path.join(REF, "trained", "poseNet_2xf8up4b.pth")
 
+    if args.config1:
+        print("config 1: tartan_air fixtures, 640x512, frames [0, 1, 0] -> 2 pairs, conf heads on")
+        L, R, K, bf = tartan_frames()
+        order = [0, 1, 0]
+        M = np.ones((3, 1, 512, 640), bool)
+        seq = FixedFrames(L[order], R[order], M, K, bf)
+        out, rec, est = run_sequence((640, 512), seed=0, n_frames=3, ckpt=ckpt, seq=seq)
+        out.update({f"s_{k}": v for k, v in stage_dict(rec, est, full=False).items()})
+        out["imgs_l"], out["imgs_r"], out["order"] = L, R, np.array(order)             # the two distinct frames only
+        out["n_evals"] = np.array([out[f"pair{k}_eval_pose"].shape[0] for k in range(2)])
+        # full-resolution fp32 flows (identical-input mask gate) go to the git-ignored oracle/_ref; the committed file keeps the 1/4 grid
+        np.savez_compressed(os.path.join(refdir, "golden_cfg1_flows.npz"), time_flow=out.pop("s_time_flow"),
+                            stereo_flow2=out.pop("s_stereo_flow2"))
+        out["s_time_flow_ds4"] = rec.stage["time_flow"][0, :, ::4, ::4].numpy()
+        out["s_stereo_flow2_ds4"] = rec.stage["stereo_flow2"][0, :, ::4, ::4].numpy()
+        np.savez_compressed(os.path.join(gold, "e2e_cfg1_tartan.npz"), **out)
+        print("tests/golden/e2e_cfg1_tartan.npz written")
+        return
+    if args.bench64:
+        import hashlib
+        print("bench inputs: 65-frame bench_sequence() -> 64 reference poses")
+        synth = _load_synth()
+        seq = synth.bench_sequence()
+        out, rec, est = run_sequence((640, 512), seed=0, n_frames=synth.BENCH_FRAMES, ckpt=ckpt, seq=seq, quiet=True)
+        n = synth.BENCH_FRAMES - 1
+        keep = {"rel_pose": out["rel_pose"], "traj": out["traj"], "K": out["K"], "bf": out["bf"],
+                "n_evals": np.array([out[f"pair{k}_eval_pose"].shape[0] for k in range(n)]),
+                "frames_sha1": np.frombuffer(hashlib.sha1(out["imgs_l"].tobytes() + out["imgs_r"].tobytes()
+                                                          + out["masks_in"].tobytes()).digest(), dtype=np.uint8)}
+        np.savez_compressed(os.path.join(gold, "bench64_poses.npz"), **keep)
+        print("tests/golden/bench64_poses.npz written")
+        return
     if not args.skip_small:
         print("stage goldens (reference operators on exact inputs)")
         np.savez_compressed(os.path.join(gold, "stages_small.npz"), **small_stage_goldens())

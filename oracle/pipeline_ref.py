@@ -13,7 +13,13 @@ Follows, op for op, the reference's CPU fp32 execution:
   PoseEstimator (f2f)      core/pose/pose_estimator.py:50-125
   DPoseSE3Head.solve       core/pose/pose_head.py:60-79 -> oracle/pose_np.lbfgs_solve (fp64)
 Pinned by tests/test_oracle_pipeline.py against tests/golden/e2e_384x352.npz (outputs of the reference itself).
+
+``RefTracker(device="cuda", autocast=True, solver="torch")`` is the same restatement executed the way the stock reference
+runs on a GPU -- (c) the "reference on the GPU" arm of bench.py: cuDNN / cuBLAS / ATen kernels, fp16 autocast around fnet,
+cnet and the update block (raft.py:92,100,117: ``with autocast():`` has no ``enabled=`` switch), batch 1 per frame, and
+oracle/pose_torch.solve = torch.optim.LBFGS over the (pure-torch) lietorch stand-in with a host sync per iteration.
 """
+import contextlib
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -83,7 +89,7 @@ def corr_lookup(pyr, coords, r=4):
     B, _, h, w = coords.shape
     coords = coords.permute(0, 2, 3, 1)
     out = []
-    d = torch.linspace(-r, r, 2 * r + 1)
+    d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
     delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1).view(1, 2 * r + 1, 2 * r + 1, 2)
     for i, corr in enumerate(pyr):
         c = coords.reshape(B * h * w, 1, 1, 2) / 2 ** i + delta
@@ -103,24 +109,30 @@ def convex_upsample(flow, mask):
     return up.reshape(N, 2, 8 * H, 8 * W)
 
 
-def raft_forward(sd, image1, image2, iters=12):
-    """-> (flow_up (B,2,H,W), net, inp) like RAFT.forward(...)[0][-1], [1], [2]."""
+def raft_forward(sd, image1, image2, iters=12, autocast=False):
+    """-> (flow_up (B,2,H,W), net, inp) like RAFT.forward(...)[0][-1], [1], [2].  ``autocast``: the fp16 autocast regions of
+    the reference's CUDA run (raft.py:92,100,117); on CPU the reference's autocast is a no-op."""
+    amp = (lambda: torch.autocast("cuda", dtype=torch.float16)) if autocast else contextlib.nullcontext
+    dev = image1.device
     image1 = (2 * (image1 / 255.0) - 1.0).contiguous()
     image2 = (2 * (image2 / 255.0) - 1.0).contiguous()
     B = image1.shape[0]
-    fm = basic_encoder(torch.cat([image1, image2], 0), sd, "flow.fnet.", False)
+    with amp():
+        fm = basic_encoder(torch.cat([image1, image2], 0), sd, "flow.fnet.", False)
     pyr = corr_pyramid(fm[:B].float(), fm[B:].float())
-    cnet = basic_encoder(image1, sd, "flow.cnet.", True)
-    net, inp = torch.split(cnet, [128, 128], dim=1)
-    net, inp = torch.tanh(net), torch.relu(inp)
+    with amp():
+        cnet = basic_encoder(image1, sd, "flow.cnet.", True)
+        net, inp = torch.split(cnet, [128, 128], dim=1)
+        net, inp = torch.tanh(net), torch.relu(inp)
     h, w = image1.shape[-2] // 8, image1.shape[-1] // 8
-    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
     coords0 = torch.stack([xs, ys], 0).float()[None].repeat(B, 1, 1, 1)
     coords1 = coords0.clone()
     flow_up = None
     for _ in range(iters):
         corr = corr_lookup(pyr, coords1)
-        net, up_mask, delta = update_block(net, inp, corr, coords1 - coords0, sd)
+        with amp():
+            net, up_mask, delta = update_block(net, inp, corr, coords1 - coords0, sd)
         coords1 = coords1 + delta
         flow_up = convex_upsample(coords1 - coords0, up_mask)      # the reference up-samples every iteration
     return flow_up, net, inp
@@ -149,7 +161,7 @@ def tiny_unet(x, sd, pre, out_size):
 # ------------------------------------------------------------------------------------------------------
 def _remap(x, flow, mode="bilinear"):
     n, _, h, w = flow.shape
-    rows, cols = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    rows, cols = torch.meshgrid(torch.arange(h, device=flow.device), torch.arange(w, device=flow.device), indexing="ij")
     g = torch.empty_like(flow)
     g[:, 1] = 2 * (flow[:, 1] + rows) / (h - 1) - 1
     g[:, 0] = 2 * (flow[:, 0] + cols) / (w - 1) - 1
@@ -158,20 +170,25 @@ def _remap(x, flow, mode="bilinear"):
 
 def _proj(depth, K):
     n, _, H, W = depth.shape
-    xs = torch.linspace(0, W - 1, W).repeat(1, H, 1) + 0.5
-    ys = torch.linspace(0, H - 1, H).repeat(1, W, 1).transpose(1, 2) + 0.5
-    ic = torch.vstack([xs.flatten(), ys.flatten(), torch.ones(H * W)])
+    dev = depth.device
+    xs = torch.linspace(0, W - 1, W, device=dev).repeat(1, H, 1) + 0.5
+    ys = torch.linspace(0, H - 1, H, device=dev).repeat(1, W, 1).transpose(1, 2) + 0.5
+    ic = torch.vstack([xs.flatten(), ys.flatten(), torch.ones(H * W, device=dev)])
     return (depth.view(n, 1, -1) * (torch.linalg.inv(K) @ ic.view(1, 3, -1))).view(n, 3, H, W)
 
 
 class RefTracker:
     """CPU port of PoseEstimator(frame2frame=True) + PoseNet.infer; ``step`` mirrors ``forward``."""
 
-    def __init__(self, state_dict, K, bf, lbgfs_iters=20, conf_weighing=True, depth_clip=250.0):
-        self.sd = {k.replace("module.", ""): v.float() if v.is_floating_point() else v for k, v in state_dict.items()}
-        self.K = torch.as_tensor(K).float()[None]
-        self.scale = torch.tensor(1 / depth_clip)
-        self.baseline = torch.tensor(bf).unsqueeze(0).float()
+    def __init__(self, state_dict, K, bf, lbgfs_iters=20, conf_weighing=True, depth_clip=250.0, device="cpu", autocast=False,
+                 solver="numpy"):
+        self.device = torch.device(device)
+        self.autocast = bool(autocast)
+        self.solver = solver            # "numpy": oracle/pose_np (fp64 restatement); "torch": torch.optim.LBFGS like the reference
+        self.sd = {k.replace("module.", ""): (v.float() if v.is_floating_point() else v).to(self.device) for k, v in state_dict.items()}
+        self.K = torch.as_tensor(K).float()[None].to(self.device)
+        self.scale = torch.tensor(1 / depth_clip, device=self.device)
+        self.baseline = torch.tensor(bf).unsqueeze(0).float().to(self.device)
         self.iters = lbgfs_iters
         self.use_weights = conf_weighing
         self.last_pose = se3_np.identity().astype(np.float32)
@@ -180,7 +197,7 @@ class RefTracker:
         self.last = {}
 
     def _flow2depth(self, limg, rimg):
-        flow = raft_forward(self.sd, limg, rimg)[0]
+        flow = raft_forward(self.sd, limg, rimg, autocast=self.autocast)[0].float()
         depth = (self.baseline * self.scale)[:, None, None] / -flow[:, 0]
         valid = (depth > 0) & (depth <= 1.0)
         depth[~valid] = 1.0
@@ -190,10 +207,12 @@ class RefTracker:
         import time
         sd = self.sd
         t0 = time.perf_counter()
-        flow, net, inp = raft_forward(sd, torch.cat([last["img"], cur["img"]]), torch.cat([cur["img"], cur["rimg"]]))
+        flow, net, inp = raft_forward(sd, torch.cat([last["img"], cur["img"]]), torch.cat([cur["img"], cur["rimg"]]),
+                                      autocast=self.autocast)
         t1 = time.perf_counter()
+        flow = flow.float()
         time_flow, sflow2 = flow[0:1], flow[1:2]
-        gru, ctx = net[0:1], inp[0:1]
+        gru, ctx = net[0:1].float(), inp[0:1].float()
         depth2 = (self.baseline * self.scale)[:, None, None] / -sflow2[:, 0]
         valid = (depth2 > 0) & (depth2 <= 1.0)
         depth2[~valid] = 1.0
@@ -213,12 +232,19 @@ class RefTracker:
             conf1 = torch.sigmoid(tiny_unet(torch.cat((inp1, gru, ctx), 1), sd, "weight_head_2d.0.", (H, W)))
             conf2 = torch.sigmoid(tiny_unet(torch.cat((inp1, inp2, gru, ctx), 1), sd, "weight_head_3d.0.", (H, W)))
         else:
-            conf1 = torch.ones((1, 1, H, W))
-            conf2 = torch.ones((1, 1, H, W))
+            conf1 = torch.ones((1, 1, H, W), device=self.device)
+            conf2 = torch.ones((1, 1, H, W), device=self.device)
         t2 = time.perf_counter()
-        X, lg, n_evals = pose_np.lbfgs_solve(time_flow[0].numpy(), pcl1[0].numpy(), pcl2w[0].numpy(), conf1[0, 0].numpy(),
-                                             conf2[0, 0].numpy(), last["mask"][0, 0].numpy(), mask2w[0, 0].numpy(),
-                                             self.K[0].numpy(), sd["loss_weight"].numpy(), max_iter=self.iters)
+        if self.solver == "torch":
+            from . import pose_torch
+            Xt, lgt, n_evals = pose_torch.solve(time_flow, pcl1, pcl2w, conf1, conf2, last["mask"], mask2w, self.K,
+                                                sd["loss_weight"][None], lbgfs_iters=self.iters)
+            X, lg = Xt[0].float().cpu().numpy().astype(np.float64), lgt[0].float().cpu().numpy().astype(np.float64)
+        else:
+            X, lg, n_evals = pose_np.lbfgs_solve(time_flow[0].cpu().numpy(), pcl1[0].cpu().numpy(), pcl2w[0].cpu().numpy(),
+                                                 conf1[0, 0].cpu().numpy(), conf2[0, 0].cpu().numpy(), last["mask"][0, 0].cpu().numpy(),
+                                                 mask2w[0, 0].cpu().numpy(), self.K[0].cpu().numpy(), sd["loss_weight"].cpu().numpy(),
+                                                 max_iter=self.iters)
         t3 = time.perf_counter()
         self.timing["raft"] += t1 - t0
         self.timing["heads"] += t2 - t1
@@ -233,6 +259,7 @@ class RefTracker:
         """limg, rimg (1,3,H,W) float tensors 0..255, mask (1,1,H,W) bool -> absolute pose (7,) float32 in mm."""
         with torch.no_grad():
             last = self.frame
+            limg, rimg, mask = limg.to(self.device), rimg.to(self.device), mask.to(self.device)
             cur = {"img": limg.contiguous(), "rimg": rimg.contiguous(), "mask": mask.bool().clone()}
             if last is None:
                 depth, sflow, _ = self._flow2depth(limg, rimg)

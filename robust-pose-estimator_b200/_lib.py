@@ -60,6 +60,7 @@ SIGNATURES = {
     "rpe_corr_level_offset": (_Z, [_I, _I, _I, _I]),
     "rpe_corr_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "rpe_corr_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
+    "rpe_corr_build_planes": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_corr_lookup": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_convex_upsample8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "rpe_convex_upsample8_nhwc": (_I, [_P, _P, _I, _P, _I, _I, _I, _P]),

@@ -50,12 +50,17 @@ class RAFT(nn.Module):
         self._col = {}
 
     # ---- weight table ------------------------------------------------------------------------
-    def _apply(self, fn, *a, **k):
+    def invalidate(self):
+        """Drop everything derived from the parameters: weight table, packed / BN-folded tensor-core weights, im2col buffers."""
         self._W = self._tc = self._enc_tc = None
+        self._col = {}
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._W = self._tc = self._enc_tc = None
+        self.invalidate()
         return super().load_state_dict(*a, **k)
 
     def weights(self):

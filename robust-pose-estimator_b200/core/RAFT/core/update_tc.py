@@ -136,7 +136,8 @@ class UpdateTC:
                           "rpe_tap_gather3x3")
             else:
                 self._run(st, "fh2")
-        coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))
+        if iters > 0:                                   # iters = 0: the reference returns flow_init unchanged
+            coords1.add_(st["delta"][..., :2].permute(0, 3, 1, 2))
         flow_lo = coords1 - grid[None]
         flow_up = None
         if want_mask:

@@ -147,15 +147,7 @@ class PoseEstimator(torch.nn.Module):
         import ctypes as C
 
         from ... import _lib
-        from ...engine import F2FEngine
-        key = (chunk, use_graphs)
-        if getattr(self, "_engine_key", None) != key:
-            self._engine, self._engine_key = F2FEngine(self, chunk, use_graphs), key
-        self._engine.reset()
-        if limgs.device.type == "cpu":
-            rel, log, evals = self._infer_from_host(limgs, rimgs, masks, chunk)
-        else:
-            rel, log, evals = self._engine.infer_sequence(limgs, rimgs, masks)
+        rel, log, evals = self.infer_pairs(limgs, rimgs, masks, chunk, use_graphs)
         n = rel.shape[0]
         host = torch.cat((rel, log), 1).cpu().contiguous()                      # the only device->host transfer
         rel_h, log_h = host[:, :7].contiguous(), host[:, 7:].contiguous()
@@ -171,7 +163,21 @@ class PoseEstimator(torch.nn.Module):
         self.last_evals = evals
         return out, failed[:n].bool()
 
-    def _infer_from_host(self, limgs, rimgs, masks, chunk):
+    def infer_pairs(self, limgs, rimgs, masks, chunk=8, use_graphs=False, sequence_start=True):
+        """Relative poses of the consecutive frame pairs of a (shard of a) sequence, device-resident: (rel (T-1,7) float32 in
+        normalised units, log (T-1,6), evals (T-1,)).  Frames on the device or in (pinned) host memory.  ``sequence_start``:
+        frame 0 is the first frame of the whole sequence (it alone keeps its un-and-ed mask); False for the halo
+        frame of a later shard (``parallel.infer_sequence_sharded``)."""
+        from ...engine import F2FEngine
+        key = (chunk, use_graphs)
+        if getattr(self, "_engine_key", None) != key:
+            self._engine, self._engine_key = F2FEngine(self, chunk, use_graphs), key
+        self._engine.reset()
+        if limgs.device.type == "cpu":
+            return self._infer_from_host(limgs, rimgs, masks, chunk, sequence_start)
+        return self._engine.infer_sequence(limgs, rimgs, masks, sequence_start)
+
+    def _infer_from_host(self, limgs, rimgs, masks, chunk, sequence_start=True):
         """``infer_sequence`` fed from HOST tensors (pinned uint8 / float frames, bool masks): the frames of engine chunk k+1
         are uploaded on a copy stream while chunk k is being solved, so the host->device transfer is hidden behind compute."""
         dev = self.baseline.device
@@ -202,7 +208,7 @@ class PoseEstimator(torch.nn.Module):
             main.wait_event(ev)
             for x in (l, r, m):
                 x.record_stream(main)
-            p, lg, e = self._engine.infer_sequence(l.float(), r.float(), m.bool())
+            p, lg, e = self._engine.infer_sequence(l.float(), r.float(), m.bool(), sequence_start)
             rel.append(p), log.append(lg), evals.append(e)
         return torch.cat(rel), torch.cat(log), torch.cat(evals)
 

@@ -44,7 +44,7 @@ class PoseNet(nn.Module):
         sd = OrderedDict((k.replace("module.", ""), v) for k, v in state_dict.items())
         out = super().load_state_dict(sd, strict=strict, **kw)
         self._Wh = None
-        self.flow._W = self.flow._tc = None
+        self.flow.invalidate()          # nn.Module.load_state_dict does not call the child's override: drop every packed-weight cache
         return out
 
     def _head_weights(self):
@@ -61,11 +61,15 @@ class PoseNet(nn.Module):
 
     def flow2depth(self, imagel, imager, baseline, upsample=True):
         """-> depth (n,1,H,W), stereo flow (n,2,H,W), valid (n,1,H,W)   (pose_net.py:127-135)."""
+        flow = self.flow(imagel, imager, upsample=upsample)[0][-1]
+        n = flow.shape[0]
+        K = torch.eye(3, device=flow.device)[None].repeat(n, 1, 1)
+        bl = baseline.float().reshape(-1)
         if not upsample:
-            raise NotImplementedError("flow2depth(upsample=False) is not used on the f2f inference path")
-        flow = self.flow(imagel, imager, upsample=True)[0][-1]
-        K = torch.eye(3, device=flow.device)[None].repeat(flow.shape[0], 1, 1)
-        depth, valid, _ = ops.depth_proj(flow, baseline.float().reshape(-1).contiguous(), K, None, want_pcl=False)
+            bl = bl / 8                 # the 1/8-resolution branch (pose_net.py:130-131): disparities are 8x smaller
+        if bl.numel() == 1 and n > 1:
+            bl = bl.expand(n)           # the reference broadcasts a (1,) baseline over the batch
+        depth, valid, _ = ops.depth_proj(flow.contiguous(), bl.contiguous(), K, None, want_pcl=False)
         return depth, flow, valid
 
     def get_weight_maps(self, pcl1, pcl2, image1l, image2l, mask2, time_flow, stereo_flow1, stereo_flow2,

@@ -17,6 +17,16 @@ def save_trajectory(trajectory, path):
             f.write(f"{tr['timestamp']} {t[0]} {t[1]} {t[2]} {vec[3]} {vec[4]} {vec[5]} {vec[6]}\n")
 
 
+def save_trajectory_array(poses, timestamps, path):
+    """``save_trajectory`` for the (n,7) float32 array ``PoseEstimator.infer_sequence`` returns (mm): the same bytes as the
+    reference writer produces for the equivalent list of {'camera-pose', 'timestamp'} entries."""
+    poses = np.asarray(poses.cpu() if isinstance(poses, torch.Tensor) else poses, dtype=np.float32)
+    with open(os.path.join(path, "trajectory.freiburg"), "w") as f:
+        for ts, vec in zip(timestamps, poses):
+            t = (vec[0] / 1000.0, vec[1] / 1000.0, vec[2] / 1000.0)
+            f.write(f"{ts} {t[0]} {t[1]} {t[2]} {vec[3]} {vec[4]} {vec[5]} {vec[6]}\n")
+
+
 def read_freiburg(path, ret_stamps=False, no_stamp=False):
     with open(path, "r") as f:
         lines = f.read().replace(",", " ").replace("\t", " ").split("\n")

@@ -28,10 +28,19 @@
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace rpe {
+
+// RPE_CONV_DEBUG (probe switches: 1 no loads, 2 no MMAs, 4 no epilogue memory traffic) exists only in builds made with
+// -DRPE_CONV_DEBUG_BUILD; in the production library every test of it folds to a constant.
+#ifdef RPE_CONV_DEBUG_BUILD
+#define RPE_CV_DBG(P) ((P).dbg)
+#else
+#define RPE_CV_DBG(P) 0
+#endif
 
 constexpr int kCvBK = 64;                             // bf16 channels per K block (one 128-byte swizzle row)
 constexpr int kCvAcc = 2;                             // TMEM accumulator stages
@@ -78,6 +87,11 @@ struct alignas(64) ConvParams {
     int aux2_ld;
     float *stat_part;                                 // kind 6: per (pixel tile, lane quarter) sums of out and out^2, [slot][cout_pad][2]
     int dbg;                                          // RPE_CONV_DEBUG bits (probe only): 1 no loads, 2 no MMAs, 4 no epilogue memory traffic
+    // kind 7 (all-pairs correlation volume + pooled pyramid, corr.py:12-27,52-60): the "weights" are the second feature map of
+    // the SAME image, read through a 4-D map as 16x16 target blocks; level l of the pyramid is (N*OH*OW, corr_h >> l, corr_w >> l)
+    float *corr_lvl[4];
+    int corr_h, corr_w, corr_nbx, corr_levels;
+    int corr_vec;                                     // bit l: level l rows may be written with vector stores
 };
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -118,7 +132,9 @@ __device__ __forceinline__ float cv_tanh_fast(float v) { return 1.0f - __fdivide
 //   0 generic mode 0 (every optional tensor tested at run time)      1 GRU z|r gates (mode 1)      2 GRU candidate + state (mode 2)
 //   3 tap projection (mode 3)      4 mode 0, split planes only (no addend / residual / fp32 copy)      5 mode 0, fp32 only
 //   6 = 5 + instance-norm partial sums: every epilogue warp reduces its 32 pixels and writes sum / sum of squares per channel
-constexpr int kKGeneric = 0, kKGates = 1, kKState = 2, kKProj = 3, kKPlanes = 4, kKF32 = 5, kKF32Stats = 6;
+//   7 all-pairs correlation: N tile = one 16x16 block of TARGET positions of the same image; the epilogue scales by 1/sqrt(C), writes
+//     level 0 and derives the 2x2 / 4x4 / 8x8 mean-pooled levels of the pyramid from the accumulators in registers
+constexpr int kKGeneric = 0, kKGates = 1, kKState = 2, kKProj = 3, kKPlanes = 4, kKF32 = 5, kKF32Stats = 6, kKCorr = 7;
 
 // fp32 x4 -> bf16 hi / lo planes (hi = bf16(v), lo = bf16(v - hi)), packed conversions
 template <bool kLo>
@@ -166,7 +182,7 @@ struct CvSide {
 
 template <int kK>
 __device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, int co, uint32_t pix) {
-    if (kK == kKPlanes || kK == kKF32 || kK == kKF32Stats || kK == kKProj) return;
+    if (kK == kKPlanes || kK == kKF32 || kK == kKF32Stats || kK == kKProj || kK == kKCorr) return;
     if (co + 3 >= P.cout) return;
     if (kK == kKGeneric) {
         if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
@@ -334,6 +350,104 @@ __device__ __forceinline__ void cv_project_chunk(const ConvParams &P, const uint
     }
 }
 
+// kind 7: one chunk = 16 accumulator columns = target row `c` (0..15) of the unit's 16x16 target block (by, bx); after the
+// transposition a lane holds, for 4 query pixels (it), the 4 targets x = bx*16 + 4*(lane & 3) .. +3 of that row.  Level 0 is
+// written as it arrives; rows are paired in registers for the pooled levels with the reference's summation order
+// avg_pool2d: ((a00 + a01) + a10 + a11) * 0.25, each level from the ROUNDED previous one (corr.py:25-27).  The x-neighbour of a
+// level-2 value lives in lane ^ 1.  Every warp drains 8 consecutive rows, i.e. complete 8x8 groups.
+struct CvCorrState {
+    float4 prev[4];
+    float2 l1p[4];
+    float l2p[4];
+};
+__device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const float *stage, int c, int by, int bx, const uint32_t *pix,
+                                                 uint32_t inside_mask, int lane, CvCorrState &st) {
+    const int h0 = P.corr_h, w0 = P.corr_w;
+    const int gy = by * 16 + c, gx = bx * 16 + ((lane & 3) << 2);
+    float4 o[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        const float4 a = *reinterpret_cast<const float4 *>(stage + r * 16 + (((lane & 3) ^ ((r >> 1) & 3)) << 2));
+        o[it] = make_float4(a.x * P.scale, a.y * P.scale, a.z * P.scale, a.w * P.scale);
+    }
+    if (gy < h0 && gx < w0) {
+        const size_t n0 = (size_t)h0 * w0;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+            if ((inside_mask >> it) & 1u) {
+                float *p = P.corr_lvl[0] + (size_t)pix[it] * n0 + (size_t)gy * w0 + gx;
+                if (P.corr_vec & 1) {
+                    *reinterpret_cast<float4 *>(p) = o[it];
+                } else {
+                    p[0] = o[it].x;
+                    if (gx + 1 < w0) p[1] = o[it].y;
+                    if (gx + 2 < w0) p[2] = o[it].z;
+                    if (gx + 3 < w0) p[3] = o[it].w;
+                }
+            }
+    }
+    if (!(c & 1)) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) st.prev[it] = o[it];
+        return;
+    }
+    if (P.corr_levels < 2) return;
+    const int h1 = h0 >> 1, w1 = w0 >> 1, y1 = gy >> 1, x1 = gx >> 1;
+    float2 l1[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        l1[it].x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(st.prev[it].x, st.prev[it].y), o[it].x), o[it].y), 0.25f);
+        l1[it].y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(st.prev[it].z, st.prev[it].w), o[it].z), o[it].w), 0.25f);
+    }
+    if (y1 < h1 && x1 < w1) {
+        const size_t n1 = (size_t)h1 * w1;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+            if ((inside_mask >> it) & 1u) {
+                float *p = P.corr_lvl[1] + (size_t)pix[it] * n1 + (size_t)y1 * w1 + x1;
+                if (P.corr_vec & 2) {
+                    *reinterpret_cast<float2 *>(p) = l1[it];
+                } else {
+                    p[0] = l1[it].x;
+                    if (x1 + 1 < w1) p[1] = l1[it].y;
+                }
+            }
+    }
+    if ((c & 3) == 1) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) st.l1p[it] = l1[it];
+        return;
+    }
+    if (P.corr_levels < 3) return;
+    const int h2 = h0 >> 2, w2 = w0 >> 2, y2 = gy >> 2, x2 = gx >> 2;
+    float l2[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+        l2[it] = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(st.l1p[it].x, st.l1p[it].y), l1[it].x), l1[it].y), 0.25f);
+    if (y2 < h2 && x2 < w2) {
+        const size_t n2 = (size_t)h2 * w2;
+#pragma unroll
+        for (int it = 0; it < 4; ++it)
+            if ((inside_mask >> it) & 1u) P.corr_lvl[2][(size_t)pix[it] * n2 + (size_t)y2 * w2 + x2] = l2[it];
+    }
+    if ((c & 7) == 3) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) st.l2p[it] = l2[it];
+        return;
+    }
+    if (P.corr_levels < 4) return;
+    const int h3 = h0 >> 3, w3 = w0 >> 3, y3 = gy >> 3, x3 = gx >> 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const float top_r = __shfl_xor_sync(0xffffffffu, st.l2p[it], 1), bot_r = __shfl_xor_sync(0xffffffffu, l2[it], 1);
+        if (!(lane & 1) && y3 < h3 && x3 < w3 && ((inside_mask >> it) & 1u)) {
+            const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(st.l2p[it], top_r), l2[it]), bot_r), 0.25f);
+            P.corr_lvl[3][(size_t)pix[it] * ((size_t)h3 * w3) + (size_t)y3 * w3 + x3] = v;
+        }
+    }
+}
+
 struct CvTile {
     int nb, img, omin0, omaj0, lin;                    // lin: pixel-tile index over the whole batch
     bool ghost;                                        // pair mode: padding tile of an odd tile count (computed, never stored)
@@ -468,7 +582,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
     uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(tmem_empty + kCvAcc);
     float *sbias = reinterpret_cast<float *>(smem + kCvSmemData + 512);
     float *sstage = reinterpret_cast<float *>(smem + kCvSmemData + 512 + kCvMaxCout * 4);
-    for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
+    if (kK != kKCorr)      // (the correlation kind has no bias; its bn * n_blocks = number of target positions exceeds the staging area)
+        for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
     // mode 3: projection weights [cout <= 256][18] fp32 behind the bias (rest of the bias area + the unused staging tiles)
     float *w2s = sbias + 256;
     if (kK == kKProj)
@@ -523,7 +638,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
 
     if (warp == 0) {
         // ===================== activation producer =====================
-        if (!(P.dbg & 1) && elect_one()) {
+        if (!(RPE_CV_DBG(P) & 1) && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int u = u_first; u < num_units; u += u_step) {
@@ -550,7 +665,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         }
     } else if (warp == 3) {
         // ===================== weight producer =====================
-        if (!(P.dbg & 1) && elect_one()) {
+        if (!(RPE_CV_DBG(P) & 1) && elect_one()) {
             const int taps = P.kmin * P.kmaj;
             const int brow = kPair ? rank * (P.bn >> 1) : 0;          // this CTA's half of the weight rows
             if (P.resident_b) {
@@ -573,6 +688,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 uint32_t phase = 0;
                 for (int u = u_first; u < num_units; u += u_step) {
                     const int nb = u % P.n_blocks;
+                    const int img = kK == kKCorr ? cv_decode<kPair>(P, u, rank).img : 0;
+                    const int cby = kK == kKCorr ? nb / P.corr_nbx : 0, cbx = kK == kKCorr ? nb - cby * P.corr_nbx : 0;
                     for (int s = 0; s < P.n_src; ++s)
                         for (int cb = 0; cb < P.cblocks[s]; ++cb)
                             for (int tm = 0; tm < P.kmin; ++tm)
@@ -582,7 +699,15 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                         mbar_wait(&b_empty[stage], phase ^ 1);
                                         if (rank == 0) mbar_expect_tx(&b_full[stage], P.b_plane_bytes * load_mult);
                                         uint8_t *dst = sB + (size_t)stage * P.b_plane_bytes;
-                                        if (kPair)
+                                        if (kK == kKCorr) {
+                                            // 16x16 block of target positions of image `img` (this CTA's 8 rows of it in pair mode): the
+                                            // box lands as [row][x][64 ch] = accumulator column row * 16 + x; outside the map reads zero
+                                            if (kPair)
+                                                tma_load_4d_pair(dst, &P.wmap[s][p], mapa_shared(smem_u32(&b_full[stage]), 0), cb * kCvBK, cbx * 16,
+                                                                 cby * 16 + rank * 8, img);
+                                            else
+                                                tma_load_4d(dst, &P.wmap[s][p], &b_full[stage], cb * kCvBK, cbx * 16, cby * 16, img);
+                                        } else if (kPair)
                                             tma_load_3d_pair(dst, &P.wmap[s][p], mapa_shared(smem_u32(&b_full[stage]), 0), cb * kCvBK,
                                                              nb * P.bn + brow, tap);
                                         else
@@ -602,7 +727,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128 (256 across a CTA pair)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
                                ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
-        const bool no_load = (P.dbg & 1) != 0, no_mma = (P.dbg & 2) != 0;
+        const bool no_load = (RPE_CV_DBG(P) & 1) != 0, no_mma = (RPE_CV_DBG(P) & 2) != 0;
         const bool planes2 = P.n_planes == 2, reuse = P.reuse != 0, resident = P.resident_b != 0;
         // shared-memory descriptors = constant upper word | (address >> 4); ring positions advance the low word only
         const uint32_t a_base16 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16), b_base16 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -711,13 +836,13 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                     uint32_t v[16];
                     cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
                     if (c + 1 == c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);
-                    if (!(P.dbg & 4)) cv_project_chunk(P, v, sbias, w2s, t.nb * P.bn + c * 16, proj);
+                    if (!(RPE_CV_DBG(P) & 4)) cv_project_chunk(P, v, sbias, w2s, t.nb * P.bn + c * 16, proj);
                 }
                 const int m = wq * 32 + lane;
                 const int gi = m >> 3, mi = m & 7;
                 const int y = P.orient == 0 ? t.omaj0 + gi : t.omin0 + mi;
                 const int x = P.orient == 0 ? t.omin0 + mi : t.omaj0 + gi;
-                if (y < P.OH && x < P.OW && !t.ghost && !(P.dbg & 4)) {
+                if (y < P.OH && x < P.OW && !t.ghost && !(RPE_CV_DBG(P) & 4)) {
                     float2 *dst = reinterpret_cast<float2 *>(P.out_f32 + (((size_t)t.img * P.OH + y) * P.OW + x) * P.f32_ld + P.f32_off +
                                                              chalf * kCvProj);
 #pragma unroll
@@ -725,9 +850,11 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 }
             } else {
                 const int co_lane = t.nb * P.bn + ((lane & 3) << 2);
+                const int cby = kK == kKCorr ? t.nb / P.corr_nbx : 0, cbx = kK == kKCorr ? t.nb - cby * P.corr_nbx : 0;
+                CvCorrState cst;
                 // side inputs of the first chunk are requested before the accumulator is even complete
                 CvSide sd[4], sd_next[4];
-                if (c_begin < c_end && !(P.dbg & 4)) cv_side_load4<kK>(P, sd, co_lane + c_begin * 16, pix, inside_mask);
+                if (c_begin < c_end && !(RPE_CV_DBG(P) & 4)) cv_side_load4<kK>(P, sd, co_lane + c_begin * 16, pix, inside_mask);
                 mbar_wait(&tmem_full[acc], acc_phase);
                 tcgen05_fence_after();
                 if (c_begin >= c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);   // nothing to drain (bn = 16)
@@ -735,7 +862,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                     uint32_t v[16];
                     cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
                     if (c + 1 == c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);
-                    if (P.dbg & 4) continue;
+                    if (RPE_CV_DBG(P) & 4) continue;
                     if (c + 1 < c_end) cv_side_load4<kK>(P, sd_next, co_lane + (c + 1) * 16, pix, inside_mask);
                     __syncwarp();                                  // previous chunk's reads of the staging tile are done
 #pragma unroll
@@ -743,7 +870,9 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                         *reinterpret_cast<uint4 *>(stage + lane * 16 + ((k ^ ((lane >> 1) & 3)) << 2)) =
                             make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
                     __syncwarp();
-                    if (kK == kKF32Stats) {
+                    if (kK == kKCorr) {
+                        cv_epilogue_corr(P, stage, c, cby, cbx, pix, inside_mask, lane, cst);
+                    } else if (kK == kKF32Stats) {
                         // ghost tiles (pair padding) have inside_mask = 0 and alias the last real tile: they must not write a slot
                         float *slot = P.stat_part + ((size_t)t.lin * 4 + wq) * (size_t)(2 * P.bn * P.n_blocks);
                         if (!t.ghost) cv_epilogue_half_stats(P, stage, sbias, co_lane + c * 16, pix, inside_mask, lane, slot);
@@ -799,6 +928,7 @@ static cudaError_t cv_dispatch(int kind, const ConvParams &p, int grid, bool pai
         case kKPlanes: return cv_launch<kKPlanes>(p, grid, pair, stream, set_attr);
         case kKF32: return cv_launch<kKF32>(p, grid, pair, stream, set_attr);
         case kKF32Stats: return cv_launch<kKF32Stats>(p, grid, pair, stream, set_attr);
+        case kKCorr: return cv_launch<kKCorr>(p, grid, pair, stream, set_attr);
         default: return cv_launch<kKGeneric>(p, grid, pair, stream, set_attr);
     }
 }
@@ -816,6 +946,37 @@ static int cv_load_encode() {
     if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return cuda_fail(e == cudaSuccess ? cudaErrorUnknown : e);
     g_cv_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     return RPE_OK;
+}
+
+// Probe / A-B switches from the environment, read once per process (not on every plan creation).
+struct CvEnv {
+    bool no_pair, generic;
+    int a_stages, dbg;
+    CvEnv() {
+        const char *e = getenv("RPE_CONV_PAIR");
+        no_pair = e && e[0] == '0';
+        generic = getenv("RPE_CONV_GENERIC") != nullptr;
+        e = getenv("RPE_CONV_ASTAGES");
+        a_stages = e ? atoi(e) : 0;
+        e = getenv("RPE_CONV_DEBUG");
+        dbg = e ? atoi(e) : 0;
+    }
+};
+static const CvEnv &cv_env() {
+    static const CvEnv env;
+    return env;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device and per kernel instantiation.
+static cudaError_t cv_ensure_attr(int kind, const ConvParams &p) {
+    static bool done[16][8] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 16 && done[dev][kind]) return cudaSuccess;
+    e = cv_dispatch(kind, p, 0, false, nullptr, true);
+    if (e == cudaSuccess && dev >= 0 && dev < 16) done[dev][kind] = true;
+    return e;
 }
 
 struct ConvPlan {
@@ -873,9 +1034,8 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.n_src = d->n_sources;
     p.n_planes = d->src[0].act_lo ? 2 : 1;
     // CTA pairs (cta_group::2): each CTA of a 2-cluster loads half of every weight tile.  RPE_CONV_PAIR=0 disables.
-    const char *pair_env = getenv("RPE_CONV_PAIR");
     const int px_tiles = d->N * (((orient == 0 ? OW : OH) + 7) / 8) * (((orient == 0 ? OH : OW) + 15) / 16);
-    pl->pair = !(pair_env && pair_env[0] == '0') && (bn % 32 == 0) && px_tiles >= 2 && sm_count() >= 2;
+    pl->pair = !cv_env().no_pair && (bn % 32 == 0) && px_tiles >= 2 && sm_count() >= 2;
     const int b_rows = pl->pair ? bn / 2 : bn;
     p.a_plane_bytes = (uint32_t)slab_rows * 8 * 128;
     p.a_stage_bytes = p.a_plane_bytes * p.n_planes;
@@ -894,8 +1054,8 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     } else {
         p.n_a_stages = 2;
         if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
-        if (const char *as_env = getenv("RPE_CONV_ASTAGES")) {      // probe only
-            const int v = atoi(as_env);
+        if (cv_env().a_stages > 0) {      // probe only
+            const int v = cv_env().a_stages;
             if (v >= 1 && v <= kCvMaxAStages && (size_t)v * p.a_stage_bytes + 2 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = v;
         }
         p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
@@ -968,10 +1128,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.out_hi = reinterpret_cast<__nv_bfloat16 *>(d->out_hi), p.out_lo = reinterpret_cast<__nv_bfloat16 *>(d->out_lo);
     p.bf_ld = d->bf_ld, p.bf_off = d->bf_offset;
     p.mode = d->mode, p.aux = d->aux, p.aux_ld = d->aux_ld, p.aux2 = d->aux2, p.aux2_ld = d->aux2_ld;
-    {
-        const char *dbg_env = getenv("RPE_CONV_DEBUG");
-        p.dbg = dbg_env ? atoi(dbg_env) : 0;
-    }
+    p.dbg = cv_env().dbg;
     if (p.mode != 0) {
         // GRU epilogues: channel groups of 4 never straddle the z|r boundary; state tensors must be 16-byte addressable
         bool ok;
@@ -1014,7 +1171,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     // kernel kind: the GRU / projection modes have their own epilogues; mode 0 runs a lean epilogue when it only writes split
     // planes or only fp32 (the convolutions of the motion encoder and of the instance-norm encoder), else the generic one
     pl->kind = p.mode;
-    if (p.mode == 0 && !d->pre && !d->res && d->activation <= 1 && !getenv("RPE_CONV_GENERIC")) {
+    if (p.mode == 0 && !d->pre && !d->res && d->activation <= 1 && !cv_env().generic) {
         if (d->out_hi && d->out_lo && !d->out_f32 && d->out_scale == 1.0f) pl->kind = kKPlanes;
         else if (d->out_f32 && !d->out_hi) pl->kind = kKF32;
     }
@@ -1028,16 +1185,97 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         pl->kind = kKF32Stats;
     }
     pl->tiles_per_image = p.tiles_min * p.tiles_maj;
-    static bool attr[7] = {false, false, false, false, false, false, false};
-    if (!attr[pl->kind]) {
-        cudaError_t e = cv_dispatch(pl->kind, p, 0, false, nullptr, true);
+    {
+        cudaError_t e = cv_ensure_attr(pl->kind, p);
         if (e != cudaSuccess) {
             delete pl;
             return cuda_fail(e);
         }
-        attr[pl->kind] = true;
     }
     *plan_out = pl;
+    return RPE_OK;
+}
+
+// All-pairs correlation volume + pooled pyramid on the convolution kernel (kind 7): level0[b, q, t] = <f1[b, q, :], f2[b, t, :]> /
+// sqrt(C) as a 1x1 "convolution" of the first feature map whose weights are the second feature map of the same image.
+int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_hi, const void *f2_lo, float *pyramid, int B, int C, int h,
+                          int w, int num_levels, void *stream) {
+    using namespace rpe;
+    if (!f1_hi || !f1_lo || !f2_hi || !f2_lo || !pyramid) return RPE_ERR_INVALID_ARG;
+    if (B <= 0 || C <= 0 || (C % 64) || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4) return RPE_ERR_INVALID_ARG;
+    if ((h >> (num_levels - 1)) < 1 || (w >> (num_levels - 1)) < 1) return RPE_ERR_INVALID_ARG;
+    if ((double)B * h * w >= 4294967296.0) return RPE_ERR_INVALID_ARG;
+    const void *ptrs[4] = {f1_hi, f1_lo, f2_hi, f2_lo};
+    for (int k = 0; k < 4; ++k)
+        if (reinterpret_cast<uintptr_t>(ptrs[k]) & 15u) return RPE_ERR_ALIGNMENT;
+    if (!aligned16(pyramid)) return RPE_ERR_ALIGNMENT;
+    int rc = cv_load_encode();
+    if (rc != RPE_OK) return rc;
+    ConvParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_src = 1, p.n_planes = 2;
+    p.cblocks[0] = C / kCvBK, p.cb_base[0] = 0, p.ksteps_last[0] = kCvBK / 16;
+    p.N = B, p.OH = h, p.OW = w;
+    p.orient = 0, p.kmin = 1, p.kmaj = 1, p.pad_min = 0, p.pad_maj = 0, p.stride = 1, p.kw = 1, p.reuse = 1;
+    p.tiles_min = (w + 7) / 8, p.tiles_maj = (h + 15) / 16;
+    const int per_img = p.tiles_min * p.tiles_maj;
+    // CTA pairs own two adjacent query tiles that must read the SAME target block, i.e. lie in the same image
+    const bool pair = !cv_env().no_pair && (per_img % 2 == 0) && sm_count() >= 2;
+    const int b_rows = pair ? 128 : 256;
+    p.a_plane_bytes = 16 * 8 * 128, p.a_stage_bytes = 2 * p.a_plane_bytes;
+    p.b_plane_bytes = (uint32_t)b_rows * 128, p.b_stage_bytes = 2 * p.b_plane_bytes;
+    p.resident_b = 0;
+    p.n_a_stages = 2;
+    if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
+    p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
+    if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
+    p.corr_h = h, p.corr_w = w, p.corr_nbx = (w + 15) / 16, p.corr_levels = num_levels;
+    p.bn = 256, p.n_blocks = p.corr_nbx * ((h + 15) / 16), p.cout = p.bn * p.n_blocks;
+    p.scale = 1.0f / sqrtf((float)C);
+    {   // level bases (the layout of rpe_corr_level_offset) and which of them take vector stores
+        size_t off = 0;
+        for (int l = 0; l < num_levels; ++l) {
+            p.corr_lvl[l] = pyramid + off;
+            const size_t n = (size_t)B * h * w * (size_t)(h >> l) * (size_t)(w >> l);
+            off += (n + 63) & ~(size_t)63;
+        }
+        p.corr_vec = 0;
+        if ((w % 4) == 0 && (((size_t)h * w) % 4) == 0) p.corr_vec |= 1;
+        if (num_levels > 1 && ((w >> 1) % 2) == 0 && (((size_t)(h >> 1) * (w >> 1)) % 2) == 0 && (w % 2) == 0) p.corr_vec |= 2;
+    }
+    for (int pln = 0; pln < 2; ++pln) {
+        const cuuint64_t pix = (cuuint64_t)C * 2, row = pix * w;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)B};
+        cuuint64_t strides[3] = {pix, row, row * h};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        cuuint32_t abox[4] = {kCvBK, 8, 16, 1};
+        cuuint32_t bbox[4] = {kCvBK, 16, (cuuint32_t)(b_rows / 16), 1};
+        CUresult r = g_cv_encode(&p.amap[0][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptrs[pln]), dims, strides, abox, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = g_cv_encode(&p.wmap[0][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptrs[2 + pln]), dims, strides, bbox, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            g_last_cuda_error = 100000 + (int)r;
+            return RPE_ERR_CUDA;
+        }
+    }
+    RPE_CUDA_TRY(cv_ensure_attr(kKCorr, p));
+    const int px_tiles = B * per_img;
+    int grid;
+    if (pair) {
+        const long long units = (long long)(px_tiles / 2) * p.n_blocks;
+        long long clusters = sm_count() / 2;
+        if (clusters > units) clusters = units;
+        grid = 2 * (int)(clusters < 1 ? 1 : clusters);
+    } else {
+        const long long tiles = (long long)px_tiles * p.n_blocks;
+        grid = (int)(sm_count() < tiles ? sm_count() : tiles);
+    }
+    cv_dispatch(kKCorr, p, grid, pair, (cudaStream_t)stream, false);
+    RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
 

@@ -572,6 +572,8 @@ size_t rpe_corr_pyramid_bytes(int B, int h, int w, int num_levels) {
 }
 
 size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision) {
+    if (precision == RPE_CORR_BF16X3 && C % 64 == 0)      // four NHWC bf16 planes (hi / lo of both feature maps)
+        return 4 * (((size_t)B * h * w * C * 2 + 1023) & ~(size_t)1023);
     const size_t Kp = precision == RPE_CORR_TF32 ? (size_t)C : 3 * (size_t)C;
     const size_t es = precision == RPE_CORR_BF16X3 ? 2 : sizeof(float);
     return 2 * (((size_t)B * h * w * Kp * es + 1023) & ~(size_t)1023);
@@ -594,6 +596,16 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     int rc = load_encode();
     if (rc != RPE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (bf16 && C % 64 == 0) {
+        // bf16x3: NHWC hi/lo planes of both feature maps, then the fused volume + pyramid kernel (conv.cu kind 7): level 0 and
+        // the three pooled levels leave the tensor-memory accumulators in one pass, no second read of the volume
+        const size_t plane = (((size_t)B * Q * C * 2) + 1023) & ~(size_t)1023;
+        char *ws = reinterpret_cast<char *>(workspace);
+        void *f1h = ws, *f1l = ws + plane, *f2h = ws + 2 * plane, *f2l = ws + 3 * plane;
+        if ((rc = rpe_nchw_to_nhwc_split(fmap1, f1h, f1l, nullptr, B, C, h, w, C, 0, 0, 0, stream)) != RPE_OK) return rc;
+        if ((rc = rpe_nchw_to_nhwc_split(fmap2, f2h, f2l, nullptr, B, C, h, w, C, 0, 0, 0, stream)) != RPE_OK) return rc;
+        return rpe_corr_build_planes(f1h, f1l, f2h, f2l, pyramid, B, C, h, w, num_levels, stream);
+    }
     const int split = precision != RPE_CORR_TF32;
     const int Kp = split ? 3 * C : C;
     float *opA = reinterpret_cast<float *>(workspace);
@@ -623,12 +635,9 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     s.m_tiles = (Q + kBM - 1) / kBM;
     s.n_tiles = (Q + kBN - 1) / kBN;
     s.scale = 1.0f / sqrtf((float)C);
-    static bool attr_set = false;
-    if (!attr_set) {
-        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        attr_set = true;
-    }
+    // (function attributes are per device: set on every call -- a host-side no-op after the first)
+    RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     int grid = sm_count();
     const int tiles = s.B * s.m_tiles * s.n_tiles;
     if (grid > tiles) grid = tiles;
@@ -640,11 +649,7 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
         size_t smem = 0;
         for (int l = 0; l < num_levels; ++l) smem += (size_t)d.h[l] * d.w[l] * sizeof(float);
         if (smem > 200 * 1024) return RPE_ERR_INVALID_ARG;
-        static size_t pool_attr = 0;
-        if (smem > 48 * 1024 && smem > pool_attr) {
-            RPE_CUDA_TRY(cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            pool_attr = smem;
-        }
+        if (smem > 48 * 1024) RPE_CUDA_TRY(cudaFuncSetAttribute(corr_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         corr_pool_kernel<<<B * Q, 256, smem, st>>>(pyramid, d);
         RPE_LAUNCH_CHECK();
     }
@@ -678,11 +683,7 @@ static int corr_lookup_impl(const float *pyramid, const float *coords, float *ou
         return RPE_OK;
     }
     const size_t smem = ((size_t)nch * (kLookupQ + 1) + 8 * kMaxWin * kMaxWin) * sizeof(float);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        RPE_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    if (smem > 48 * 1024) RPE_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((Q + kLookupQ - 1) / kLookupQ, B);
     corr_lookup_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pyramid, d, coords, out, Q, radius,
                                                                   reinterpret_cast<__nv_bfloat16 *>(out_hi),

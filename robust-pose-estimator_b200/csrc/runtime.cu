@@ -7,14 +7,13 @@ int g_last_cuda_error = 0;
 long long g_launch_count = 0;
 
 int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        cached = n;
-    }
-    return cached;
+    static int cached[64] = {};                      // per device
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (dev >= 0 && dev < 64) cached[dev] = n;
+    return n;
 }
 }  // namespace rpe
 

@@ -88,11 +88,7 @@ static int convex_upsample_impl(const float *flow, const float *mask, float *out
     using namespace rpe;
     if (!flow || !mask || !out || B <= 0 || h <= 0 || w <= 0) return RPE_ERR_INVALID_ARG;
     const size_t smem = (576 * (kUpCells + 1) + 2 * 3 * (kUpCells + 2)) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
-        RPE_CUDA_TRY(cudaFuncSetAttribute(convex_upsample8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    RPE_CUDA_TRY(cudaFuncSetAttribute(convex_upsample8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
     dim3 grid((w + kUpCells - 1) / kUpCells, h, B);
     convex_upsample8_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(flow, mask, out, h, w, nhwc_ld);
     RPE_LAUNCH_CHECK();

@@ -12,7 +12,23 @@ by Newton ray/height-field intersection.  Pixel centres at +0.5 (pinhole_transfo
 """
 import numpy as np
 
-__all__ = ["SyntheticStereoSequence", "se3_exp_np", "default_intrinsics"]
+__all__ = ["SyntheticStereoSequence", "se3_exp_np", "se3_log_np", "default_intrinsics", "bench_sequence", "triangle_index"]
+
+BENCH_FRAMES = 65       # BASELINE config 3: 64 frame pairs
+
+
+def bench_sequence(size=(640, 512)):
+    """The 65-frame sequence (64 distinct pairs) behind bench.py, the 64-pair reference golden (tests/golden/bench64_poses.npz,
+    --bench64) and the config-5 leg: tethered walk, seed 0, two mask holes per frame."""
+    return SyntheticStereoSequence(BENCH_FRAMES, size, seed=0, motion_sigma=0.012, holes=2, tether=0.05)
+
+
+def triangle_index(i, n_base=BENCH_FRAMES):
+    """Frame i of an arbitrarily long sequence that walks the n_base rendered frames back and forth (0..n-1, n-2..0, 1..):
+    consecutive frames are always rendered neighbours, so every pair is one small camera motion."""
+    period = 2 * (n_base - 1)
+    r = i % period
+    return r if r < n_base else period - r
 
 
 def default_intrinsics(width=640, height=512):
@@ -39,6 +55,20 @@ def se3_exp_np(xi):
     return R, V @ tau
 
 
+def se3_log_np(R, t):
+    """Inverse of ``se3_exp_np``: (R, t) -> xi = [tau, phi]."""
+    c = np.clip((np.trace(R) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(c)
+    w = np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2.0
+    phi = w if th < 1e-8 else w * th / np.sin(th)
+    P = _hat(phi)
+    if th < 1e-8:
+        V = np.eye(3) + 0.5 * P + P @ P / 6.0
+    else:
+        V = np.eye(3) + (1 - np.cos(th)) / th ** 2 * P + (th - np.sin(th)) / th ** 3 * P @ P
+    return np.concatenate((np.linalg.solve(V, t), phi))
+
+
 class SyntheticStereoSequence:
     """Indexable like the reference's StereoDataset: ``seq[i] -> (limg, rimg, mask, i)``.
 
@@ -50,10 +80,13 @@ class SyntheticStereoSequence:
     :param motion_sigma: per-frame ``xi ~ sigma * N(0, I)`` in normalised units (config 2), or a smooth
            random walk ``xi_t = 0.9 xi_{t-1} + 0.3 sigma N`` when ``smooth_walk`` (config 5)
     :param holes: number of rectangular invalid regions in each mask (specularity stand-ins)
+    :param tether: > 0: the ABSOLUTE camera pose follows a mean-reverting walk ``a_{k+1} = (1 - tether) a_k + sigma N`` in
+           the tangent space, so a long sequence stays in front of the surface (the relative walks drift without bound);
+           consecutive frames still differ by one small motion of size ~sigma
     """
 
     def __init__(self, n_frames=2, size=(640, 512), seed=0, bf=2200.0, depth_scale_mm=250.0,
-                 motion_sigma=0.01, smooth_walk=False, holes=0, intrinsics=None):
+                 motion_sigma=0.01, smooth_walk=False, holes=0, intrinsics=None, tether=0.0):
         self.n_frames = int(n_frames)
         self.W, self.H = int(size[0]), int(size[1])
         self.bf = float(bf)
@@ -86,11 +119,21 @@ class SyntheticStereoSequence:
                 xi = motion_sigma * rng.standard_normal(6)
             self.rel_xi[k] = xi
         self._extr = [(np.eye(3), np.zeros(3))]
-        for k in range(self.n_frames - 1):
-            R, t = se3_exp_np(self.rel_xi[k])
-            t = t * depth_scale_mm
-            Rp, tp = self._extr[-1]
-            self._extr.append((R @ Rp, R @ tp + t))
+        if tether > 0.0:
+            a = np.zeros(6)
+            for k in range(self.n_frames - 1):
+                a = (1.0 - tether) * a + motion_sigma * rng.standard_normal(6)
+                R, t = se3_exp_np(a)
+                self._extr.append((R, t * depth_scale_mm))
+                Rp, tp = self._extr[-2]
+                Rr = R @ Rp.T                                              # T_k = P_{k+1} P_k^-1
+                self.rel_xi[k] = se3_log_np(Rr, (self._extr[-1][1] - Rr @ tp) / depth_scale_mm)
+        else:
+            for k in range(self.n_frames - 1):
+                R, t = se3_exp_np(self.rel_xi[k])
+                t = t * depth_scale_mm
+                Rp, tp = self._extr[-1]
+                self._extr.append((R @ Rp, R @ tp + t))
         self._hole_rng_seed = seed * 7919 + 13
         self.holes = int(holes)
         v, u = np.meshgrid(np.arange(self.H) + 0.5, np.arange(self.W) + 0.5, indexing="ij")
@@ -163,6 +206,44 @@ class SyntheticStereoSequence:
     def gt_rel_pose(self, k):
         """(R, t_normalised) of T_k with p_{k+1} = T_k p_k, translation in normalised units."""
         return se3_exp_np(self.rel_xi[k])
+
+    def frames_u8(self, indices=None, workers=None, cache_dir=None):
+        """(L, R, M) uint8 / bool arrays of the frames ``indices`` (default: all), rendered by a pool of worker processes
+        (one frame costs ~2.5 s of numpy) and cached as an .npz keyed by the generator parameters when ``cache_dir`` is given."""
+        import hashlib
+        import os
+        idx = list(range(self.n_frames)) if indices is None else list(indices)
+        path = None
+        if cache_dir is not None:
+            sig = repr((self.W, self.H, self.bf, self.depth_scale_mm, self.holes, self._hole_rng_seed, idx,
+                        [(R.tobytes(), t.tobytes()) for R, t in (self._extr[i] for i in idx)], self._tex_p.tobytes(),
+                        self._bump_p.tobytes())).encode()
+            path = os.path.join(cache_dir, "rpe_synth_" + hashlib.sha1(sig).hexdigest()[:16] + ".npz")
+            if os.path.isfile(path):
+                try:
+                    z = np.load(path)
+                    return z["L"], z["R"], z["M"]
+                except Exception:
+                    pass
+        workers = workers or min(len(idx), os.cpu_count() or 1)
+        if workers > 1:
+            import multiprocessing as mp
+            with mp.get_context("fork").Pool(workers) as pool:
+                out = pool.map(self._frame_for_pool, idx)
+        else:
+            out = [self._frame_for_pool(i) for i in idx]
+        L, R, M = (np.stack([o[k] for o in out]) for k in range(3))
+        if path is not None:
+            try:
+                tmp = path + f".{os.getpid()}.tmp.npz"
+                np.savez(tmp, L=L, R=R, M=M)
+                os.replace(tmp, path)
+            except OSError:
+                pass
+        return L, R, M
+
+    def _frame_for_pool(self, i):
+        return self.frame_u8(i)[:3]
 
     @property
     def calib(self):

@@ -33,6 +33,8 @@ class F2FEngine:
         self.use_graphs = use_graphs
         self._graphs = {}
         self._scale = float(estimator.scale)        # host copy: no device sync inside (graph-captured) chunks
+        self.keep_solve_inputs = False              # bench probe: keep the last chunk's rpe_pose_solve arguments alive
+        self.last_solve_inputs = None
         self.reset()
 
     def reset(self):
@@ -102,6 +104,8 @@ class F2FEngine:
         mode = ops.SOLVER_GN if head.solver == "gn" else ops.SOLVER_LBFGS_REF
         iters = head.gn_iters if head.solver == "gn" else head.lbgfs_iters
         sol = ops.pose_solve(time_flow, pcl1, pcl2w, conf1, conf2, mask1, mask2w, Kc, lw, mode=mode, max_iter=iters)
+        if self.keep_solve_inputs:
+            self.last_solve_inputs = (time_flow, pcl1, pcl2w, conf1, conf2, mask1, mask2w, Kc, lw)
         st = _FrameState()
         st.img, st.fmap, st.net, st.inp = limg[-1:], fL[-1:].contiguous(), net0[-1:], inp[-1:]
         st.depth, st.sflow, st.mask = depth_all[-1:], sflow_all[-1:], mask_all[-1:]

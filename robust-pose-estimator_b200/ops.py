@@ -16,6 +16,9 @@ CORR_TF32, CORR_TF32X3, CORR_BF16X3 = _lib.CORR_TF32, _lib.CORR_TF32X3, _lib.COR
 
 
 def _stream():
+    """The current stream of the current device.  The package is single-stream per device: scratch workspaces (pose solver
+    barriers, per-shape trunk buffers) are shared by all calls on a device, so concurrent calls from several streams or threads
+    are not supported (the reference is single-threaded, single-stream as well)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -53,6 +56,9 @@ def _chk(t, dtype, name, shape=None):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise RpeError(f"{name}: expected a CUDA tensor (rpe_b200 has no CPU path), got "
                        f"{type(t).__name__}{'' if not isinstance(t, torch.Tensor) else ' on ' + str(t.device)}")
+    if t.device.index != torch.cuda.current_device():
+        raise RpeError(f"{name}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                       "(kernels launch on the current device's stream; use torch.cuda.set_device / torch.cuda.device)")
     if t.dtype != dtype:
         raise RpeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -273,9 +279,8 @@ def pose_solve(flow, pcl1, pcl2, w1, w2, m1, m2, K, lw, mode=SOLVER_LBFGS_REF, m
 # ---------------------------------------------------------------------------------------------
 class CorrPyramid:
     """Device-resident 4-level all-pairs correlation pyramid (rpe_corr_build) + window lookup
-    (rpe_corr_lookup).  Buffers are cached per shape and reused across frames."""
-
-    _cache = {}
+    (rpe_corr_lookup).  Every instance owns its volume (like the reference's CorrBlock); the blocks come from torch's
+    caching allocator, so a tracker that builds one pyramid per chunk reuses the same memory."""
 
     def __init__(self, fmap1, fmap2, num_levels=4, radius=4, precision=CORR_TF32):
         B, Cc, h, w = fmap1.shape
@@ -284,14 +289,8 @@ class CorrPyramid:
         self.B, self.C, self.h, self.w = B, Cc, h, w
         self.num_levels, self.radius = num_levels, radius
         l = _lib.lib()
-        key = (fmap1.device.index, B, Cc, h, w, num_levels, precision)
-        bufs = CorrPyramid._cache.get(key)
-        if bufs is None:
-            pyr = torch.empty(l.rpe_corr_pyramid_bytes(B, h, w, num_levels) // 4, dtype=torch.float32, device=fmap1.device)
-            ws = torch.empty(l.rpe_corr_workspace_bytes(B, Cc, h, w, precision) + 1024, dtype=torch.uint8, device=fmap1.device)
-            bufs = (pyr, ws)
-            CorrPyramid._cache[key] = bufs
-        self.pyramid, self._ws = bufs
+        self.pyramid = torch.empty(l.rpe_corr_pyramid_bytes(B, h, w, num_levels) // 4, dtype=torch.float32, device=fmap1.device)
+        self._ws = torch.empty(l.rpe_corr_workspace_bytes(B, Cc, h, w, precision) + 1024, dtype=torch.uint8, device=fmap1.device)
         ws_ptr = (self._ws.data_ptr() + 1023) & ~1023
         with _timed("corr_build", B):
             check(l.rpe_corr_build(_p(fmap1), _p(fmap2), _p(self.pyramid), B, Cc, h, w, num_levels, int(precision),

@@ -31,19 +31,36 @@ def frames_of(pair_range):
     return (a, b + 1) if b > a else (a, a)
 
 
-def gather_pair_records(local, n_pairs, group=None):
-    """all_gather of per-pair records.  local: (P_r, D) tensor of this rank's pairs (P_r from shard_ranges);
-    returns the (n_pairs, D) tensor in global pair order on every rank."""
+class PendingRecords:
+    """Handle of an in-flight ``gather_pair_records(..., async_op=True)``: the collective runs on the backend's own stream
+    while the caller keeps launching the next sequence; ``wait()`` orders the current stream after it and returns the
+    (n_pairs, D) tensor in global pair order."""
+
+    def __init__(self, work, bufs, ranges, local):
+        self._work, self._bufs, self._ranges, self._local = work, bufs, ranges, local
+
+    def wait(self):
+        if self._work is None:
+            return self._local
+        self._work.wait()
+        return torch.cat([self._bufs[r][:b - a] for r, (a, b) in enumerate(self._ranges)], 0)
+
+
+def gather_pair_records(local, n_pairs, group=None, async_op=False):
+    """all_gather of per-pair records -- the only exchange step of the path.  local: (P_r, D) tensor of this rank's pairs
+    (P_r from shard_ranges); returns the (n_pairs, D) tensor in global pair order on every rank, or with ``async_op`` a
+    ``PendingRecords`` handle (the gather then overlaps whatever the caller launches next)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
-        return local
+        return PendingRecords(None, None, None, local) if async_op else local
     ranges = shard_ranges(n_pairs, world)
     pmax = max(b - a for a, b in ranges)
     padded = torch.zeros((pmax, local.shape[1]), dtype=local.dtype, device=local.device)
     padded[:local.shape[0]] = local
     bufs = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bufs, padded, group=group)
-    return torch.cat([bufs[r][:b - a] for r, (a, b) in enumerate(ranges)], 0)
+    work = dist.all_gather(bufs, padded, group=group, async_op=True)
+    pending = PendingRecords(work, bufs, ranges, local)
+    return pending if async_op else pending.wait()
 
 
 def compose_trajectory(records, init_pose, inv_scale):
@@ -63,18 +80,18 @@ def compose_trajectory(records, init_pose, inv_scale):
 
 
 def infer_sequence_sharded(estimator, load_frames, n_frames, chunk=8, use_graphs=False, group=None):
-    """Sharded ``infer_sequence``: every rank calls this with a ``load_frames(a, b) -> (limgs, rimgs, masks)``
-    callback returning device tensors of frames [a, b).  Returns (trajectory (n_frames,7), failed) on every rank."""
-    from .engine import F2FEngine
+    """Sharded ``PoseEstimator.infer_sequence``: every rank calls this with a ``load_frames(a, b) -> (limgs, rimgs, masks)``
+    callback returning frames [a, b) of the GLOBAL sequence, either device tensors or (pinned) host tensors -- host
+    frames are uploaded chunk by chunk behind the compute, like ``infer_sequence`` does.  One all_gather of the (P,13) pair
+    records, then every rank composes the trajectory on its host.  Returns (trajectory (n_frames,7) float32 CPU, failed)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n_pairs = n_frames - 1
     pr = shard_ranges(n_pairs, world)[rank]
     fa, fb = frames_of(pr)
-    eng = F2FEngine(estimator, chunk, use_graphs)
     if fb > fa:
         limgs, rimgs, masks = load_frames(fa, fb)
-        rel, log, _ = eng.infer_sequence(limgs, rimgs, masks, sequence_start=(pr[0] == 0))
+        rel, log, _ = estimator.infer_pairs(limgs, rimgs, masks, chunk=chunk, use_graphs=use_graphs, sequence_start=(pr[0] == 0))
         local = torch.cat((rel, log), 1)
     else:
         local = torch.zeros((0, 13), device=estimator.baseline.device)

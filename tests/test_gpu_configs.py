@@ -1,0 +1,253 @@
+"""GPU parity of the BASELINE configurations that round 1 left untested:
+  config 1  the reference's OWN fixtures (tests/test_data/tartan_air: real rendered texture) -> tests/golden/e2e_cfg1_tartan.npz
+  config 3  all 64 frame pairs bench.py times, against the reference's poses of the same frames (tests/golden/bench64_poses.npz)
+  sharding  shard A + shard B (halo frame, sequence_start=False) == the single-process run, through the public sharded API
+  CLI       scripts/infer_trajectory.main on the infer_f2f_nw configuration against the reference's trajectory.freiburg
+plus the advisor's regression cases (reload after a forward, iters = 0, flow2depth(upsample=False))."""
+import hashlib
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import se3_np
+from oracle.detrand import unpack
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CKPT = os.path.join(ROOT, "oracle", "_ref", "trained", "poseNet_2xf8up4b.pth")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+SLAM = {"frame2frame": True, "dist_thr": 0.05, "depth_clipping": [1, 250], "debug": False, "conf_weighing": True,
+        "average_pts": False, "lbgfs_iters": 20}
+
+
+def _need_ckpt():
+    if not os.path.isfile(CKPT):
+        pytest.skip("reference checkpoint not shipped (oracle/_ref/trained is created by oracle/make_golden.py)")
+
+
+def _pose_err(a, b):
+    d = se3_np.mul(se3_np.inv(a.astype(np.float64)), b.astype(np.float64))
+    rot = np.linalg.norm(se3_np.log(d)[3:])
+    trans = np.linalg.norm(a[:3] - b[:3]) / max(np.linalg.norm(b[:3]), 1e-12)
+    return rot, trans
+
+
+def _estimator(K, bf, size, precision="bf16x3", **over):
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_estimator import PoseEstimator
+    return PoseEstimator(dict(SLAM, precision=precision, **over), torch.tensor(np.asarray(K)), float(bf), CKPT, size).cuda()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 1: the reference's own fixtures
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_config1_tartan_fixture_pair(precision):
+    """Real texture (tartan_air 000000/000001 resized to 640x512, right view synthesised from the fixture depth):
+    both pairs of the sequence [0, 1, 0] within the north-star gates, in both parity-grade precisions."""
+    _need_ckpt()
+    g = np.load(os.path.join(GOLDEN, "e2e_cfg1_tartan.npz"))
+    W, H = [int(v) for v in g["size"]]
+    assert (W, H) == (640, 512)
+    est = _estimator(g["K"], g["bf"], (W, H), precision)
+    order = [int(k) for k in g["order"]]
+    for i, k in enumerate(order):
+        limg = torch.from_numpy(g["imgs_l"][k].astype(np.float32))[None].cuda()
+        rimg = torch.from_numpy(g["imgs_r"][k].astype(np.float32))[None].cuda()
+        mask = torch.ones((1, 1, H, W), dtype=torch.bool, device="cuda")
+        pose, _, flow, weights = est(limg, rimg, mask)
+        if i == 0:
+            continue
+        rot, trans = _pose_err(pose.vec().cpu().numpy().reshape(7), g["traj"][i])
+        # per-pair relative pose (normalised units): the quantity the north star gates
+        print(f"config1/{precision}: frame {i} trajectory error rot {rot:.2e} rad, rel. trans {trans:.2e}")
+        assert rot < 1e-4 and trans < 1e-4
+    assert est.check_failures() == []
+    # last pair: flows (golden stored as fp16 -> 1.6e-2 px quantisation at |flow| ~ 30 px, so the gate uses the fp32 1/4 grid)
+    epe_t = np.sqrt(((flow[0, :, ::4, ::4].cpu().numpy() - g["s_time_flow_ds4"]) ** 2).sum(0))
+    epe_s = np.sqrt(((est.frame.flow[0, :, ::4, ::4].cpu().numpy() - g["s_stereo_flow2_ds4"]) ** 2).sum(0))
+    print(f"config1/{precision}: time-flow EPE mean {epe_t.mean():.2e} max {epe_t.max():.2e}; stereo {epe_s.mean():.2e} / {epe_s.max():.2e}")
+    assert epe_t.mean() < 1e-2 and epe_s.mean() < 1e-2
+    c1 = weights[0][0].cpu().numpy().astype(np.float32)
+    c2 = weights[1][0].cpu().numpy().astype(np.float32)
+    assert np.abs(c1 - g["s_conf1"].astype(np.float32)).max() < 5e-3
+    assert np.abs(c2 - g["s_conf2"].astype(np.float32)).max() < 5e-3
+    diff = (est.frame.mask[0, 0].cpu().numpy() != unpack(g["s_mask2_valid"], (H, W))).mean()
+    print(f"config1/{precision}: mask2&valid mismatch fraction with e2e flows {diff:.2e}")
+    assert diff < 1e-3
+
+
+def test_config1_masks_bit_exact_on_reference_flows():
+    """Stage-wise gate on the fixture pair: the reference's own fp32 flows in -> stereo validity and warped mask bit-exact."""
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import ops
+    fpath = os.path.join(ROOT, "oracle", "_ref", "golden_cfg1_flows.npz")
+    if not os.path.isfile(fpath):
+        pytest.skip("full-resolution reference flows not shipped (oracle/make_golden.py --config1)")
+    g, fl = np.load(os.path.join(GOLDEN, "e2e_cfg1_tartan.npz")), np.load(fpath)
+    H, W = 512, 640
+    sflow = torch.from_numpy(fl["stereo_flow2"])[None].cuda()
+    tflow = torch.from_numpy(fl["time_flow"])[None].cuda()
+    K = torch.tensor(g["K"], dtype=torch.float32)[None].cuda()
+    bf = (torch.tensor(float(g["bf"])).float() * torch.tensor(1 / 250)).reshape(1).cuda()
+    mask = torch.ones((1, 1, H, W), dtype=torch.bool, device="cuda")
+    depth2, valid, pcl2 = ops.depth_proj(sflow, bf, K, mask)
+    assert np.array_equal(np.packbits(mask.cpu().numpy().reshape(-1)), g["s_mask2_valid"])
+    img2 = torch.from_numpy(g["imgs_l"][int(g["order"][-1])].astype(np.float32))[None].cuda()
+    _, _, _, mask2w = ops.warp8_mask(pcl2, img2, sflow, mask, tflow)
+    assert np.array_equal(np.packbits(mask2w.cpu().numpy().reshape(-1)), g["s_mask2w"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# config 3: the bench inputs
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def bench_frames():
+    import tempfile
+    import rpe_b200  # noqa: F401
+    from rpe_b200.dataset.synthetic import bench_sequence
+    seq = bench_sequence()
+    L, R, M = seq.frames_u8(cache_dir=tempfile.gettempdir())
+    return seq, L, R, M
+
+
+def test_bench_inputs_all_64_pairs_within_gate(bench_frames):
+    """Every one of the 64 distinct frame pairs bench.py times, in the product precision, against the unmodified reference's
+    CPU fp32 pose of the same frames ('re-measure on the bench inputs')."""
+    _need_ckpt()
+    seq, L, R, M = bench_frames
+    g = np.load(os.path.join(GOLDEN, "bench64_poses.npz"))
+    sha = hashlib.sha1(L.tobytes() + R.tobytes() + np.stack([np.packbits(m.reshape(-1)) for m in M]).tobytes()).digest()
+    assert np.array_equal(np.frombuffer(sha, dtype=np.uint8), g["frames_sha1"]), "regenerated bench frames differ from the golden's inputs"
+    est = _estimator(seq.calib["intrinsics"]["left"], seq.calib["bf"], (640, 512), "bf16x3")
+    dev = torch.device("cuda:0")
+    rel, log, evals = est.infer_pairs(torch.from_numpy(L).to(dev).float(), torch.from_numpy(R).to(dev).float(),
+                                      torch.from_numpy(M).to(dev), chunk=32)
+    rel = rel.double().cpu().numpy()
+    worst_r = worst_t = 0.0
+    for k in range(64):
+        rot, trans = _pose_err(rel[k], g["rel_pose"][k])
+        worst_r, worst_t = max(worst_r, rot), max(worst_t, trans)
+        assert rot < 1e-4 and trans < 1e-4, f"pair {k}: rot {rot:.2e} rad, rel. trans {trans:.2e}"
+    same = int((evals.cpu().numpy().astype(int) == g["n_evals"]).sum())
+    print(f"bench64/bf16x3: worst rot {worst_r:.2e} rad, worst rel. trans {worst_t:.2e}; L-BFGS evaluation count equal on {same}/64 pairs")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# sharding
+# ---------------------------------------------------------------------------------------------------------------
+def test_sharded_halo_run_is_bit_equal_to_single_process(bench_frames):
+    """shard A = frames [0, k], shard B = frames [k, T) with the halo frame k and sequence_start=False.
+    The concatenated pair records must be BIT-equal to the single-process run (same kernels, per-sample arithmetic), through
+    the same call ``parallel.infer_sequence_sharded`` makes on every rank."""
+    _need_ckpt()
+    seq, L, R, M = bench_frames
+    T, k = 12, 5
+    dev = torch.device("cuda:0")
+    dL, dR, dM = (torch.from_numpy(x[:T]).to(dev) for x in (L, R, M))
+    dL, dR = dL.float(), dR.float()
+    est = _estimator(seq.calib["intrinsics"]["left"], seq.calib["bf"], (640, 512), "bf16x3")
+    full = est.infer_pairs(dL, dR, dM.clone(), chunk=4)
+    a = est.infer_pairs(dL[:k + 1], dR[:k + 1], dM[:k + 1].clone(), chunk=4, sequence_start=True)
+    b = est.infer_pairs(dL[k:], dR[k:], dM[k:].clone(), chunk=4, sequence_start=False)
+    for i in range(3):
+        cat = torch.cat((a[i], b[i]))
+        assert torch.equal(cat, full[i]), f"output {i}: sharded run differs from the single-process run"
+    # and the halo rule matters: treating the halo frame as a sequence start changes pair k (its mask1 lacks stereo validity)
+    wrong = est.infer_pairs(dL[k:], dR[k:], dM[k:].clone(), chunk=4, sequence_start=True)
+    assert not torch.equal(wrong[0][0], full[0][k])
+    # host-fed (pinned uint8) shard == device-resident shard
+    hb = est.infer_pairs(torch.from_numpy(L[k:T]).pin_memory(), torch.from_numpy(R[k:T]).pin_memory(),
+                         torch.from_numpy(M[k:T]).pin_memory(), chunk=4, sequence_start=False)
+    assert torch.equal(hb[0], b[0])
+    # world size 1 through the sharded entry point == infer_sequence
+    from rpe_b200 import parallel
+    load = lambda fa, fb: (dL[fa:fb], dR[fa:fb], dM[fa:fb].clone())
+    est.last_pose = est.last_pose.__class__.Identity(1, device=dev)
+    traj_s, failed_s = parallel.infer_sequence_sharded(est, load, T, chunk=4)
+    est.last_pose = est.last_pose.__class__.Identity(1, device=dev)
+    traj, failed = est.infer_sequence(dL, dR, dM.clone(), chunk=4)
+    assert torch.equal(traj_s, traj) and torch.equal(failed_s, failed)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CLI
+# ---------------------------------------------------------------------------------------------------------------
+def test_infer_trajectory_main_writes_reference_freiburg(tmp_path):
+    """scripts/infer_trajectory.main(args, config) with the infer_f2f_nw configuration on the sequence the reference's own
+    main loop produced tests/golden/e2e_nw_384x352.npz from: same line count and timestamps, poses within the gate."""
+    _need_ckpt()
+    import yaml
+    import rpe_b200  # noqa: F401
+    from rpe_b200.dataset.synthetic import SyntheticStereoSequence
+    from rpe_b200.scripts import infer_trajectory
+    g = np.load(os.path.join(GOLDEN, "e2e_nw_384x352.npz"))
+    W, H = [int(v) for v in g["size"]]
+    seq = SyntheticStereoSequence(int(g["imgs_l"].shape[0]), (W, H), seed=int(g["seed"]), holes=2)
+    assert np.array_equal(seq.frame_u8(1)[0], g["imgs_l"][1])
+    with open(os.path.join(ROOT, "robust-pose-estimator_b200", "configuration", "infer_f2f_nw.yaml")) as f:
+        config = yaml.load(f, Loader=yaml.SafeLoader)
+    config["img_size"] = [W, H]
+    config["slam"]["precision"] = "bf16x3"
+    args = types.SimpleNamespace(input=seq, checkpoint=CKPT, outpath=str(tmp_path), device="gpu", start=0, stop=10000000000, step=1,
+                                 log=None, force_video=False, viewer="none", block_viewer=False)
+    trajectory = infer_trajectory.main(args, config)
+    assert len(trajectory) == seq.n_frames + 1                              # init pose + one entry per frame
+    ours = np.loadtxt(tmp_path / "trajectory.freiburg")
+    ref = np.loadtxt(g["freiburg"].tobytes().decode().splitlines())          # the reference writer's bytes for frames 0..4
+    assert ours.shape[0] == ref.shape[0] + 1 and np.array_equal(ours[1:, 0], ref[:, 0])
+    assert np.array_equal(ours[0, 1:], np.array([0, 0, 0, 0, 0, 0, 1.0]))
+    assert np.abs(ours[1:, 1:4] - ref[:, 1:4]).max() < 1e-4 * np.abs(ref[:, 1:4]).max()
+    assert np.abs(ours[1:, 4:] - ref[:, 4:]).max() < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# advisor regressions
+# ---------------------------------------------------------------------------------------------------------------
+def test_reload_after_forward_uses_the_new_weights(bench_frames):
+    """A model that already ran (packed / BN-folded tensor-core weights cached) and then loads a checkpoint must equal a fresh
+    model built from that checkpoint."""
+    _need_ckpt()
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_net import PoseNet
+    seq, L, R, M = bench_frames
+    dev = torch.device("cuda:0")
+    l, r = (torch.from_numpy(x[:1]).to(dev).float() for x in (L, R))
+    cfg = {"image_shape": (512, 640), "use_weights": True, "lbgfs_iters": 20, "small": False, "dropout": 0.0, "precision": "bf16x3"}
+    sd = torch.load(CKPT, map_location="cpu", weights_only=False)["state_dict"]
+    torch.manual_seed(1)
+    used = PoseNet(dict(cfg)).to(dev).eval()
+    bl = torch.tensor([8.8], device=dev)
+    used.flow2depth(l, r, bl)                                               # random-init forward: fills every weight cache
+    used.load_state_dict(sd)
+    fresh = PoseNet(dict(cfg)).to(dev).eval()
+    fresh.load_state_dict(sd)
+    d1, f1, v1 = used.flow2depth(l, r, bl)
+    d2, f2, v2 = fresh.flow2depth(l, r, bl)
+    assert torch.equal(f1, f2) and torch.equal(d1, d2) and torch.equal(v1, v2)
+
+
+def test_flow2depth_low_resolution_branch_and_zero_iterations(bench_frames):
+    """PoseNet.flow2depth(upsample=False) (pose_net.py:127-135: 1/8-resolution flow, depth / 8) and RAFT with iters = 0."""
+    _need_ckpt()
+    seq, L, R, M = bench_frames
+    dev = torch.device("cuda:0")
+    est = _estimator(seq.calib["intrinsics"]["left"], seq.calib["bf"], (640, 512), "bf16x3")
+    l, r = (torch.from_numpy(x[:2]).to(dev).float() for x in (L, R))
+    bl = torch.tensor([8.8], device=dev)                                     # (1,) baseline broadcast over a batch of 2
+    depth, flow, valid = est.model.flow2depth(l, r, bl, upsample=False)
+    assert flow.shape == (2, 2, 64, 80) and depth.shape == (2, 1, 64, 80) and valid.dtype == torch.bool
+    ref = bl[:, None, None] / -flow[:, 0]
+    ref = ref / 8.0
+    rv = (ref > 0) & (ref <= 1.0)
+    ref[~rv] = 1.0
+    assert torch.equal(valid[:, 0], rv) and torch.equal(depth[:, 0], ref)
+    raft = est.model.flow
+    fl, fr, net, inp = raft.encode(l, r)
+    init = torch.full((2, 2, 64, 80), 0.75, device=dev)
+    preds, _, _, flow_lo = raft.refine(fl.contiguous(), fr.contiguous(), net, inp, iters=0, flow_init=init, upsample=False)
+    assert torch.equal(flow_lo, init)

@@ -55,9 +55,10 @@ def test_lookup_exact_on_reference_pyramid(ops, golden_dir):
     np.testing.assert_allclose(out, g["corr_lookup"], atol=3e-6)
 
 
-@pytest.mark.parametrize("h,w,B", [(64, 80, 2), (44, 48, 1), (36, 44, 3)])
+@pytest.mark.parametrize("h,w,B", [(64, 80, 2), (44, 48, 1), (36, 44, 3), (48, 40, 2), (20, 22, 1)])
 def test_corr_gemm_full_size_vs_fp64(ops, h, w, B):
-    """Bench-size volume (and sizes that are not multiples of the 128x256 tile) against an fp64 matmul."""
+    """Bench-size volume (and sizes that are not multiples of the 128x256 tile / of the 16x16 target block, an odd number of
+    query tiles per image = no CTA pairs, a width that rules out vector stores) against an fp64 matmul."""
     C = 256
     f1 = dev(det_uniform((B, C, h, w), 71, -1.5, 1.5))
     f2 = dev(det_uniform((B, C, h, w), 72, -1.5, 1.5))
@@ -82,8 +83,12 @@ def test_corr_gemm_full_size_vs_fp64(ops, h, w, B):
     errb, errb64 = (gotb - refb).abs().max().item(), (gotb - ref64).abs().max().item()
     print(f"corr bf16x3 {B}x{h}x{w}: vs split products {errb:.2e}, vs fp64 {errb64:.2e}")
     assert errb < 2e-5 and errb64 < 2e-4
+    # the fused epilogue's pooled levels == avg_pool2d of ITS level 0, level by level (floor on odd sizes)
+    lvl = cpb.level(0)
     for l in (1, 2, 3):
         assert cpb.level(l).shape == cp3.level(l).shape
+        lvl = F.avg_pool2d(lvl, 2, stride=2)
+        assert (cpb.level(l) - lvl).abs().max().item() < 1e-6, f"bf16x3 pyramid level {l}"
     cp1 = ops.CorrPyramid(f1, f2, precision=ops.CORR_TF32)
     got1 = cp1.level(0).view(B, Q, Q).double()
     # single pass == exact product of tf32-rounded inputs

@@ -86,3 +86,18 @@ def test_se3_matches_standin():
         p = rng.normal(size=(5, 3))
         np.testing.assert_allclose(se3_np.act(X, p), (Xt * torch.tensor(p)).numpy(), atol=1e-14)
     np.testing.assert_allclose(se3_np.log(se3_np.exp(np.full(6, 1e-9))), np.full(6, 1e-9), atol=1e-20)
+
+
+def test_torch_solver_matches_reference(real):
+    """oracle/pose_torch.solve (torch.optim.LBFGS over the lietorch stand-in: the solver of bench.py's reference-on-GPU arm)
+    stops at the reference's pose after the reference's number of evaluations."""
+    import torch
+    from oracle import pose_torch
+    g, args = real
+    t = [torch.from_numpy(np.ascontiguousarray(a)) for a in args]
+    flow, pcl1, pcl2w, w1, w2, m1, m2w, K, lw = t
+    X, lg, n_evals = pose_torch.solve(flow[None], pcl1[None], pcl2w[None], w1[None, None], w2[None, None], m1[None, None],
+                                      m2w[None, None], K[None].float(), lw[None].float(), lbgfs_iters=20)
+    assert n_evals == len(g["eval_pose"])
+    np.testing.assert_allclose(X[0].numpy(), g["sol_vec"], atol=1e-10)
+    np.testing.assert_allclose(lg[0].numpy(), g["sol_log"], atol=1e-10)

@@ -139,8 +139,9 @@ def test_gpu_only3d_1280x1024(precision):
     print(f"only3d/{precision}: rot {rot:.2e} rad, rel. trans {trans:.2e}, abs trans {np.linalg.norm(p[:3] - g['traj'][1][:3]):.2e} mm, "
           f"flow EPE {epe_t.mean():.2e} / {epe_s.mean():.2e}")
     assert epe_t.mean() < 1e-2 and epe_s.mean() < 1e-2
-    # Tolerances: flow 1e-2 px EPE and rotation 1e-4 rad as in the north star.  Relative translation: 2e-4 for THIS config only.
+    # Tolerances: flow 1e-2 px EPE and rotation 1e-4 rad as in the north star.  Relative translation: 2e-4 for the cuDNN fp32 mode of THIS config only.
     # The frame-to-frame translation of this pair is 0.27 mm, so 1e-4 relative is 27 nm; the 3-D-only objective at 1.3 Mpx
     # turns the 2e-5 px flow difference between cuDNN and oneDNN fp32 convolutions (summation order) into 1.06e-4 relative
     # (2.8e-5 mm absolute; measured on B200, profiles/r1_s6_pytest_gpu.log).  Configs 1-3 and 5 keep the 1e-4 gate.
-    assert rot < 1e-4 and trans < 2e-4 and np.linalg.norm(p[:3] - g["traj"][1][:3]) < 1e-4
+    # The product precision (bf16x3) keeps the north-star gate; only the cuDNN fp32 debugging mode carries the slack below.
+    assert rot < 1e-4 and trans < (1e-4 if precision == "bf16x3" else 2e-4) and np.linalg.norm(p[:3] - g["traj"][1][:3]) < 1e-4
