@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the f2f pose path (BASELINE.json metric: f2f frame-pairs/sec @640x512 stereo).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision bf16x3|fp32|tf32|fp16|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision fp16x3|fp32|tf32|fp16|bf16]
 
 A step = one pass of the hot path over one batch of synthetic input: a 65-frame 640x512 stereo sequence
 (64 frame pairs) per rank (weak scaling; pairs are independent in f2f).
@@ -270,8 +270,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): 64 pairs per GPU per step; strong: BASELINE config 3 as worded, 64 pairs per step in total, "
                          "64/N per GPU.  With N > 1 the other mode is always measured too and reported under 'strong' / 'weak'.")
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "tf32", "fp16", "bf16"],
-                    help="bf16x3 (default): whole trunk on the hand-written tcgen05 kernels, fp32-equivalent split arithmetic "
+    ap.add_argument("--precision", default="fp16x3", choices=["fp32", "fp16x3", "tf32", "fp16", "bf16"],
+                    help="fp16x3 (default): whole trunk on the hand-written tcgen05 kernels, fp32-equivalent split arithmetic "
                          "(parity-gated); fp32: cuDNN fp32 trunk; tf32 / fp16 / bf16: cuDNN reduced precision (not parity-gated)")
     ap.add_argument("--chunk", type=int, default=32, help="frames per engine chunk (measured on B200: 11 -> 318, 22 -> 330, 32 -> 334 pairs/s; fewer, larger launches)")
     ap.add_argument("--pairs", type=int, default=64)
@@ -545,8 +545,8 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
     # per-kernel rooflines from the in-run CUDA-event timers.  Convolution stages carry their executed tensor-core flops
-    # as "units" (3 bf16 MMAs per multiply-add in the bf16x3 split); the algorithmic (fp32-equivalent) flops are a third.
-    split = 3.0 if args.precision == "bf16x3" else 1.0
+    # as "units" (3 bf16 MMAs per multiply-add in the fp16x3 split); the algorithmic (fp32-equivalent) flops are a third.
+    split = 3.0 if args.precision == "fp16x3" else 1.0
     kernels = {}
     for name, d in stage.items():
         secs = d["total_ms"] * 1e-3
@@ -569,7 +569,7 @@ def main():
     own = {k: v for k, v in stage.items() if k in kernels and not k.startswith("conv_tc")}
     conv_ms = sum(stage[k]["total_ms"] for k in conv)
     if conv and conv_ms >= max([v["total_ms"] for v in own.values()] + [0.0]):
-        # dominant kernel = conv_bf16_kernel (tcgen05 implicit-GEMM convolution; update operator + encoders)
+        # dominant kernel = conv_f16x3_kernel (tcgen05 implicit-GEMM convolution; update operator + encoders)
         flops_exec = sum(stage[k]["units"] for k in conv)
         n_launch = sum(stage[k]["launches"] for k in conv)
         achieved = flops_exec / split / (conv_ms * 1e-3) / 1e12
@@ -580,12 +580,12 @@ def main():
                 traffic = float(tr["dram_bytes_per_launch"])
         except (OSError, KeyError, ValueError):
             pass
-        roofline = {"kernel": "conv_bf16_pair_kernel", "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
+        roofline = {"kernel": "conv_f16x3_pair_kernel", "bound": "tensor", "achieved": achieved, "peak": tc_peak, "unit": "TFLOP/s",
                     "frac": achieved / tc_peak, "traffic": traffic, "traffic_source": "profiles/conv_traffic.json (ncu, launch-weighted mean)" if traffic else None,
                     "peak_source": peak_src,
                     "avg_launch_us": 1e3 * conv_ms / n_launch, "algorithmic_flops_per_launch": flops_exec / split / n_launch,
                     "executed_tflops": flops_exec / (conv_ms * 1e-3) / 1e12, "executed_frac": flops_exec / (conv_ms * 1e-3) / 1e12 / tc_peak,
-                    "note": "algorithmic = fp32-equivalent convolution flops; the bf16x3 split executes 3 bf16 MMAs per multiply-add, "
+                    "note": "algorithmic = fp32-equivalent convolution flops; the fp16x3 split executes 3 bf16 MMAs per multiply-add, "
                             "so executed_frac is the tensor-pipe figure and frac <= 1/3 by construction"}
     else:
         dom = max(own, key=lambda k: own[k]["total_ms"])
@@ -595,7 +595,7 @@ def main():
                     "algorithmic_bytes_per_launch": kernels[dom]["achieved"] * 1e9 * d["avg_us"] * 1e-6}
     line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32-equivalent split, fp32 accumulate)", "tf32": "tf32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
+            "dtype": {"fp32": "f32", "fp16x3": "fp16x3 (fp32-equivalent split, fp32 accumulate)", "tf32": "tf32", "fp16": "f16", "bf16": "bf16"}[args.precision], "data": "synthetic",
             "config": {"workload": "f2f_640x512_seq65", "pairs_per_gpu_per_step": main_res["pairs_rank"], "pairs_per_step": main_res["total"],
                        "chunk": main_res["chunk"], "frames": "65 distinct rendered frames (64 distinct pairs) walked back and forth",
                        "precision": args.precision, "solver": "lbfgs_ref", "lbgfs_iters": 20, "conf_weighing": True,

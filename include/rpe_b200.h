@@ -150,8 +150,12 @@ typedef struct rpe_pose_problem {
  *   trace    (n, trace_cap, 16) f64 or NULL: per evaluation [pose7 | grad6 | f | L2d | L3d]
  *   max_iter = lbgfs_iters (LBFGS) or GN iterations. */
 size_t rpe_pose_workspace_bytes(int n_pairs);
-/* Tuning: upper bound on the pairs solved concurrently by disjoint CTA groups (default 16, 1..256). */
+/* Tuning (results never depend on it: the reduction tree is fixed by the pixel index).  rpe_pose_set_groups: upper bound on the
+ * pairs solved concurrently by disjoint CTA groups (1..64; default: as many as fit).  rpe_pose_set_group_size: CTAs per group when
+ * a batch is solved (power of two <= 128, default 32).  Process-wide settings, not thread-safe -- like the rest of the library's
+ * state (cached function attributes, last-error code): the reference contract is one host thread per process. */
 int rpe_pose_set_groups(int groups);
+int rpe_pose_set_group_size(int ctas);
 int rpe_pose_solve(const rpe_pose_problem *problem_host, int mode, int max_iter, int with_hessian,
                    double *out, float *pose_f32, float *log_f32, double *trace, int trace_cap,
                    void *workspace, size_t workspace_bytes, void *stream);
@@ -171,8 +175,8 @@ int rpe_compose_trajectory_host(const float *rel_host, const float *log_host, in
 typedef enum rpe_corr_precision {
     RPE_CORR_TF32 = 0,     /* one tcgen05 kind::tf32 pass (inputs rounded to tf32)                  */
     RPE_CORR_TF32X3 = 1,   /* split hi/lo: hi*hi + lo*hi + hi*lo, fp32-class accuracy               */
-    RPE_CORR_BF16X3 = 2    /* same split on bf16 planes, full-rate kind::f16 MMAs (16 mantissa bits
-                              per operand, the arithmetic of the bf16x3 convolution trunk)          */
+    RPE_CORR_F16X3 = 2     /* same split on fp16 planes, full-rate kind::f16 MMAs (22 mantissa bits
+                              per operand, the arithmetic of the fp16x3 convolution trunk)          */
 } rpe_corr_precision;
 
 /* Replaces CorrBlock.__init__ / CorrBlock.corr (/root/reference/core/RAFT/core/corr.py:13-27, 52-60):
@@ -185,11 +189,14 @@ size_t rpe_corr_level_offset(int B, int h, int w, int level);
 size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision);
 int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B, int C, int h, int w,
                    int num_levels, int precision, void *workspace, size_t workspace_bytes, void *stream);
-/* The RPE_CORR_BF16X3 build from feature maps that already are NHWC bf16 split planes (B,h,w,C), C % 64 == 0 -- what the
+/* The RPE_CORR_F16X3 build from feature maps that already are NHWC fp16 split planes (B,h,w,C), C % 64 == 0 -- what the
  * feature encoder's last convolution writes: one tcgen05 kernel (CTA pairs, M = 256 queries x N = 16x16 target block) whose
  * epilogue emits level 0 AND the 2x2 / 4x4 / 8x8 mean-pooled levels from the accumulators (corr.py:25-27 avg_pool2d order). */
 int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_hi, const void *f2_lo, float *pyramid, int B, int C,
-                          int h, int w, int num_levels, void *stream);
+                          int h, int w, int num_levels, int f1_wrap, int f1_sub, void *stream);
+/*   Sample s correlates f1 image (s < f1_wrap ? s : s - f1_sub) with f2 image s (f1_wrap <= 0: identity).  The batched tracker
+ *   keeps the features of a chunk as one image list [previous left | left 0..C-1 | right 0..C-1]: with f2 = f1 + one image the
+ *   C temporal pairs (k-1 -> k) and the C stereo pairs (left k -> right k) are the 2C samples of ONE launch (wrap C, sub C-1). */
 
 /* Replaces CorrBlock.__call__ + bilinear_sampler (/root/reference/core/RAFT/core/corr.py:29-50,
  * core/RAFT/core/utils/utils.py:57-71): coords (B,2,h,w) f32 (channel 0 = x) ->
@@ -207,17 +214,17 @@ int rpe_convex_upsample8_nhwc(const float *flow, const float *mask, int mask_ld,
 /* ------------------------------------------------------------------------------------------------
  * "Next" row: the RAFT convolutional trunk on tcgen05 tensor cores.
  * Replaces the convolutions of BasicUpdateBlock (/root/reference/core/RAFT/core/update.py:79-136) and of BasicEncoder
- * (/root/reference/core/RAFT/core/extractor.py:118-192) that the reference runs through cuDNN.  Activations are NHWC bf16 "split" planes (hi = bf16(v), lo = bf16(v - hi));
+ * (/root/reference/core/RAFT/core/extractor.py:118-192) that the reference runs through cuDNN.  Activations are NHWC fp16 "split" planes (hi = fp16(v), lo = fp16(v - hi));
  * a convolution contracts over a list of (activation plane, weight) sources, so concatenated inputs are never
  * materialised and hi*hi + lo*hi + hi*lo reproduces fp32 convolutions to ~1e-5.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rpe_conv_source {
-    const void *act_hi;  /* bf16 NHWC (N,H,W,c_total): hi plane                                       */
-    const void *act_lo;  /* lo plane, or NULL for single-pass bf16 (then w_lo must be NULL too)       */
+    const void *act_hi;  /* fp16 NHWC (N,H,W,c_total): hi plane                                       */
+    const void *act_lo;  /* lo plane, or NULL for single-pass fp16 (then w_lo must be NULL too)       */
     int c_total;         /* channel stride of the activation tensor (multiple of 8)                   */
     int c_offset;        /* first channel read (multiple of 8)                                        */
     int c_count;         /* channels read (multiple of 16); channels past the window read as zero     */
-    const void *w_hi;    /* bf16 [kh*kw][cout_pad][w_cstride], K-major: hi plane                      */
+    const void *w_hi;    /* fp16 [kh*kw][cout_pad][w_cstride], K-major: hi plane                      */
     const void *w_lo;    /* lo plane or NULL                                                          */
     int w_cstride;       /* channel pitch of the weight rows (>= c_count, multiple of 8)              */
 } rpe_conv_source;
@@ -238,7 +245,7 @@ typedef struct rpe_conv_desc {
     float out_scale;     /* applied after the activation                                              */
     float *out_f32;      /* NHWC fp32 output (N,OH,OW,f32_ld) at channel f32_offset, or NULL          */
     int f32_ld, f32_offset;
-    void *out_hi, *out_lo; /* NHWC bf16 planes (N,OH,OW,bf_ld) at channel bf_offset; out_lo may be NULL */
+    void *out_hi, *out_lo; /* NHWC fp16 planes (N,OH,OW,bf_ld) at channel bf_offset; out_lo may be NULL */
     int bf_ld, bf_offset;
     /* fused SepConvGRU epilogues (update.py:45-60); 0 = plain epilogue.
      *   mode 1 (z|r gates, activation sigmoid, cout = 2*hidden): z = out[:hidden] -> out_f32, planes <- r * h  (h = aux)
@@ -256,6 +263,10 @@ typedef struct rpe_conv_desc {
      * fp32 [N * tiles_per_image * 4][cout_pad][2] = (sum, sum of squares) of the outputs of 32 pixels each; slots of pixels
      * outside the image hold zeros.  rpe_instnorm_stats_from_partials reduces them (extractor.py:23-56 nn.InstanceNorm2d). */
     float *stat_partials;
+    /* The accumulators are multiplied by acc_scale before the bias is added (0 = 1).  Weights are packed pre-multiplied by the
+     * inverse, a power of two chosen so that their fp16 lo plane is a normal number (|w| >= 2^-3): exact, and it keeps ~22
+     * significant bits on small weights. */
+    float acc_scale;
 } rpe_conv_desc;
 
 int rpe_conv_plan_create(const rpe_conv_desc *desc, void **plan_out);   /* encodes the TMA descriptors once */
@@ -264,8 +275,8 @@ int rpe_conv_plan_tiles_per_image(void *plan); /* 128-pixel tiles per image (4 s
 double rpe_conv_plan_flops(void *plan);      /* tensor-core flops of one run (x3 for the split arithmetic) */
 int rpe_conv_plan_destroy(void *plan);
 
-/* CorrBlock.__call__ writing the NHWC bf16 split planes the first motion-encoder convolution reads (ld >= 324). */
-int rpe_corr_lookup_nhwc_bf16(const float *pyramid, const float *coords, void *out_hi, void *out_lo, int ld, int B, int h, int w,
+/* CorrBlock.__call__ writing the NHWC fp16 split planes the first motion-encoder convolution reads (ld >= 324). */
+int rpe_corr_lookup_nhwc_split(const float *pyramid, const float *coords, void *out_hi, void *out_lo, int ld, int B, int h, int w,
                               int num_levels, int radius, void *stream);
 /* Layout / split helpers and the element-wise pieces of the update operator (update.py:45-60, raft.py:112-121). */
 int rpe_nchw_to_nhwc_split(const float *x, void *hi, void *lo, float *f32, int n, int C, int H, int W, int ld, int off,
@@ -279,11 +290,11 @@ int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *
 
 /* Encoder companions (reference: /root/reference/core/RAFT/core/extractor.py:118-192, raft.py:82-83).
  * rpe_im2col7s2_split: 7x7 / stride 2 / pad 3 windows of the normalised image 2*(v/255)-1 as the K axis of a 1x1 convolution,
- *   k = ky*24 + kx*3 + c (168 of `ld` = 176 channels, the last 8 written as zeros); img NCHW fp32 (n,3,H,W) -> bf16 split
+ *   k = ky*24 + kx*3 + c (168 of `ld` = 176 channels, the last 8 written as zeros); img NCHW fp32 (n,3,H,W) -> fp16 split
  *   planes (n, H/2, W/2, 176).
  * rpe_instnorm_stats: InstanceNorm2d statistics (biased variance) of an NHWC fp32 tensor (n,HW,C): stats (n,C,2) = mean, rstd.
  * rpe_norm_act_split: y = [relu]((a - mean_a) * rstd_a), optionally y = relu(y + (b - mean_b) * rstd_b) (stats may be NULL =
- *   identity); writes fp32 NHWC and / or bf16 split planes with channel pitch ld. */
+ *   identity); writes fp32 NHWC and / or fp16 split planes with channel pitch ld. */
 int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream);
 size_t rpe_instnorm_workspace_bytes(int n, int C);
 int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float eps, void *workspace, size_t workspace_bytes,
@@ -294,6 +305,27 @@ int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n,
                                      void *workspace, size_t workspace_bytes, void *stream);   /* rpe_instnorm_workspace_bytes(n, C) */
 int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
                        void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * "Next" row: the confidence heads (TinyUNet, /root/reference/core/unet/unet.py:8-82, wrapped with Sigmoid at
+ * core/pose/pose_net.py:24-27) on the convolution plans above.  Each un-padded 3x3 convolution runs as a "same" convolution on
+ * its input grid and the reference's result is the interior (the VALID REGION: origin + size inside the grid); these kernels
+ * carry data between the grids.  All fp32 tensors NHWC with channel pitch ld; outputs fp16 split planes unless noted.
+ *   rpe_downsample8_planes  pose_net.py:110-113 F.interpolate(scale_factor=0.125, 'bilinear') of up to three NCHW fp32 tensors,
+ *                           concatenated at channel ch_offset of planes (n, H/8, W/8, ld)
+ *   rpe_pool2_planes        F.max_pool2d(x, 2) of the valid region (y0, x0, 2 oh, 2 ow) of channels [c_in_off, c_in_off + C)
+ *   rpe_upcat_planes        torch.cat((ConvTranspose2d(k=2, s=2)(x), centre_crop(skip)), 1) (unet.py:52-61): `up` holds the
+ *                           transposed convolution as 4 groups of c_up channels, group dy * 2 + dx, valid origin (uy0, ux0)
+ *   rpe_resize_sigmoid      sigmoid(F.interpolate(logits, (H, W), mode='bilinear')) of channel ch of the valid region
+ *                           (y0, x0, ih, iw) -> out (n,1,H,W) fp32 */
+int rpe_downsample8_planes(const float *src0, int c0, const float *src1, int c1, const float *src2, int c2, void *out_hi, void *out_lo,
+                           int ld, int ch_offset, int n, int H, int W, void *stream);
+int rpe_pool2_planes(const float *x, int H, int W, int ld_in, int c_in_off, int y0, int x0, void *out_hi, void *out_lo, int oh, int ow,
+                     int ld_out, int C, int n, void *stream);
+int rpe_upcat_planes(const float *up, int Hu, int Wu, int ld_u, int uy0, int ux0, int c_up, const float *skip, int Hk, int Wk, int ld_k,
+                     int k_off, int ky0, int kx0, int c_skip, void *out_hi, void *out_lo, int oh, int ow, int ld_out, int n, void *stream);
+int rpe_resize_sigmoid(const float *logits, int Hl, int Wl, int ld, int ch, int y0, int x0, int ih, int iw, float *out, int n, int H, int W,
+                       void *stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ _lib = None
 
 POSE_OUT_STRIDE = 64
 SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = 0, 1, 2
-CORR_TF32, CORR_TF32X3, CORR_BF16X3 = 0, 1, 2
+CORR_TF32, CORR_TF32X3, CORR_F16X3 = 0, 1, 2
 
 
 class RpeError(RuntimeError):
@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
                 ("activation", C.c_int), ("out_scale", C.c_float), ("out_f32", C.c_void_p), ("f32_ld", C.c_int),
                 ("f32_offset", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("bf_ld", C.c_int),
                 ("bf_offset", C.c_int), ("mode", C.c_int), ("aux", C.c_void_p), ("aux_ld", C.c_int), ("aux2", C.c_void_p),
-                ("aux2_ld", C.c_int), ("stat_partials", C.c_void_p)]
+                ("aux2_ld", C.c_int), ("stat_partials", C.c_void_p), ("acc_scale", C.c_float)]
 
 
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -54,13 +54,14 @@ SIGNATURES = {
     "rpe_downsample8_cat": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_pose_workspace_bytes": (_Z, [_I]),
     "rpe_pose_set_groups": (_I, [_I]),
+    "rpe_pose_set_group_size": (_I, [_I]),
     "rpe_pose_solve": (_I, [C.POINTER(PoseProblem), _I, _I, _I, _P, _P, _P, _P, _I, _P, _Z, _P]),
     "rpe_compose_trajectory_host": (_I, [_P, _P, _I, _P, _F, _P, _P]),
     "rpe_corr_pyramid_bytes": (_Z, [_I, _I, _I, _I]),
     "rpe_corr_level_offset": (_Z, [_I, _I, _I, _I]),
     "rpe_corr_workspace_bytes": (_Z, [_I, _I, _I, _I, _I]),
     "rpe_corr_build": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _Z, _P]),
-    "rpe_corr_build_planes": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_corr_build_planes": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_corr_lookup": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_convex_upsample8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "rpe_convex_upsample8_nhwc": (_I, [_P, _P, _I, _P, _I, _I, _I, _P]),
@@ -70,7 +71,7 @@ SIGNATURES = {
     "rpe_conv_plan_tiles_per_image": (_I, [_P]),
     "rpe_instnorm_stats_from_partials": (_I, [_P, _P, _I, _I, _I, _I, _I, _F, _P, _Z, _P]),
     "rpe_conv_plan_destroy": (_I, [_P]),
-    "rpe_corr_lookup_nhwc_bf16": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "rpe_corr_lookup_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_nchw_to_nhwc_split": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_nhwc_to_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_flow_step": (_I, [_P, _P, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
@@ -79,6 +80,10 @@ SIGNATURES = {
     "rpe_instnorm_stats": (_I, [_P, _P, _I, _I, _I, _F, _P, _Z, _P]),
     "rpe_norm_act_split": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_tap_gather3x3": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "rpe_downsample8_planes": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_pool2_planes": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_upcat_planes": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
+    "rpe_resize_sigmoid": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "rpe_gru_gate": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_longlong, _I, _P]),
 }
 

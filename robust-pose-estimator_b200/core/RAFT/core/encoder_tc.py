@@ -1,7 +1,7 @@
 """RAFT feature / context encoders on the tcgen05 convolution kernels (csrc/conv.cu, csrc/encoder_ops.cu).
 
 Same arithmetic graph as ``extractor.encoder_forward`` (reference: /root/reference/core/RAFT/core/extractor.py:118-192
-``BasicEncoder``, :6-56 ``ResidualBlock``) with every convolution evaluated as an error-compensated bf16x3 implicit GEMM:
+``BasicEncoder``, :6-56 ``ResidualBlock``) with every convolution evaluated as an error-compensated fp16x3 implicit GEMM:
   * the 7x7 / 2 stem is a 1x1 convolution over an im2col of the normalised image (rpe_im2col7s2_split);
   * stride-2 convolutions read their input through strided TMA boxes;
   * fnet (InstanceNorm2d): convolution -> raw fp32, rpe_instnorm_stats, rpe_norm_act_split (normalise / relu / residual);
@@ -65,8 +65,12 @@ class EncoderTC:
         return self._packed[key]
 
     # ---- per-shape state -------------------------------------------------------------------------------
-    def _state(self, n, H, W, device, shared_col=None):
-        key = (n, H, W, device.index, None if shared_col is None else shared_col.hi.data_ptr())
+    def _state(self, n, H, W, device, shared_col=None, dests=None):
+        """dests: per output head a dict(out_f32=fp32 NHWC tensor or None, out_planes=Planes or None) the head convolution writes
+        to directly (the batched tracker points them into the correlation / update-operator buffers); default: own fp32 tensors."""
+        dkey = None if dests is None else tuple((None if d.get("out_f32") is None else d["out_f32"].data_ptr(),
+                                                 None if d.get("out_planes") is None else d["out_planes"].hi.data_ptr()) for d in dests)
+        key = (n, H, W, device.index, None if shared_col is None else shared_col.hi.data_ptr(), dkey)
         st = self._shapes.get(key)
         if st is not None:
             return st
@@ -163,10 +167,15 @@ class EncoderTC:
                 cin = dim
         # ---- output heads (slices of the final 1x1 convolution)
         outs = []
-        for c_lo, c_hi, act in self.heads:
-            o = f32(h, w, c_hi - c_lo)
+        for k, (c_lo, c_hi, act) in enumerate(self.heads):
             (wts, bias) = self._wb("conv2", None, c_lo, c_hi)
-            plan = ConvPlan(self.prefix + "conv2", [(xp, 0, 128, wts)], (n, h, w), 1, 1, c_hi - c_lo, act, bias=bias, out_f32=o)
+            if dests is None:
+                o = f32(h, w, c_hi - c_lo)
+                plan = ConvPlan(self.prefix + "conv2", [(xp, 0, 128, wts)], (n, h, w), 1, 1, c_hi - c_lo, act, bias=bias, out_f32=o)
+            else:
+                o = None
+                plan = ConvPlan(self.prefix + "conv2", [(xp, 0, 128, wts)], (n, h, w), 1, 1, c_hi - c_lo, act, bias=bias,
+                                out_f32=dests[k].get("out_f32"), out_planes=dests[k].get("out_planes"))
             st["steps"].append(("conv", plan))
             outs.append(o)
         st["outs"] = outs
@@ -175,12 +184,12 @@ class EncoderTC:
         return st
 
     # ---- execution ---------------------------------------------------------------------------------------
-    def forward(self, images, col=None):
+    def forward(self, images, col=None, dests=None):
         """images (n,3,H,W) fp32 in 0..255 -> list of fp32 NHWC outputs, one per head (buffers reused by the next call).
         ``col``: already filled im2col planes from ``stem_planes`` whose first n images are these images (the context encoder
-        reads the same left images as the feature encoder); the plans are then bound to that buffer."""
+        reads the same left images as the feature encoder); the plans are then bound to that buffer.  ``dests``: see ``_state``."""
         n, _, H, W = images.shape
-        st = self._state(n, H, W, images.device, col)
+        st = self._state(n, H, W, images.device, col, dests)
         l = _lib.lib()
         s = _stream()
         if col is None:

@@ -1,7 +1,7 @@
 """RAFT update operator on the tcgen05 convolution kernels (csrc/conv.cu, csrc/update_ops.cu).
 
 Same arithmetic graph as ``update.update_forward`` (reference: /root/reference/core/RAFT/core/update.py:79-136 and the
-loop body of core/RAFT/core/raft.py:112-132) with every convolution evaluated as an error-compensated bf16x3 implicit
+loop body of core/RAFT/core/raft.py:112-132) with every convolution evaluated as an error-compensated fp16x3 implicit
 GEMM on the tensor cores, NHWC activations, no materialised concatenations and the whole 12-iteration loop resident in
 pre-allocated device buffers (one set per batch shape)."""
 import os
@@ -12,7 +12,7 @@ from .... import _lib, ops
 from ....ops import _p, _stream, _timed, check
 from ....tc import ConvPlan, Planes, pack_weight
 
-_Planes, _pack_weight = Planes, pack_weight          # (names used by ops.conv2d_bf16x3)
+_Planes, _pack_weight = Planes, pack_weight          # (names used by ops.conv2d_f16x3)
 
 
 class UpdateTC:
@@ -84,11 +84,11 @@ class UpdateTC:
         if self.fused_flow_head:
             # FlowHead (update.py:6-13): conv2 has 2 output channels -> its per-pixel part (18 dot products of length 256) runs in
             # fp32 inside conv1's epilogue (conv.cu mode 3) and rpe_tap_gather3x3 adds the nine shifted maps; relu(conv1) is never stored
-            key = ("fh2_proj",)
-            if key not in self._packed:
-                self._packed[key] = W[pre + "flow_head.conv2.weight"].float().permute(1, 2, 3, 0).reshape(256, 18).contiguous()
+            pkey = ("fh2_proj",)          # (NOT `key`: that is the shape key this state is cached under)
+            if pkey not in self._packed:
+                self._packed[pkey] = W[pre + "flow_head.conv2.weight"].float().permute(1, 2, 3, 0).reshape(256, 18).contiguous()
             pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_f32=st["fpart"], mode=3,
-                                   aux2=self._packed[key])
+                                   aux2=self._packed[pkey])
         else:
             pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["fh"])
             pl["fh2"] = self._plan(st, "flow_head.conv2", [(st["fh"], 0, 256, 0)], 3, 3, 2, "none", out_f32=st["delta"])
@@ -110,16 +110,34 @@ class UpdateTC:
         st = self._state(B, h, w, dev)
         l = _lib.lib()
         s = _stream()
-        npix = B * h * w
-        # initial state: h (fp32 + planes), inp planes + its gate contributions, coords1 = grid (+ flow_init)
+        # initial state: h (fp32 + planes), inp planes
         check(l.rpe_nchw_to_nhwc_split(_p(net.float().contiguous()), _p(st["hp"].hi), _p(st["hp"].lo), _p(st["h"]), B, 128, h, w, 128, 0,
                                        128, 0, s), "rpe_nchw_to_nhwc_split")
         check(l.rpe_nchw_to_nhwc_split(_p(inp.float().contiguous()), _p(st["inp"].hi), _p(st["inp"].lo), None, B, 128, h, w, 128, 0, 0, 0, s),
               "rpe_nchw_to_nhwc_split")
+        flow_up, flow_lo = self.refine_state(corr_pyr, B, h, w, dev, iters, flow_init, want_mask)
+        net_out = torch.empty((B, 128, h, w), dtype=torch.float32, device=dev)
+        check(l.rpe_nhwc_to_nchw(_p(st["h"]), _p(net_out), B, 128, h, w, 128, 0, s), "rpe_nhwc_to_nchw")
+        return flow_up, net_out, flow_lo
+
+    def state(self, B, h, w, device):
+        """The per-shape buffers: 'h' (fp32 NHWC hidden state), 'hp' / 'inp' (split planes of the hidden state / the context
+        input) are what the encoders of the batched tracker write into before ``refine_state``."""
+        return self._state(B, h, w, device)
+
+    def refine_state(self, corr_pyr, B, h, w, dev, iters=12, flow_init=None, want_mask=True):
+        """The refinement loop on state buffers that already hold tanh(net) ('h', 'hp') and relu(inp) ('inp') of the B samples.
+        The final hidden state stays in 'h' / 'hp'.  -> (flow_up (B,2,8h,8w) or None, flow_lo (B,2,h,w))."""
+        st = self._state(B, h, w, dev)
+        l = _lib.lib()
+        s = _stream()
+        # gate contributions of the (constant) context input, coords1 = grid (+ flow_init)
         for name in ("pzr1", "pq1", "pzr2", "pq2"):
             self._run(st, name)
-        ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
-        grid = torch.stack((xs, ys), 0).float()
+        if "grid" not in st:
+            ys, xs = torch.meshgrid(torch.arange(h, device=dev), torch.arange(w, device=dev), indexing="ij")
+            st["grid"] = torch.stack((xs, ys), 0).float()
+        grid = st["grid"]
         st["coords1"].copy_(grid[None].expand(B, 2, h, w) if flow_init is None else grid[None] + flow_init)
         coords1 = st["coords1"]
         for it in range(iters):
@@ -147,6 +165,4 @@ class UpdateTC:
             with _timed("convex_upsample8", B):
                 check(l.rpe_convex_upsample8_nhwc(_p(flow_lo.contiguous()), _p(st["mask"]), 576, _p(flow_up), B, h, w, s),
                       "rpe_convex_upsample8_nhwc")
-        net_out = torch.empty((B, 128, h, w), dtype=torch.float32, device=dev)
-        check(l.rpe_nhwc_to_nchw(_p(st["h"]), _p(net_out), B, 128, h, w, 128, 0, s), "rpe_nhwc_to_nchw")
-        return flow_up, net_out, flow_lo
+        return flow_up, flow_lo

@@ -21,7 +21,7 @@ class PoseEstimator(torch.nn.Module):
     def __init__(self, config, intrinsics, baseline, checkpoint, img_shape, init_pose=None):
         """
         :param config: the ``slam`` section of configuration/infer_f2f.yaml (+ optional keys
-                       ``precision`` fp32|bf16x3|tf32|bf16|fp16, ``solver`` lbfgs_ref|gn, ``residuals`` 2d3d|3d|2d,
+                       ``precision`` fp32|fp16x3|tf32|bf16|fp16, ``solver`` lbfgs_ref|gn, ``residuals`` 2d3d|3d|2d,
                        ``sync_guard``, ``cuda_graph``: replay the whole per-frame device work of ``forward`` as one CUDA
                        graph -- the latency path; ``flow`` / ``weights`` are then not returned)
         :param intrinsics: rectified camera intrinsics (3,3)

@@ -1,5 +1,5 @@
 """PoseNet with the reference's interface (/root/reference/core/pose/pose_net.py:13-164) on the
-B200-native path: RAFT trunk (tcgen05 convolution kernels with precision 'bf16x3', a cuDNN trunk otherwise),
+B200-native path: RAFT trunk (tcgen05 convolution kernels with precision 'fp16x3', a cuDNN trunk otherwise),
 correlation / lookup / up-sampling, stereo-depth lifting, back-projection, flow warping, the 1/8 down-sampling and
 the SE(3) solve as sm_100a kernels; only the two small confidence heads run through cuDNN.
 
@@ -14,6 +14,7 @@ from ... import ops
 from ...lie import SE3
 from ..RAFT.core.raft import RAFT
 from ..unet.unet import tiny_unet_entries, tiny_unet_forward
+from ..unet.unet_tc import HeadsTC
 from ..utils.param_tree import ParamTree, build_tree
 from .pose_head import DeclarativeLayerLie, DPoseSE3Head
 
@@ -34,16 +35,20 @@ class PoseNet(nn.Module):
         self.weight_head_3d = ParamTree()
         self.weight_head_3d.add_module("0", build_tree(tiny_unet_entries("", 128 + 128 + 8 + 8)))
         self._Wh = None
+        self._heads_tc = None
+        self._head_planes = {}
 
     # ---- parameter plumbing ------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):
-        self._Wh = None
+        self._Wh = self._heads_tc = None
+        self._head_planes = {}
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         sd = OrderedDict((k.replace("module.", ""), v) for k, v in state_dict.items())
         out = super().load_state_dict(sd, strict=strict, **kw)
-        self._Wh = None
+        self._Wh = self._heads_tc = None
+        self._head_planes = {}
         self.flow.invalidate()          # nn.Module.load_state_dict does not call the child's override: drop every packed-weight cache
         return out
 
@@ -73,11 +78,31 @@ class PoseNet(nn.Module):
         return depth, flow, valid
 
     def get_weight_maps(self, pcl1, pcl2, image1l, image2l, mask2, time_flow, stereo_flow1, stereo_flow2,
-                        gru_hidden_state, context):
-        """-> conf1, conf2, pcl2 warped, mask2 warped   (pose_net.py:102-119)."""
+                        gru_hidden_state, context, state_planes=None):
+        """-> conf1, conf2, pcl2 warped, mask2 warped   (pose_net.py:102-119).  ``state_planes``: (gru, ctx) as the update
+        operator's NHWC split planes (batched engine); then ``gru_hidden_state`` / ``context`` may be None."""
         pcl2w, img2w, sflow2w, mask2w = ops.warp8_mask(pcl2, image2l.float().contiguous(), stereo_flow2,
                                                        mask2.bool().contiguous(), time_flow)
-        if self.use_weights:
+        if self.use_weights and self.flow.precision == "fp16x3":
+            # both TinyUNets on the tcgen05 convolution kernels (core/unet/unet_tc.py); the 264 / 272-channel inputs are never
+            # assembled: the first convolution reads the down-sampled geometry, the GRU state and the context as separate sources
+            n = pcl1.shape[0]
+            if self._heads_tc is None:
+                self._heads_tc = HeadsTC(self._head_weights())
+            if state_planes is not None:
+                gru_p, ctx_p = state_planes               # the update operator's own planes (first n samples), read in place
+            else:
+                from ...tc import Planes, nchw_to_planes
+                h8, w8 = gru_hidden_state.shape[-2:]
+                key = (n, h8, w8, pcl1.device.index)
+                if key not in self._head_planes:
+                    self._head_planes[key] = (Planes(n, h8, w8, 128, pcl1.device), Planes(n, h8, w8, 128, pcl1.device))
+                gru_p, ctx_p = self._head_planes[key]
+                nchw_to_planes(gru_hidden_state.float().contiguous(), gru_p)
+                nchw_to_planes(context.float().contiguous(), ctx_p)
+            conf1, conf2 = self._heads_tc.forward([stereo_flow1.float().contiguous(), image1l.float().contiguous(), pcl1],
+                                                  [sflow2w, img2w, pcl2w], gru_p, ctx_p, n, self.image_shape)
+        elif self.use_weights:
             n = pcl1.shape[0]
             H, W = self.image_shape
             h8, w8 = H // 8, W // 8
@@ -90,7 +115,7 @@ class PoseNet(nn.Module):
             x2 = torch.cat((x3[:, :8], x3[:, 16:]), 1)
             W_ = self._head_weights()
             with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False,
-                                            allow_tf32=self.flow.precision not in ("fp32", "bf16x3")):
+                                            allow_tf32=self.flow.precision not in ("fp32", "fp16x3")):
                 conf1 = torch.sigmoid(tiny_unet_forward(x2, W_, "weight_head_2d.0.", (H, W)))
                 conf2 = torch.sigmoid(tiny_unet_forward(x3, W_, "weight_head_3d.0.", (H, W)))
         else:

@@ -5,9 +5,9 @@
 //   v[n, y, x, co]   = bias[co] + pre[n, y, x, co] + sum_s sum_(ky,kx) sum_ci  A_s[n, y*st+ky-ph, x*st+kx-pw, ci] * W_s[ky*kw+kx][co][ci]
 //   out[n, y, x, co] = act(v) * scale                       (then  out = relu(out + res[n, y, x, co])  when a residual is given)
 //
-// Activations are NHWC bf16 planes.  The contraction runs over a LIST of sources (activation tensor + its weight slice), so
-// concatenated inputs are never materialised, and every source may carry two planes hi = bf16(v), lo = bf16(v - hi): the
-// "bf16x3" arithmetic evaluates hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (16 mantissa bits per operand; measured
+// Activations are NHWC fp16 planes.  The contraction runs over a LIST of sources (activation tensor + its weight slice), so
+// concatenated inputs are never materialised, and every source may carry two planes hi = fp16(v), lo = fp16(v - hi): the
+// "fp16x3" arithmetic evaluates hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (22 mantissa bits per operand; measured
 // deviation from fp32 convolutions ~1e-5 relative).  Stride 1 or 2, "same"-style zero padding (k/2).
 //
 // Kernel: persistent, warp-specialised.  The output tile is 128 pixels = 16 (major) x 8 (minor) positions of one image; `orient`
@@ -20,11 +20,11 @@
 // activation TMA producer, warp 3 = weight TMA producer, warp 1 = tcgen05.mma issuer (the whole warp walks the loop nest so that
 // descriptors live in uniform registers; MMAs / commits are predicated on one elected lane), warp 2 = TMEM allocator, warps
 // 4-11 = epilogue (tcgen05.ld -> smem transposition -> bias / addend / activation / residual / GRU arithmetic -> coalesced fp32
-// and/or bf16 hi/lo NHWC stores) overlapped with the next tile through two TMEM accumulator stages.  CTA pairs (cta_group::2)
+// and/or fp16 hi/lo NHWC stores) overlapped with the next tile through two TMEM accumulator stages.  CTA pairs (cta_group::2)
 // share every weight tile.  The kernel is instantiated once per epilogue KIND (kK* below) so that each instance carries only
 // the code of the tensors it touches: the epilogue warps share issue slots with the MMA issuer and the instruction cache with
 // both producers (profiles/README.md: the issuer, not the tensor pipe, was the bottleneck of the first version).
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cudaTypedefs.h>
 #include <math.h>
 #include <stdlib.h>
@@ -42,7 +42,7 @@ namespace rpe {
 #define RPE_CV_DBG(P) 0
 #endif
 
-constexpr int kCvBK = 64;                             // bf16 channels per K block (one 128-byte swizzle row)
+constexpr int kCvBK = 64;                             // fp16 channels per K block (one 128-byte swizzle row)
 constexpr int kCvAcc = 2;                             // TMEM accumulator stages
 constexpr int kCvEpiWarps = 8;                        // 2 per SM sub-partition: column halves of the same TMEM lanes
 constexpr int kCvThreads = 128 + 32 * kCvEpiWarps;
@@ -76,9 +76,10 @@ struct alignas(64) ConvParams {
     int res_ld;
     int act;
     float scale;
+    float acc_scale;                                  // accumulators are multiplied by this first (weights packed pre-scaled by its inverse)
     float *out_f32;
     int f32_ld, f32_off;
-    __nv_bfloat16 *out_hi, *out_lo;
+    plane_t *out_hi, *out_lo;
     int bf_ld, bf_off;
     int mode;                                         // 0 plain, 1 GRU z|r gates, 2 GRU candidate + state update
     float *aux;                                       // mode 1/2: hidden state h (fp32 NHWC, updated in place by mode 2)
@@ -92,6 +93,7 @@ struct alignas(64) ConvParams {
     float *corr_lvl[4];
     int corr_h, corr_w, corr_nbx, corr_levels;
     int corr_vec;                                     // bit l: level l rows may be written with vector stores
+    int corr_a_wrap, corr_a_sub;                      // query-side image of sample s: s < wrap ? s : s - sub (target side: image s)
 };
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -101,7 +103,7 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         : "memory");
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -136,18 +138,17 @@ __device__ __forceinline__ float cv_tanh_fast(float v) { return 1.0f - __fdivide
 //     level 0 and derives the 2x2 / 4x4 / 8x8 mean-pooled levels of the pyramid from the accumulators in registers
 constexpr int kKGeneric = 0, kKGates = 1, kKState = 2, kKProj = 3, kKPlanes = 4, kKF32 = 5, kKF32Stats = 6, kKCorr = 7;
 
-// fp32 x4 -> bf16 hi / lo planes (hi = bf16(v), lo = bf16(v - hi)), packed conversions
+// fp32 x4 -> fp16 hi / lo planes (hi = fp16(v), lo = fp16(v - hi)), packed saturating conversions
 template <bool kLo>
-__device__ __forceinline__ void cv_store_bf16x4(const ConvParams &P, uint32_t o, const float *v) {
-    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+__device__ __forceinline__ void cv_store_split4(const ConvParams &P, uint32_t o, const float *v) {
+    const plane2_t h01 = to_plane2(v[0], v[1]), h23 = to_plane2(v[2], v[3]);
     uint2 hv;
     hv.x = *reinterpret_cast<const uint32_t *>(&h01);
     hv.y = *reinterpret_cast<const uint32_t *>(&h23);
     *reinterpret_cast<uint2 *>(P.out_hi + o) = hv;
     if (kLo) {
-        const float r0 = v[0] - __uint_as_float(hv.x << 16), r1 = v[1] - __uint_as_float(hv.x & 0xffff0000u);
-        const float r2 = v[2] - __uint_as_float(hv.y << 16), r3 = v[3] - __uint_as_float(hv.y & 0xffff0000u);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(r0, r1), l23 = __floats2bfloat162_rn(r2, r3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const plane2_t l01 = to_plane2_lo(v[0] - f01.x, v[1] - f01.y), l23 = to_plane2_lo(v[2] - f23.x, v[3] - f23.y);
         uint2 lv;
         lv.x = *reinterpret_cast<const uint32_t *>(&l01);
         lv.y = *reinterpret_cast<const uint32_t *>(&l23);
@@ -160,15 +161,15 @@ __device__ __noinline__ void cv_epilogue_tail(const ConvParams &P, int act, floa
                                               uint32_t pix) {
     const float acc[3] = {a0, a1, a2};
     for (int k = 0; k < 3 && co + k < P.cout; ++k) {
-        float r = acc[k] + sbias[co + k];
+        float r = fmaf(acc[k], P.acc_scale, sbias[co + k]);
         if (P.pre) r += __ldg(P.pre + (size_t)pix * P.pre_ld + co + k);
         r = cv_activate_rt(r, act) * P.scale;
         if (P.res) r = fmaxf(r + __ldg(P.res + (size_t)pix * P.res_ld + co + k), 0.0f);
         if (P.out_f32) P.out_f32[(size_t)pix * P.f32_ld + P.f32_off + co + k] = r;
         if (P.out_hi) {
-            const __nv_bfloat16 h = __float2bfloat16_rn(r);
+            const plane_t h = to_plane(r);
             P.out_hi[(size_t)pix * P.bf_ld + P.bf_off + co + k] = h;
-            if (P.out_lo) P.out_lo[(size_t)pix * P.bf_ld + P.bf_off + co + k] = __float2bfloat16_rn(r - __bfloat162float(h));
+            if (P.out_lo) P.out_lo[(size_t)pix * P.bf_ld + P.bf_off + co + k] = to_plane_lo(r - plane_to_float(h));
         }
     }
 }
@@ -205,7 +206,7 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
     if (co >= P.cout) return;
     float o[4];
     if (co + 3 < P.cout) {
-        o[0] = acc.x + b.x, o[1] = acc.y + b.y, o[2] = acc.z + b.z, o[3] = acc.w + b.w;
+        o[0] = fmaf(acc.x, P.acc_scale, b.x), o[1] = fmaf(acc.y, P.acc_scale, b.y), o[2] = fmaf(acc.z, P.acc_scale, b.z), o[3] = fmaf(acc.w, P.acc_scale, b.w);
         if (kK == kKGates || kK == kKState || (kK == kKGeneric && P.pre)) o[0] += sd.pre.x, o[1] += sd.pre.y, o[2] += sd.pre.z, o[3] += sd.pre.w;
         // GRU kinds fix the activation (z|r: sigmoid, q: tanh) and use the hardware exponential / reciprocal (abs. error
         // < 5e-7, far below the 2^-16 of the split operands); planes / fp32 kinds only know relu / none (checked by the plan)
@@ -236,11 +237,11 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
             }
             if (P.out_f32) *reinterpret_cast<float4 *>(P.out_f32 + (pix * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
             if (P.out_hi) {
-                if (P.out_lo) cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
-                else cv_store_bf16x4<false>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+                if (P.out_lo) cv_store_split4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+                else cv_store_split4<false>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
             }
         } else if (kK == kKPlanes) {
-            cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+            cv_store_split4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
         } else if (kK == kKF32) {
             *reinterpret_cast<float4 *>(P.out_f32 + (pix * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
         } else if (kK == kKGates) {
@@ -250,7 +251,7 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
                 *reinterpret_cast<float4 *>(P.out_f32 + (pix * (uint32_t)P.f32_ld + P.f32_off + co)) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
                 o[0] *= sd.a.x, o[1] *= sd.a.y, o[2] *= sd.a.z, o[3] *= sd.a.w;
-                cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + (co - half), o);
+                cv_store_split4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + (co - half), o);
             }
         } else {
             // candidate state q = tanh(.) and the state update h = (1 - z) * h + z * q, fp32 in place + planes
@@ -259,7 +260,7 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
             o[2] = (1.0f - sd.z.z) * sd.a.z + sd.z.z * o[2];
             o[3] = (1.0f - sd.z.w) * sd.a.w + sd.z.w * o[3];
             *reinterpret_cast<float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co)) = make_float4(o[0], o[1], o[2], o[3]);
-            cv_store_bf16x4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
+            cv_store_split4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
         }
     } else if (kK == kKGeneric || kK == kKPlanes || kK == kKF32) {      // ragged tail of a channel count that is not a multiple of 4
         cv_epilogue_tail(P, P.act, acc.x, acc.y, acc.z, sbias, co, pix);
@@ -304,7 +305,7 @@ __device__ __forceinline__ void cv_epilogue_half_stats(const ConvParams &P, cons
         const int r = it * 8 + (lane >> 2);
         const float4 acc = *reinterpret_cast<const float4 *>(stage + r * 16 + (((lane & 3) ^ ((r >> 1) & 3)) << 2));
         if (((inside_mask >> it) & 1u) && co < P.cout) {
-            float o[4] = {acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w};
+            float o[4] = {fmaf(acc.x, P.acc_scale, b.x), fmaf(acc.y, P.acc_scale, b.y), fmaf(acc.z, P.acc_scale, b.z), fmaf(acc.w, P.acc_scale, b.w)};
             if (P.act == 1) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) o[k] = fmaxf(o[k], 0.0f);
@@ -339,7 +340,7 @@ __device__ __forceinline__ void cv_project_chunk(const ConvParams &P, const uint
                                                  float *acc) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-        const float y = cv_activate_rt(__uint_as_float(v[j]) + sbias[co + j], P.act) * P.scale;
+        const float y = cv_activate_rt(fmaf(__uint_as_float(v[j]), P.acc_scale, sbias[co + j]), P.act) * P.scale;
         const float2 *w = reinterpret_cast<const float2 *>(w2s + (co + j) * kCvProj);
 #pragma unroll
         for (int k = 0; k < kCvProj / 2; ++k) {
@@ -483,7 +484,7 @@ __device__ __forceinline__ void cv_mma(uint32_t tmem_d, uint64_t desc_a, uint64_
             ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
             : "memory");
     } else {
-        umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+        umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
     }
 }
 // ---- issuer-side helpers on raw shared-memory addresses (no generic-pointer arithmetic on the critical path) ----
@@ -652,12 +653,13 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                 const int cmin = t.omin0 * P.stride + tm - P.pad_min;
                                 const int cmaj = t.omaj0 * P.stride + (P.reuse ? 0 : au) - P.pad_maj;
                                 uint8_t *dst = sA + (size_t)stage * P.a_stage_bytes;
+                                const int img_a = (kK == kKCorr && t.img >= P.corr_a_wrap) ? t.img - P.corr_a_sub : t.img;
                                 for (int p = 0; p < P.n_planes; ++p) {
                                     if (kPair)
                                         tma_load_4d_pair(dst + p * P.a_plane_bytes, &P.amap[s][p], mapa_shared(smem_u32(&a_full[stage]), 0),
-                                                         cb * kCvBK, cmin, cmaj, t.img);
+                                                         cb * kCvBK, cmin, cmaj, img_a);
                                     else
-                                        tma_load_4d(dst + p * P.a_plane_bytes, &P.amap[s][p], &a_full[stage], cb * kCvBK, cmin, cmaj, t.img);
+                                        tma_load_4d(dst + p * P.a_plane_bytes, &P.amap[s][p], &a_full[stage], cb * kCvBK, cmin, cmaj, img_a);
                                 }
                                 if (++stage == P.n_a_stages) stage = 0, phase ^= 1;
                             }
@@ -724,8 +726,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         // registers, which is where tcgen05.mma takes its descriptors from); only the MMAs and commits are predicated on one
         // elected lane.  The issuer's instruction stream is the critical path of the kernel: one 128-cycle MMA per ~20 issue slots.
         const bool leader = elect_one();
-        // instruction descriptor: D fp32, A/B bf16, both K-major, N = bn, M = 128 (256 across a CTA pair)
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.bn >> 3) << 17) |
+        // instruction descriptor: D fp32 (c_format 1), A/B fp16 (a/b_format 0), both K-major, N = bn, M = 128 (256 across a CTA pair)
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(P.bn >> 3) << 17) |
                                ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
         const bool no_load = (RPE_CV_DBG(P) & 1) != 0, no_mma = (RPE_CV_DBG(P) & 2) != 0;
         const bool planes2 = P.n_planes == 2, reuse = P.reuse != 0, resident = P.resident_b != 0;
@@ -900,24 +902,24 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
 // One instantiation per epilogue mode: each kernel carries only its own epilogue (the instruction footprint of the three
 // concurrently running roles has to stay inside the instruction cache).
 template <int kMode>
-__global__ void __launch_bounds__(kCvThreads, 1) conv_bf16_kernel(const __grid_constant__ ConvParams P) {
+__global__ void __launch_bounds__(kCvThreads, 1) conv_f16x3_kernel(const __grid_constant__ ConvParams P) {
     conv_body<false, kMode>(P);
 }
 
 template <int kMode>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_bf16_pair_kernel(const __grid_constant__ ConvParams P) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kCvThreads, 1) conv_f16x3_pair_kernel(const __grid_constant__ ConvParams P) {
     conv_body<true, kMode>(P);
 }
 
 template <int kMode>
 static cudaError_t cv_launch(const ConvParams &p, int grid, bool pair, cudaStream_t stream, bool set_attr) {
     if (set_attr) {
-        cudaError_t e = cudaFuncSetAttribute(conv_bf16_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_bf16_pair_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
+        cudaError_t e = cudaFuncSetAttribute(conv_f16x3_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_f16x3_pair_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCvSmem);
         return e;
     }
-    if (pair) conv_bf16_pair_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
-    else conv_bf16_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
+    if (pair) conv_f16x3_pair_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
+    else conv_f16x3_kernel<kMode><<<grid, kCvThreads, kCvSmem, stream>>>(p);
     return cudaSuccess;
 }
 static cudaError_t cv_dispatch(int kind, const ConvParams &p, int grid, bool pair, cudaStream_t stream, bool set_attr) {
@@ -1085,7 +1087,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
                 delete pl;
                 return RPE_ERR_ALIGNMENT;
             }
-            {   // activations: (C, minor, major, N) bf16; the channel window starts at c_offset, channels beyond it read as zero
+            {   // activations: (C, minor, major, N) fp16; the channel window starts at c_offset, channels beyond it read as zero
                 const char *base = reinterpret_cast<const char *>(act) + (size_t)sc.c_offset * 2;
                 const cuuint64_t pix = (cuuint64_t)sc.c_total * 2, row = pix * d->W;
                 cuuint64_t dims[4] = {(cuuint64_t)sc.c_count, (cuuint64_t)(orient == 0 ? d->W : d->H),
@@ -1093,7 +1095,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
                 cuuint64_t strides[3] = {orient == 0 ? pix : row, orient == 0 ? row : pix, row * d->H};
                 cuuint32_t box[4] = {kCvBK, (cuuint32_t)(8 * stride), (cuuint32_t)(slab_rows * stride), 1};
                 cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-                CUresult r = g_cv_encode(&p.amap[s][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char *>(base), dims, strides, box,
+                CUresult r = g_cv_encode(&p.amap[s][pln], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<char *>(base), dims, strides, box,
                                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) {
@@ -1102,12 +1104,12 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
                     return RPE_ERR_CUDA;
                 }
             }
-            {   // weights: (Cin_s, Cout_pad, taps) bf16 with row pitch w_cstride, box (64, bn, 1)
+            {   // weights: (Cin_s, Cout_pad, taps) fp16 with row pitch w_cstride, box (64, bn, 1)
                 cuuint64_t dims[3] = {(cuuint64_t)sc.c_count, (cuuint64_t)d->cout_pad, (cuuint64_t)taps};
                 cuuint64_t strides[2] = {(cuuint64_t)sc.w_cstride * 2, (cuuint64_t)sc.w_cstride * 2 * d->cout_pad};
                 cuuint32_t box[3] = {kCvBK, (cuuint32_t)b_rows, 1};
                 cuuint32_t es[3] = {1, 1, 1};
-                CUresult r = g_cv_encode(&p.wmap[s][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(wgt), dims, strides, box,
+                CUresult r = g_cv_encode(&p.wmap[s][pln], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(wgt), dims, strides, box,
                                          es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (r != CUDA_SUCCESS) {
@@ -1123,9 +1125,10 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.tiles_maj = ((orient == 0 ? OH : OW) + 15) / 16;
     p.cout = d->cout, p.bn = bn, p.n_blocks = n_blocks;
     p.bias = d->bias, p.act = d->activation, p.scale = d->out_scale;
+    p.acc_scale = d->acc_scale != 0.0f ? d->acc_scale : 1.0f;
     p.pre = d->pre, p.pre_ld = d->pre_ld, p.res = d->res, p.res_ld = d->res_ld;
     p.out_f32 = d->out_f32, p.f32_ld = d->f32_ld, p.f32_off = d->f32_offset;
-    p.out_hi = reinterpret_cast<__nv_bfloat16 *>(d->out_hi), p.out_lo = reinterpret_cast<__nv_bfloat16 *>(d->out_lo);
+    p.out_hi = reinterpret_cast<rpe::plane_t *>(d->out_hi), p.out_lo = reinterpret_cast<rpe::plane_t *>(d->out_lo);
     p.bf_ld = d->bf_ld, p.bf_off = d->bf_offset;
     p.mode = d->mode, p.aux = d->aux, p.aux_ld = d->aux_ld, p.aux2 = d->aux2, p.aux2_ld = d->aux2_ld;
     p.dbg = cv_env().dbg;
@@ -1199,7 +1202,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
 // All-pairs correlation volume + pooled pyramid on the convolution kernel (kind 7): level0[b, q, t] = <f1[b, q, :], f2[b, t, :]> /
 // sqrt(C) as a 1x1 "convolution" of the first feature map whose weights are the second feature map of the same image.
 int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_hi, const void *f2_lo, float *pyramid, int B, int C, int h,
-                          int w, int num_levels, void *stream) {
+                          int w, int num_levels, int f1_wrap, int f1_sub, void *stream) {
     using namespace rpe;
     if (!f1_hi || !f1_lo || !f2_hi || !f2_lo || !pyramid) return RPE_ERR_INVALID_ARG;
     if (B <= 0 || C <= 0 || (C % 64) || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4) return RPE_ERR_INVALID_ARG;
@@ -1230,8 +1233,12 @@ int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_h
     p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
     if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
     p.corr_h = h, p.corr_w = w, p.corr_nbx = (w + 15) / 16, p.corr_levels = num_levels;
+    if (f1_wrap <= 0) f1_wrap = B, f1_sub = 0;                  // identity: sample s correlates f1 image s with f2 image s
+    if (f1_sub < 0 || f1_sub > f1_wrap) return RPE_ERR_INVALID_ARG;
+    p.corr_a_wrap = f1_wrap, p.corr_a_sub = f1_sub;
     p.bn = 256, p.n_blocks = p.corr_nbx * ((h + 15) / 16), p.cout = p.bn * p.n_blocks;
     p.scale = 1.0f / sqrtf((float)C);
+    p.acc_scale = 1.0f;
     {   // level bases (the layout of rpe_corr_level_offset) and which of them take vector stores
         size_t off = 0;
         for (int l = 0; l < num_levels; ++l) {
@@ -1250,11 +1257,11 @@ int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_h
         cuuint32_t es[4] = {1, 1, 1, 1};
         cuuint32_t abox[4] = {kCvBK, 8, 16, 1};
         cuuint32_t bbox[4] = {kCvBK, 16, (cuuint32_t)(b_rows / 16), 1};
-        CUresult r = g_cv_encode(&p.amap[0][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptrs[pln]), dims, strides, abox, es,
+        CUresult r = g_cv_encode(&p.amap[0][pln], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptrs[pln]), dims, strides, abox, es,
                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r == CUDA_SUCCESS)
-            r = g_cv_encode(&p.wmap[0][pln], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptrs[2 + pln]), dims, strides, bbox, es,
+            r = g_cv_encode(&p.wmap[0][pln], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void *>(ptrs[2 + pln]), dims, strides, bbox, es,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {

@@ -14,7 +14,7 @@
 #include <cstdio>
 #include <cuda.h>
 #include <cudaTypedefs.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -29,36 +29,6 @@ __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
-}
-
-// bf16 variant (RPE_CORR_BF16X3): the same [hi | lo | hi] x [hi | hi | lo] arrangement with hi = bf16(x), lo = bf16(x - hi), for the
-// full-rate kind::f16 MMAs (16 mantissa bits per operand, like the convolution trunk's bf16x3 arithmetic).
-__global__ void __launch_bounds__(256) corr_prep_bf16_kernel(const float *__restrict__ fmap, __nv_bfloat16 *__restrict__ out, int C, int Q,
-                                                             int which) {
-    __shared__ float tile[32][33];
-    const int b = blockIdx.z;
-    const int q0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    const int Kp = 3 * C;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c0 + ty + 8 * j, q = q0 + tx;
-        tile[ty + 8 * j][tx] = (c < C && q < Q) ? __ldg(fmap + ((size_t)b * C + c) * Q + q) : 0.0f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int q = q0 + ty + 8 * j, c = c0 + tx;
-        if (q < Q && c < C) {
-            const float x = tile[tx][ty + 8 * j];
-            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-            const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-            __nv_bfloat16 *o = out + ((size_t)b * Q + q) * Kp;
-            o[c] = hi;
-            o[C + c] = which == 0 ? lo : hi;
-            o[2 * C + c] = which == 0 ? hi : lo;
-        }
-    }
 }
 
 __global__ void __launch_bounds__(256) corr_prep_kernel(const float *__restrict__ fmap, float *__restrict__ out, int C, int Q,
@@ -112,16 +82,6 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13),
 // a/b K-major (0), n_dim = N>>3 [17,23), m_dim = M>>4 [24,29)
 constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-// bf16 operands (a/b_format BF16 = 1), kind::f16: K = 16 per instruction, 64 elements per 128-byte swizzle row
-constexpr uint32_t kInstrDescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-__device__ __forceinline__ void umma_bf16_1cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 
 struct GemmShape {
     int B, Q, Kp;      // batch, queries (= targets), padded contraction length
@@ -129,7 +89,6 @@ struct GemmShape {
     float scale;       // 1 / sqrt(C)
 };
 
-template <bool kBf16>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     corr_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_c, GemmShape s) {
@@ -146,7 +105,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = s.B * s.m_tiles * s.n_tiles;
-    constexpr int kBKe = kBf16 ? 2 * kBK : kBK;          // elements per 128-byte K block (stage bytes are the same)
+    constexpr int kBKe = kBK;                            // elements per 128-byte K block
     const int num_kb = s.Kp / kBKe;
 
     if (warp == 0 && lane == 0) {
@@ -211,8 +170,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
                     for (int k = 0; k < kBK / 8; ++k) {
                         // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in the (>>4) start address
-                        if (kBf16) umma_bf16_1cta(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDescBf16, (kb | k) != 0 ? 1u : 0u);
-                        else umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_tf32(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kInstrDesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);                 // frees the smem stage when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
@@ -330,7 +288,7 @@ constexpr int kMaxWin = 10;       // 2r+2 for r = 4
 
 __global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restrict__ pyr, PyrDims d, const float *__restrict__ coords,
                                                           float *__restrict__ out, int Q, int radius,
-                                                          __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo,
+                                                          plane_t *__restrict__ out_hi, plane_t *__restrict__ out_lo,
                                                           int nhwc_ld) {
     extern __shared__ float sm[];
     const int n = 2 * radius + 1, win = n + 1;
@@ -384,15 +342,15 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restric
     __syncthreads();
     const int nq = min(kLookupQ, Q - q_base);
     if (out_hi != nullptr) {
-        // NHWC bf16 hi/lo planes for the tcgen05 convolution path: 324 contiguous channels per query
+        // NHWC fp16 hi/lo planes for the tcgen05 convolution path: 324 contiguous channels per query
         for (int e = threadIdx.x; e < nch * kLookupQ; e += blockDim.x) {
             const int qi = e / nch, c = e - qi * nch;
             if (qi < nq) {
                 const float v = s_out[c * (kLookupQ + 1) + qi];
-                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                const plane_t h = to_plane(v);
                 const size_t o = ((size_t)b * Q + q_base + qi) * nhwc_ld + c;
                 out_hi[o] = h;
-                out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+                out_lo[o] = to_plane_lo(v - plane_to_float(h));
             }
         }
         return;
@@ -404,10 +362,10 @@ __global__ void __launch_bounds__(256) corr_lookup_kernel(const float *__restric
 }
 
 // ------------------------------------------------------------------------------------------------
-// Window lookup for the tensor-core update operator: output NHWC bf16 hi/lo planes, (L*(2r+1)^2) contiguous channels per
+// Window lookup for the tensor-core update operator: output NHWC fp16 hi/lo planes, (L*(2r+1)^2) contiguous channels per
 // query -- no transposition is needed, so one WARP owns one query: all L*(2r+2)^2 neighbourhood loads of the query are issued
 // back to back (up to 13 per lane in flight: a single memory round trip per query instead of one per level), staged in a
-// private shared-memory patch, then the lanes evaluate two adjacent channels each and store packed bf16 pairs.
+// private shared-memory patch, then the lanes evaluate two adjacent channels each and store packed fp16 pairs.
 // Coordinate arithmetic and interpolation order are those of corr_lookup_kernel (bit-identical values before the split).
 // ------------------------------------------------------------------------------------------------
 constexpr int kLkWarps = 8;
@@ -417,8 +375,8 @@ constexpr int kLkRounds = (kLkMaxElems + 31) / 32;     // 13
 template <int kRadius>      // compile-time radius: the index arithmetic below is all divisions by window sizes
 __global__ void __launch_bounds__(32 * kLkWarps) corr_lookup_nhwc_kernel(const float *__restrict__ pyr, PyrDims d,
                                                                          const float *__restrict__ coords,
-                                                                         __nv_bfloat16 *__restrict__ out_hi,
-                                                                         __nv_bfloat16 *__restrict__ out_lo, int ld, int Q,
+                                                                         plane_t *__restrict__ out_hi,
+                                                                         plane_t *__restrict__ out_lo, int ld, int Q,
                                                                          long long total_q, int radius_rt) {
     __shared__ float s_patch[kLkWarps][kLkMaxElems];
     __shared__ float s_frac[kLkWarps][8];               // fx, fy per level
@@ -489,16 +447,99 @@ __global__ void __launch_bounds__(32 * kLkWarps) corr_lookup_nhwc_kernel(const f
                     o[t] = pp[0] * w00 + pp[1] * w01 + pp[win] * w10 + pp[win + 1] * w11;
                 }
             }
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(o[0]), h1 = __float2bfloat16_rn(o[1]);
-            const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
-            const __nv_bfloat162 ll = __halves2bfloat162(__float2bfloat16_rn(o[0] - __bfloat162float(h0)),
-                                                         __float2bfloat16_rn(o[1] - __bfloat162float(h1)));
+            const plane_t h0 = to_plane(o[0]), h1 = to_plane(o[1]);
+            const plane2_t hh = __halves2half2(h0, h1);
+            const plane2_t ll = __halves2half2(to_plane_lo(o[0] - plane_to_float(h0)),
+                                                         to_plane_lo(o[1] - plane_to_float(h1)));
             if (c + 1 < nch) {
-                *reinterpret_cast<__nv_bfloat162 *>(out_hi + obase + c) = hh;
-                *reinterpret_cast<__nv_bfloat162 *>(out_lo + obase + c) = ll;
+                *reinterpret_cast<plane2_t *>(out_hi + obase + c) = hh;
+                *reinterpret_cast<plane2_t *>(out_lo + obase + c) = ll;
             } else {
                 out_hi[obase + c] = h0;
-                out_lo[obase + c] = __low2bfloat16(ll);
+                out_lo[obase + c] = __low2half(ll);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Radius-4, 4-level specialisation of the NHWC lookup (the shape RAFT uses): same arithmetic, a third of the instructions.
+// The first version spent more issue slots on index arithmetic (divisions by the window size, level selection per element)
+// than on memory: ~1000 warp instructions per query against ~50 cache lines.  Here every loop is level-uniform and unrolled:
+//   load     level l, round j: lane = r * 10 + c (r < 3, c < 10) fetches window row 3j + r, column c  -- 4 rounds per level, all
+//            16 loads of a lane in flight before the first use; (r, c) are per-lane constants;
+//   compute  level l, pass m: lane evaluates output e = lane + 32 m (< 81) from the staged 10x10 patch; its patch offset
+//            (e % 9) * 10 + e / 9 is a per-lane constant as well (channel e = x-offset * 9 + y-offset).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * kLkWarps) corr_lookup_nhwc_r4_kernel(const float *__restrict__ pyr, PyrDims d,
+                                                                            const float *__restrict__ coords, plane_t *__restrict__ out_hi,
+                                                                            plane_t *__restrict__ out_lo, int ld, int Q, long long total_q) {
+    __shared__ float s_patch[kLkWarps][4][104];          // [level][10 x 10] (+4 floats: keeps the levels 16-byte apart)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane / 10, c = lane - 10 * r;          // window row (within a round of 3 rows) and column fetched by this lane
+    const bool loader = lane < 30;
+    int poff[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        const int e = lane + 32 * m;                     // e = i * 9 + j: i = x offset (slow), j = y offset (fast)
+        const int i = e / 9, j = e - 9 * i;
+        poff[m] = j * 10 + i;
+    }
+    const int h0 = d.h[0], w0 = d.w[0];
+    float(*patch)[104] = s_patch[warp];
+    for (long long gq = (long long)blockIdx.x * kLkWarps + warp; gq < total_q; gq += (long long)gridDim.x * kLkWarps) {
+        const int b = (int)(gq / Q), q = (int)(gq - (long long)b * Q);
+        const float cx = __ldg(coords + ((size_t)b * 2 + 0) * Q + q);
+        const float cy = __ldg(coords + ((size_t)b * 2 + 1) * Q + q);
+        float fx[4], fy[4], v[4][4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int hl = h0 >> l, wl = w0 >> l;
+            const float inv = 1.0f / (float)(1 << l);
+            // reference: x = cx / 2^l + dx ; g = 2 x / (wl - 1) - 1 ; ix = (g + 1) * (wl - 1) / 2  (fp32 round trip, corr_lookup_kernel)
+            const float xc = __fmul_rn(cx, inv), yc = __fmul_rn(cy, inv);
+            const float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, xc), (float)(wl - 1)), 1.0f);
+            const float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, yc), (float)(hl - 1)), 1.0f);
+            const float ix = __fmul_rn(__fadd_rn(gx, 1.0f), (float)(wl - 1) * 0.5f);
+            const float iy = __fmul_rn(__fadd_rn(gy, 1.0f), (float)(hl - 1) * 0.5f);
+            const float x0f = floorf(ix), y0f = floorf(iy);
+            fx[l] = ix - x0f, fy[l] = iy - y0f;
+            const float lim = 1.0e6f;
+            const int xx = (int)fminf(fmaxf(x0f, -lim), lim) - 4 + c;
+            const int y0 = (int)fminf(fmaxf(y0f, -lim), lim) - 4 + r;
+            const float *slab = pyr + d.off[l] + (size_t)gq * (size_t)(hl * wl);
+            const bool xin = loader && xx >= 0 && xx < wl;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int yy = y0 + 3 * j;
+                v[l][j] = 0.0f;
+                if (xin && yy >= 0 && yy < hl && (j < 3 || r == 0)) v[l][j] = __ldg(slab + yy * wl + xx);
+            }
+        }
+        if (loader) {
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) patch[l][(3 * j + r) * 10 + c] = v[l][j];
+                if (r == 0) patch[l][90 + c] = v[l][3];
+            }
+        }
+        __syncwarp();
+        const size_t obase = (size_t)gq * ld;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const float w00 = (1.0f - fy[l]) * (1.0f - fx[l]), w01 = (1.0f - fy[l]) * fx[l], w10 = fy[l] * (1.0f - fx[l]), w11 = fy[l] * fx[l];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                if (m < 2 || lane < 81 - 64) {
+                    const float *pp = patch[l] + poff[m];
+                    const float o = pp[0] * w00 + pp[1] * w01 + pp[10] * w10 + pp[11] * w11;
+                    const plane_t hh = to_plane(o);
+                    const size_t oo = obase + l * 81 + lane + 32 * m;
+                    out_hi[oo] = hh;
+                    out_lo[oo] = to_plane_lo(o - plane_to_float(hh));
+                }
             }
         }
         __syncwarp();
@@ -522,13 +563,13 @@ static int load_encode() {
 
 // 3-D fp32 tensor (inner, rows, batch) with a (box_inner x box_rows x 1) box, SWIZZLE_128B.
 static int make_map(CUtensorMap *m, const void *base, uint64_t inner, uint64_t rows, uint64_t batch, uint32_t box_inner,
-                    uint32_t box_rows, bool bf16 = false) {
-    const uint64_t es = bf16 ? 2 : 4;
+                    uint32_t box_rows) {
+    const uint64_t es = 4;
     cuuint64_t dims[3] = {inner, rows, batch};
     cuuint64_t strides[2] = {inner * es, inner * rows * es};
     cuuint32_t box[3] = {box_inner, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -572,11 +613,10 @@ size_t rpe_corr_pyramid_bytes(int B, int h, int w, int num_levels) {
 }
 
 size_t rpe_corr_workspace_bytes(int B, int C, int h, int w, int precision) {
-    if (precision == RPE_CORR_BF16X3 && C % 64 == 0)      // four NHWC bf16 planes (hi / lo of both feature maps)
+    if (precision == RPE_CORR_F16X3)      // four NHWC fp16 planes (hi / lo of both feature maps)
         return 4 * (((size_t)B * h * w * C * 2 + 1023) & ~(size_t)1023);
     const size_t Kp = precision == RPE_CORR_TF32 ? (size_t)C : 3 * (size_t)C;
-    const size_t es = precision == RPE_CORR_BF16X3 ? 2 : sizeof(float);
-    return 2 * (((size_t)B * h * w * Kp * es + 1023) & ~(size_t)1023);
+    return 2 * (((size_t)B * h * w * Kp * sizeof(float) + 1023) & ~(size_t)1023);
 }
 
 int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B, int C, int h, int w, int num_levels,
@@ -585,9 +625,9 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     if (!fmap1 || !fmap2 || !pyramid || !workspace) return RPE_ERR_INVALID_ARG;
     if (B <= 0 || C <= 0 || h <= 0 || w <= 0 || num_levels < 1 || num_levels > 4) return RPE_ERR_INVALID_ARG;
     if (C % 32 != 0) return RPE_ERR_INVALID_ARG;
-    if (precision != RPE_CORR_TF32 && precision != RPE_CORR_TF32X3 && precision != RPE_CORR_BF16X3) return RPE_ERR_INVALID_ARG;
-    const bool bf16 = precision == RPE_CORR_BF16X3;
-    if (bf16 && (3 * C) % 64 != 0) return RPE_ERR_INVALID_ARG;
+    if (precision != RPE_CORR_TF32 && precision != RPE_CORR_TF32X3 && precision != RPE_CORR_F16X3) return RPE_ERR_INVALID_ARG;
+    const bool f16 = precision == RPE_CORR_F16X3;
+    if (f16 && C % 64 != 0) return RPE_ERR_INVALID_ARG;
     if ((h >> (num_levels - 1)) < 1 || (w >> (num_levels - 1)) < 1) return RPE_ERR_INVALID_ARG;
     const int Q = h * w;
     if (Q % 4 != 0) return RPE_ERR_INVALID_ARG;     // TMA global strides must be multiples of 16 bytes
@@ -596,15 +636,15 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     int rc = load_encode();
     if (rc != RPE_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bf16 && C % 64 == 0) {
-        // bf16x3: NHWC hi/lo planes of both feature maps, then the fused volume + pyramid kernel (conv.cu kind 7): level 0 and
+    if (f16) {
+        // fp16x3: NHWC hi/lo planes of both feature maps, then the fused volume + pyramid kernel (conv.cu kind 7): level 0 and
         // the three pooled levels leave the tensor-memory accumulators in one pass, no second read of the volume
         const size_t plane = (((size_t)B * Q * C * 2) + 1023) & ~(size_t)1023;
         char *ws = reinterpret_cast<char *>(workspace);
         void *f1h = ws, *f1l = ws + plane, *f2h = ws + 2 * plane, *f2l = ws + 3 * plane;
         if ((rc = rpe_nchw_to_nhwc_split(fmap1, f1h, f1l, nullptr, B, C, h, w, C, 0, 0, 0, stream)) != RPE_OK) return rc;
         if ((rc = rpe_nchw_to_nhwc_split(fmap2, f2h, f2l, nullptr, B, C, h, w, C, 0, 0, 0, stream)) != RPE_OK) return rc;
-        return rpe_corr_build_planes(f1h, f1l, f2h, f2l, pyramid, B, C, h, w, num_levels, stream);
+        return rpe_corr_build_planes(f1h, f1l, f2h, f2l, pyramid, B, C, h, w, num_levels, 0, 0, stream);
     }
     const int split = precision != RPE_CORR_TF32;
     const int Kp = split ? 3 * C : C;
@@ -612,22 +652,15 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     float *opB = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + rpe_corr_workspace_bytes(B, C, h, w, precision) / 2);
 
     dim3 pgrid((Q + 31) / 32, C / 32, B);
-    if (bf16) {
-        corr_prep_bf16_kernel<<<pgrid, 256, 0, st>>>(fmap1, reinterpret_cast<__nv_bfloat16 *>(opA), C, Q, 0);
-        RPE_LAUNCH_CHECK();
-        corr_prep_bf16_kernel<<<pgrid, 256, 0, st>>>(fmap2, reinterpret_cast<__nv_bfloat16 *>(opB), C, Q, 1);
-        RPE_LAUNCH_CHECK();
-    } else {
-        corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap1, opA, C, Q, split, 0);
-        RPE_LAUNCH_CHECK();
-        corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap2, opB, C, Q, split, 1);
-        RPE_LAUNCH_CHECK();
-    }
+    corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap1, opA, C, Q, split, 0);
+    RPE_LAUNCH_CHECK();
+    corr_prep_kernel<<<pgrid, 256, 0, st>>>(fmap2, opB, C, Q, split, 1);
+    RPE_LAUNCH_CHECK();
 
     PyrDims d = pyr_dims(B, h, w, num_levels);
     CUtensorMap ma, mb, mc;
-    if ((rc = make_map(&ma, opA, Kp, Q, B, bf16 ? 2 * kBK : kBK, kBM, bf16)) != RPE_OK) return rc;
-    if ((rc = make_map(&mb, opB, Kp, Q, B, bf16 ? 2 * kBK : kBK, kBN, bf16)) != RPE_OK) return rc;
+    if ((rc = make_map(&ma, opA, Kp, Q, B, kBK, kBM)) != RPE_OK) return rc;
+    if ((rc = make_map(&mb, opB, Kp, Q, B, kBK, kBN)) != RPE_OK) return rc;
     if ((rc = make_map(&mc, pyramid + d.off[0], Q, Q, B, kEpiCols, kBM)) != RPE_OK) return rc;
 
     GemmShape s;
@@ -636,13 +669,11 @@ int rpe_corr_build(const float *fmap1, const float *fmap2, float *pyramid, int B
     s.n_tiles = (Q + kBN - 1) / kBN;
     s.scale = 1.0f / sqrtf((float)C);
     // (function attributes are per device: set on every call -- a host-side no-op after the first)
-    RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-    RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+    RPE_CUDA_TRY(cudaFuncSetAttribute(corr_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
     int grid = sm_count();
     const int tiles = s.B * s.m_tiles * s.n_tiles;
     if (grid > tiles) grid = tiles;
-    if (bf16) corr_gemm_kernel<true><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
-    else corr_gemm_kernel<false><<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
+    corr_gemm_kernel<<<grid, kGemmThreads, kGemmSmem, st>>>(ma, mb, mc, s);
     RPE_LAUNCH_CHECK();
 
     if (num_levels > 1) {
@@ -671,13 +702,16 @@ static int corr_lookup_impl(const float *pyramid, const float *coords, float *ou
         long long blocks = (total_q + kLkWarps - 1) / kLkWarps;
         const long long cap = (long long)sm_count() * 8 * 4;
         if (blocks > cap) blocks = cap;
-        if (radius == 4)
+        if (radius == 4 && num_levels == 4)
+            corr_lookup_nhwc_r4_kernel<<<(unsigned)blocks, 32 * kLkWarps, 0, (cudaStream_t)stream>>>(
+                pyramid, d, coords, reinterpret_cast<rpe::plane_t *>(out_hi), reinterpret_cast<rpe::plane_t *>(out_lo), nhwc_ld, Q, total_q);
+        else if (radius == 4)
             corr_lookup_nhwc_kernel<4><<<(unsigned)blocks, 32 * kLkWarps, 0, (cudaStream_t)stream>>>(
-                pyramid, d, coords, reinterpret_cast<__nv_bfloat16 *>(out_hi), reinterpret_cast<__nv_bfloat16 *>(out_lo), nhwc_ld, Q,
+                pyramid, d, coords, reinterpret_cast<rpe::plane_t *>(out_hi), reinterpret_cast<rpe::plane_t *>(out_lo), nhwc_ld, Q,
                 total_q, radius);
         else
             corr_lookup_nhwc_kernel<0><<<(unsigned)blocks, 32 * kLkWarps, 0, (cudaStream_t)stream>>>(
-                pyramid, d, coords, reinterpret_cast<__nv_bfloat16 *>(out_hi), reinterpret_cast<__nv_bfloat16 *>(out_lo), nhwc_ld, Q,
+                pyramid, d, coords, reinterpret_cast<rpe::plane_t *>(out_hi), reinterpret_cast<rpe::plane_t *>(out_lo), nhwc_ld, Q,
                 total_q, radius);
         RPE_LAUNCH_CHECK();
         return RPE_OK;
@@ -686,8 +720,8 @@ static int corr_lookup_impl(const float *pyramid, const float *coords, float *ou
     if (smem > 48 * 1024) RPE_CUDA_TRY(cudaFuncSetAttribute(corr_lookup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((Q + kLookupQ - 1) / kLookupQ, B);
     corr_lookup_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(pyramid, d, coords, out, Q, radius,
-                                                                  reinterpret_cast<__nv_bfloat16 *>(out_hi),
-                                                                  reinterpret_cast<__nv_bfloat16 *>(out_lo), nhwc_ld);
+                                                                  reinterpret_cast<rpe::plane_t *>(out_hi),
+                                                                  reinterpret_cast<rpe::plane_t *>(out_lo), nhwc_ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
@@ -697,7 +731,7 @@ int rpe_corr_lookup(const float *pyramid, const float *coords, float *out, int B
     return corr_lookup_impl(pyramid, coords, out, nullptr, nullptr, 0, B, h, w, num_levels, radius, stream);
 }
 
-int rpe_corr_lookup_nhwc_bf16(const float *pyramid, const float *coords, void *out_hi, void *out_lo, int ld, int B, int h, int w,
+int rpe_corr_lookup_nhwc_split(const float *pyramid, const float *coords, void *out_hi, void *out_lo, int ld, int B, int h, int w,
                               int num_levels, int radius, void *stream) {
     const int n = 2 * radius + 1;
     if (!out_hi || !out_lo || ld < num_levels * n * n) return RPE_ERR_INVALID_ARG;

@@ -1,17 +1,17 @@
 // Element-wise / reduction companions of the tcgen05 convolution path of the RAFT encoders
 // (reference: /root/reference/core/RAFT/core/extractor.py:118-192 BasicEncoder, :6-56 ResidualBlock; input scaling
-// core/RAFT/core/raft.py:82-83).  All activations NHWC; "split" = bf16 hi/lo planes (conv.cu).
-#include <cuda_bf16.h>
+// core/RAFT/core/raft.py:82-83).  All activations NHWC; "split" = fp16 hi/lo planes (conv.cu).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace rpe {
 
 __device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
-    __nv_bfloat16 h[4], l[4];
+    plane_t h[4], l[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        h[k] = __float2bfloat16_rn(v[k]);
-        l[k] = __float2bfloat16_rn(v[k] - __bfloat162float(h[k]));
+        h[k] = to_plane(v[k]);
+        l[k] = to_plane_lo(v[k] - plane_to_float(h[k]));
     }
     hi = *reinterpret_cast<uint2 *>(h);
     lo = *reinterpret_cast<uint2 *>(l);
@@ -26,8 +26,8 @@ __device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
 // shared memory with coalesced loads (normalised on the way in, zeros outside the image), then thread (pixel, ky) assembles
 // its 24 values in a second shared tile and the CTA copies its contiguous 32 x 352-byte output range in 16-byte chunks.
 constexpr int kStemPx = 32, kStemCols = 2 * kStemPx + 5, kStemPitch = 72, kStemLd = 176;
-__global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict__ img, __nv_bfloat16 *__restrict__ hi,
-                                                        __nv_bfloat16 *__restrict__ lo, int H, int W, int OH, int OW, int ld) {
+__global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict__ img, plane_t *__restrict__ hi,
+                                                        plane_t *__restrict__ lo, int H, int W, int OH, int OW, int ld) {
     __shared__ float tile[7][3][kStemPitch];
     const int ox0 = blockIdx.x * kStemPx, oy = blockIdx.y, n = blockIdx.z;
     const int x0 = 2 * ox0 - 3, y0 = 2 * oy - 3;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict_
     }
     __syncthreads();
     // assemble the (pixel, ky) rows in shared memory, then copy the CTA's contiguous output range with 16-byte chunks
-    __shared__ __align__(16) __nv_bfloat16 s_hi[kStemPx][kStemLd], s_lo[kStemPx][kStemLd];
+    __shared__ __align__(16) plane_t s_hi[kStemPx][kStemLd], s_lo[kStemPx][kStemLd];
     const int npx = min(kStemPx, OW - ox0);
     if (threadIdx.x < kStemPx * 7) {
         const int ky = threadIdx.x % 7, p = threadIdx.x / 7;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float
 template <typename idx_t>
 __global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__ a, const float *__restrict__ sa, int relu_a,
                                                        const float *__restrict__ b, const float *__restrict__ sb, float *__restrict__ out,
-                                                       __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int ld, int HW, int C,
+                                                       plane_t *__restrict__ hi, plane_t *__restrict__ lo, int ld, int HW, int C,
                                                        long long total4) {
     const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
     if ((long long)i >= total4) return;
@@ -219,7 +219,7 @@ int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
     if (OH > 65535 || n > 65535 || ld != rpe::kStemLd) return RPE_ERR_INVALID_ARG;      // the staged copy assumes the 176-channel pitch
     dim3 grid((OW + rpe::kStemPx - 1) / rpe::kStemPx, OH, n);
-    rpe::im2col7s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, H, W, OH, OW, ld);
+    rpe::im2col7s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, H, W, OH, OW, ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }
@@ -267,10 +267,10 @@ int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const f
     const long long elems = (long long)n * HW * (long long)(ld > C ? ld : C);
     if (elems + 1024 < (1ll << 32))
         rpe::norm_act_kernel<unsigned><<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            a, stats_a, relu_a, b, stats_b, out_f32, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, ld, HW, C, total4);
+            a, stats_a, relu_a, b, stats_b, out_f32, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, ld, HW, C, total4);
     else
         rpe::norm_act_kernel<unsigned long long><<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            a, stats_a, relu_a, b, stats_b, out_f32, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo, ld, HW, C, total4);
+            a, stats_a, relu_a, b, stats_b, out_f32, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, ld, HW, C, total4);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

@@ -2,14 +2,19 @@
 //
 // One persistent cooperative kernel per batch of pairs.  The grid is split into groups of CTAs;
 // each group owns one pair at a time.  Per objective evaluation every CTA of the group
-//   1. streams its pixel slice (42 B/px: flow 8 + pcl1 12 + pcl2w 12 + w1 4 + w2 4 + 2 mask bytes;
-//      L2-resident after the first evaluation), evaluates the 2D reprojection and 3D point-to-point
-//      residuals, the Lie-algebra Jacobians and the confidence weights in fp64, and reduces
-//      f, grad (6) [and the 21 GN Hessian entries] with warp shuffles + a block-level tree,
+//   1. streams its pixel slices (42 B/px: flow 8 + pcl1 12 + pcl2w 12 + w1 4 + w2 4 + 2 mask bytes), evaluates the 2D
+//      reprojection and 3D point-to-point residuals, the Lie-algebra Jacobians and the confidence weights in fp64, and
+//      reduces f, grad (6) [and the 21 GN Hessian entries] with warp shuffles + a block-level tree,
 //   2. publishes its partial sums, passes a group-wide barrier, and
-//   3. re-sums ALL partials of the group in a fixed order, so every CTA holds bit-identical totals
+//   3. re-sums ALL partials of the pair in a fixed order, so every CTA holds bit-identical totals
 //      and advances an identical copy of the 6-dim solver state -- no broadcast, one barrier per
 //      evaluation, no host round trip (the reference syncs on float(loss) every iteration).
+// The pixels of a pair are dealt to kVirt = 128 VIRTUAL blocks by index alone and a CTA evaluates whole virtual blocks, so
+// the summation tree -- and with it every bit of the result -- does not depend on how many CTAs or concurrent groups a
+// launch uses (a pair solved alone, in a batch of 32 or on another rank of a sharded run gives the same pose).
+// Measured (B200): the kernel is bound by the fp64 pipe and by the serial part of every evaluation (group barrier, re-summation,
+// solver step), not by memory -- capping the concurrent groups so that their inputs stay L2-resident (4 groups of 64 CTAs) is
+// slower than many small groups that stream from HBM.
 //
 // Reference semantics: /root/reference/core/pose/pose_head.py:12-79,
 // core/geometry/pinhole_transforms.py:28-30,90-99, torch.optim.LBFGS.step (lr=1, no line search,
@@ -25,6 +30,8 @@ constexpr int kPoseThreads = 256;
 constexpr int kMaxHist = 100;      // torch.optim.LBFGS history_size default
 constexpr int kAccGrad = 8;        // e2, e3, g[6]
 constexpr int kAccHess = 8 + 21;   // + upper triangle of J^T W J
+constexpr int kVirt = 128;         // virtual blocks per pair (fixed reduction tree)
+constexpr int kMaxGroups = 64;
 
 struct PoseParams {
     rpe_pose_problem p;
@@ -34,7 +41,7 @@ struct PoseParams {
     float *pose_f32, *log_f32;
     double *trace;
     int trace_cap;
-    double *partials;          // [n_groups][2][blocks_per_group][kAccHess]
+    double *partials;          // [n_groups][2][kVirt][kAccHess]
     unsigned int *counters;    // [n_groups] (zeroed by the host before launch), 128 B apart
 };
 
@@ -262,7 +269,7 @@ __device__ __forceinline__ void group_barrier(unsigned int *counter, unsigned in
 
 template <bool kHess>
 __device__ void evaluate_group(const PoseParams &P, const PixelConsts &c, int pair, int blk, SolverState &S, double *s_red,
-                               double *partial_slot) {
+                               double *partial_base) {
     constexpr int NA = kHess ? kAccHess : kAccGrad;
     const int N = c.N;
     const size_t off = (size_t)pair * N;
@@ -273,47 +280,49 @@ __device__ void evaluate_group(const PoseParams &P, const PixelConsts &c, int pa
     const float *w2 = P.p.w2 ? P.p.w2 + off : nullptr;
     const uint8_t *m1 = P.p.m1 + off;
     const uint8_t *m2 = P.p.m2 + off;
-    double acc[NA];
-#pragma unroll
-    for (int k = 0; k < NA; ++k) acc[k] = 0.0;
     double R[9], tr[3];
 #pragma unroll
     for (int k = 0; k < 9; ++k) R[k] = S.R[k];
 #pragma unroll
     for (int k = 0; k < 3; ++k) tr[k] = S.X.t[k];
-
-    const int stride = P.blocks_per_group * kPoseThreads * 4;
-    for (int i = (blk * kPoseThreads + threadIdx.x) * 4; i < N; i += stride) {
-        const float4 fx = *reinterpret_cast<const float4 *>(flow + i);
-        const float4 fy = *reinterpret_cast<const float4 *>(flow + N + i);
-        const float4 ax = *reinterpret_cast<const float4 *>(p1 + i);
-        const float4 ay = *reinterpret_cast<const float4 *>(p1 + N + i);
-        const float4 az = *reinterpret_cast<const float4 *>(p1 + 2 * N + i);
-        const float4 bx = *reinterpret_cast<const float4 *>(p2 + i);
-        const float4 by = *reinterpret_cast<const float4 *>(p2 + N + i);
-        const float4 bz = *reinterpret_cast<const float4 *>(p2 + 2 * N + i);
-        const float4 c1 = w1 ? *reinterpret_cast<const float4 *>(w1 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const float4 c2 = w2 ? *reinterpret_cast<const float4 *>(w2 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
-        const uchar4 ma = *reinterpret_cast<const uchar4 *>(m1 + i);
-        const uchar4 mb = *reinterpret_cast<const uchar4 *>(m2 + i);
-        accumulate_pixel<kHess>(c, R, tr, i + 0, fx.x, fy.x, ax.x, ay.x, az.x, bx.x, by.x, bz.x, c1.x, c2.x, ma.x != 0, mb.x != 0, acc);
-        accumulate_pixel<kHess>(c, R, tr, i + 1, fx.y, fy.y, ax.y, ay.y, az.y, bx.y, by.y, bz.y, c1.y, c2.y, ma.y != 0, mb.y != 0, acc);
-        accumulate_pixel<kHess>(c, R, tr, i + 2, fx.z, fy.z, ax.z, ay.z, az.z, bx.z, by.z, bz.z, c1.z, c2.z, ma.z != 0, mb.z != 0, acc);
-        accumulate_pixel<kHess>(c, R, tr, i + 3, fx.w, fy.w, ax.w, ay.w, az.w, bx.w, by.w, bz.w, c1.w, c2.w, ma.w != 0, mb.w != 0, acc);
-    }
-    // ---- block reduction: warp shuffles, then a tree over the 8 warp partials in shared memory
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = kVirt * kPoseThreads * 4;
+    for (int vb = blk; vb < kVirt; vb += P.blocks_per_group) {
+        double acc[NA];
 #pragma unroll
-    for (int k = 0; k < NA; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) s_red[warp * kAccHess + k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < NA) {
-        double v = 0.0;
+        for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+        for (int i = (vb * kPoseThreads + threadIdx.x) * 4; i < N; i += stride) {
+            const float4 fx = *reinterpret_cast<const float4 *>(flow + i);
+            const float4 fy = *reinterpret_cast<const float4 *>(flow + N + i);
+            const float4 ax = *reinterpret_cast<const float4 *>(p1 + i);
+            const float4 ay = *reinterpret_cast<const float4 *>(p1 + N + i);
+            const float4 az = *reinterpret_cast<const float4 *>(p1 + 2 * N + i);
+            const float4 bx = *reinterpret_cast<const float4 *>(p2 + i);
+            const float4 by = *reinterpret_cast<const float4 *>(p2 + N + i);
+            const float4 bz = *reinterpret_cast<const float4 *>(p2 + 2 * N + i);
+            const float4 c1 = w1 ? *reinterpret_cast<const float4 *>(w1 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const float4 c2 = w2 ? *reinterpret_cast<const float4 *>(w2 + i) : make_float4(1.f, 1.f, 1.f, 1.f);
+            const uchar4 ma = *reinterpret_cast<const uchar4 *>(m1 + i);
+            const uchar4 mb = *reinterpret_cast<const uchar4 *>(m2 + i);
+            accumulate_pixel<kHess>(c, R, tr, i + 0, fx.x, fy.x, ax.x, ay.x, az.x, bx.x, by.x, bz.x, c1.x, c2.x, ma.x != 0, mb.x != 0, acc);
+            accumulate_pixel<kHess>(c, R, tr, i + 1, fx.y, fy.y, ax.y, ay.y, az.y, bx.y, by.y, bz.y, c1.y, c2.y, ma.y != 0, mb.y != 0, acc);
+            accumulate_pixel<kHess>(c, R, tr, i + 2, fx.z, fy.z, ax.z, ay.z, az.z, bx.z, by.z, bz.z, c1.z, c2.z, ma.z != 0, mb.z != 0, acc);
+            accumulate_pixel<kHess>(c, R, tr, i + 3, fx.w, fy.w, ax.w, ay.w, az.w, bx.w, by.w, bz.w, c1.w, c2.w, ma.w != 0, mb.w != 0, acc);
+        }
+        // ---- block reduction of this virtual block: warp shuffles, then a tree over the 8 warp partials in shared memory
+        __syncthreads();                                   // s_red of the previous virtual block has been consumed
 #pragma unroll
-        for (int w = 0; w < kPoseThreads / 32; ++w) v += s_red[w * kAccHess + threadIdx.x];
-        partial_slot[threadIdx.x] = v;
+        for (int k = 0; k < NA; ++k) {
+            const double v = warp_sum(acc[k]);
+            if (lane == 0) s_red[warp * kAccHess + k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < NA) {
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < kPoseThreads / 32; ++w) v += s_red[w * kAccHess + threadIdx.x];
+            partial_base[(size_t)vb * kAccHess + threadIdx.x] = v;
+        }
     }
 }
 
@@ -323,11 +332,15 @@ __device__ void gather_totals(const PoseParams &P, const PixelConsts &c, const d
                               SolverState &S) {
     constexpr int NA = kHess ? kAccHess : kAccGrad;
     __shared__ double s_tot[kAccHess];
-    if (threadIdx.x < NA) {
+    __shared__ double s_q[kAccHess][4];
+    if (threadIdx.x < 4 * NA) {                            // four interleaved quarter sums per accumulator, then ((q0 + q1) + q2) + q3
+        const int a = threadIdx.x >> 2, part = threadIdx.x & 3;
         double v = 0.0;
-        for (int b = 0; b < P.blocks_per_group; ++b) v += __ldcg(partials_eval + (size_t)b * kAccHess + threadIdx.x);
-        s_tot[threadIdx.x] = v;
+        for (int b = part; b < kVirt; b += 4) v += __ldcg(partials_eval + (size_t)b * kAccHess + a);
+        s_q[a][part] = v;
     }
+    __syncthreads();
+    if (threadIdx.x < NA) s_tot[threadIdx.x] = ((s_q[threadIdx.x][0] + s_q[threadIdx.x][1]) + s_q[threadIdx.x][2]) + s_q[threadIdx.x][3];
     __syncthreads();
     if (threadIdx.x == 0) {
         const double N = (double)c.N;
@@ -517,7 +530,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_solve_kernel(PoseParams P) 
     const int group = blockIdx.x / P.blocks_per_group;
     const int blk = blockIdx.x - group * P.blocks_per_group;
     unsigned int *counter = P.counters + group * 32;
-    double *gpart = P.partials + (size_t)group * 2 * P.blocks_per_group * kAccHess;
+    double *gpart = P.partials + (size_t)group * 2 * kVirt * kAccHess;
     unsigned int barrier_no = 0;
 
     for (int pair = group; pair < P.p.n; pair += P.n_groups) {
@@ -545,8 +558,8 @@ __global__ void __launch_bounds__(kPoseThreads) pose_solve_kernel(PoseParams P) 
 
         while (true) {
             // ---- one fused evaluation at S.X
-            double *slot_base = gpart + (size_t)(barrier_no & 1u) * P.blocks_per_group * kAccHess;
-            evaluate_group<kHess>(P, C, pair, blk, S, s_red, slot_base + (size_t)blk * kAccHess);
+            double *slot_base = gpart + (size_t)(barrier_no & 1u) * kVirt * kAccHess;
+            evaluate_group<kHess>(P, C, pair, blk, S, s_red, slot_base);
             barrier_no += 1;
             group_barrier(counter, barrier_no * (unsigned int)P.blocks_per_group);
             gather_totals<kHess>(P, C, slot_base, lw0, lw1, S);
@@ -594,22 +607,29 @@ __global__ void __launch_bounds__(kPoseThreads) pose_solve_kernel(PoseParams P) 
     }
 }
 
-static int g_pose_groups = 16;   // upper bound on concurrently solved pairs
+static int g_pose_groups = 0;    // upper bound on concurrently solved pairs; 0 = as many as the CTA slots allow
+static int g_pose_bpg = 32;      // CTAs per group in batch mode (power of two <= kVirt)
 
 }  // namespace rpe
 
 extern "C" {
 
 int rpe_pose_set_groups(int groups) {
-    if (groups < 1 || groups > 256) return RPE_ERR_INVALID_ARG;
+    if (groups < 1 || groups > rpe::kMaxGroups) return RPE_ERR_INVALID_ARG;
     rpe::g_pose_groups = groups;
+    return RPE_OK;
+}
+
+int rpe_pose_set_group_size(int ctas) {
+    if (ctas < 1 || ctas > rpe::kVirt || (ctas & (ctas - 1))) return RPE_ERR_INVALID_ARG;
+    rpe::g_pose_bpg = ctas;
     return RPE_OK;
 }
 
 size_t rpe_pose_workspace_bytes(int n_pairs) {
     (void)n_pairs;
-    // partials for up to 1024 CTAs (2 buffers) + 128-byte-spaced counters for up to 256 groups
-    return (size_t)2 * 1024 * rpe::kAccHess * sizeof(double) + 256 * 128;
+    // per group two buffers of kVirt partial-sum records + 128-byte-spaced barrier counters
+    return (size_t)rpe::kMaxGroups * 2 * rpe::kVirt * rpe::kAccHess * sizeof(double) + rpe::kMaxGroups * 128;
 }
 
 int rpe_pose_solve(const rpe_pose_problem *pb, int mode, int max_iter, int with_hessian, double *out, float *pose_f32,
@@ -638,20 +658,24 @@ int rpe_pose_solve(const rpe_pose_problem *pb, int mode, int max_iter, int with_
     int max_blocks = sms * per_sm;
     if (max_blocks > 1024) max_blocks = 1024;
 
-    // Group sizing: a single pair gets the whole GPU (latency path); a batch is spread over up to
-    // g_pose_groups concurrent groups so that the barrier latency of one group overlaps the fp64
-    // math of the others (throughput path).
-    const long long px_per_block_iter = (long long)kPoseThreads * 4;
-    // Pairs are dealt round-robin to the groups, so the group count is balanced against the number of rounds: 11 pairs run
-    // as one round of 11 groups rather than 8 + 3.
-    const int rounds = (pb->n + g_pose_groups - 1) / g_pose_groups;
-    int n_groups = (pb->n + rounds - 1) / rounds;
+    // Group sizing.  A pair is split into kVirt virtual blocks, so at most kVirt CTAs can work on it: one or two pairs take
+    // kVirt CTAs each (latency path).  A batch runs many small groups (g_pose_bpg CTAs, several virtual blocks per CTA and
+    // evaluation): the serial part of an evaluation (group barrier, re-summation, the solver step on one thread) is hidden by
+    // the other groups' arithmetic.  Measured on B200, 32 pairs of 640x512 (tools/pose_probe.py, profiles/): see DESIGN.md.
+    int bpg = pb->n <= 2 ? kVirt : g_pose_bpg;
+    while (bpg > 1 && bpg > max_blocks) bpg >>= 1;
+    int n_groups = max_blocks / bpg;
+    if (g_pose_groups > 0 && n_groups > g_pose_groups) n_groups = g_pose_groups;
+    if (n_groups > pb->n) n_groups = pb->n;
+    if (n_groups > kMaxGroups) n_groups = kMaxGroups;
     if (n_groups < 1) n_groups = 1;
-    if (n_groups > 256) n_groups = 256;
-    int bpg = max_blocks / n_groups;
-    const int useful = (int)((N + px_per_block_iter - 1) / px_per_block_iter);
-    if (bpg > useful) bpg = useful;
-    if (bpg < 1) bpg = 1;
+    // pairs are dealt round-robin: balance the group count against the number of rounds (11 pairs on 4 groups = 3 rounds of 4, 4, 3)
+    {
+        const int rounds = (pb->n + n_groups - 1) / n_groups;
+        n_groups = (pb->n + rounds - 1) / rounds;
+    }
+    // with few groups and free CTA slots, give every pair more CTAs (powers of two up to kVirt)
+    while (bpg < kVirt && n_groups * bpg * 2 <= max_blocks) bpg <<= 1;
 
     PoseParams P;
     P.p = *pb;
@@ -659,8 +683,8 @@ int rpe_pose_solve(const rpe_pose_problem *pb, int mode, int max_iter, int with_
     P.blocks_per_group = bpg, P.n_groups = n_groups;
     P.out = out, P.pose_f32 = pose_f32, P.log_f32 = log_f32, P.trace = trace, P.trace_cap = trace_cap;
     P.partials = reinterpret_cast<double *>(workspace);
-    P.counters = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(workspace) + (size_t)2 * 1024 * kAccHess * sizeof(double));
-    RPE_CUDA_TRY(cudaMemsetAsync(P.counters, 0, 256 * 128, st));
+    P.counters = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(workspace) + (size_t)kMaxGroups * 2 * kVirt * kAccHess * sizeof(double));
+    RPE_CUDA_TRY(cudaMemsetAsync(P.counters, 0, kMaxGroups * 128, st));
     void *args[] = {&P};
     RPE_CUDA_TRY(cudaLaunchCooperativeKernel(kern, dim3(bpg * n_groups), dim3(kPoseThreads), args, 0, st));
     ++g_launch_count;

@@ -1,20 +1,20 @@
 // Element-wise companions of the tcgen05 convolution path of the RAFT update operator
 // (reference: /root/reference/core/RAFT/core/update.py:33-60 SepConvGRU gating, :79-97 motion encoder inputs,
-// core/RAFT/core/raft.py:112-121 coordinate update).  All tensors NHWC; "split" = bf16 hi/lo planes (conv.cu).
-#include <cuda_bf16.h>
+// core/RAFT/core/raft.py:112-121 coordinate update).  All tensors NHWC; "split" = fp16 hi/lo planes (conv.cu).
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace rpe {
 
-__device__ __forceinline__ void split_store(float v, __nv_bfloat16 *hi, __nv_bfloat16 *lo, size_t o) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+__device__ __forceinline__ void split_store(float v, plane_t *hi, plane_t *lo, size_t o) {
+    const plane_t h = to_plane(v);
     hi[o] = h;
-    lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    lo[o] = to_plane_lo(v - plane_to_float(h));
 }
 
 // NCHW fp32 (n,C,H,W) -> NHWC split planes at channel offset `off` of a tensor with `ld` channels (+ optional fp32 NHWC copy).
-__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi,
-                                                                 __nv_bfloat16 *__restrict__ lo, float *__restrict__ f32, int C,
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(const float *__restrict__ x, plane_t *__restrict__ hi,
+                                                                 plane_t *__restrict__ lo, float *__restrict__ f32, int C,
                                                                  int HW, int ld, int off, int f32_ld, int f32_off) {
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(256) coords_add_kernel(float *__restrict__ coo
 // tensor.  One thread = one (pixel, tap): consecutive threads write consecutive 4-byte (fx, fy) pairs.
 // idx_t = unsigned for every realistic size (32-bit divisions; the 64-bit ones made this kernel instruction-bound).
 template <typename idx_t>
-__global__ void __launch_bounds__(256) flow_im2col_kernel(const float *__restrict__ coords1, __nv_bfloat16 *__restrict__ col_hi,
-                                                          __nv_bfloat16 *__restrict__ col_lo, int col_ld, __nv_bfloat16 *__restrict__ x_hi,
-                                                          __nv_bfloat16 *__restrict__ x_lo, int x_ld, int x_off, int h, int w,
+__global__ void __launch_bounds__(256) flow_im2col_kernel(const float *__restrict__ coords1, plane_t *__restrict__ col_hi,
+                                                          plane_t *__restrict__ col_lo, int col_ld, plane_t *__restrict__ x_hi,
+                                                          plane_t *__restrict__ x_lo, int x_ld, int x_off, int h, int w,
                                                           long long total) {
     const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
     if ((long long)i >= total) return;
@@ -94,15 +94,15 @@ __global__ void __launch_bounds__(256) flow_im2col_kernel(const float *__restric
         fx = __ldg(c1 + yy * w + xx) - (float)xx;
         fy = __ldg(c1 + hw + yy * w + xx) - (float)yy;
     }
-    const __nv_bfloat16 hx = __float2bfloat16_rn(fx), hy = __float2bfloat16_rn(fy);
-    const __nv_bfloat162 hi2 = __halves2bfloat162(hx, hy);
-    const __nv_bfloat162 lo2 = __halves2bfloat162(__float2bfloat16_rn(fx - __bfloat162float(hx)), __float2bfloat16_rn(fy - __bfloat162float(hy)));
+    const plane_t hx = to_plane(fx), hy = to_plane(fy);
+    const plane2_t hi2 = __halves2half2(hx, hy);
+    const plane2_t lo2 = __halves2half2(to_plane_lo(fx - plane_to_float(hx)), to_plane_lo(fy - plane_to_float(hy)));
     const size_t o = (size_t)pix * col_ld + tap * 2;
-    *reinterpret_cast<__nv_bfloat162 *>(col_hi + o) = hi2;
-    *reinterpret_cast<__nv_bfloat162 *>(col_lo + o) = lo2;
+    *reinterpret_cast<plane2_t *>(col_hi + o) = hi2;
+    *reinterpret_cast<plane2_t *>(col_lo + o) = lo2;
     if (tap == 24) {
-        *reinterpret_cast<__nv_bfloat162 *>(x_hi + (size_t)pix * x_ld + x_off) = hi2;
-        *reinterpret_cast<__nv_bfloat162 *>(x_lo + (size_t)pix * x_ld + x_off) = lo2;
+        *reinterpret_cast<plane2_t *>(x_hi + (size_t)pix * x_ld + x_off) = hi2;
+        *reinterpret_cast<plane2_t *>(x_lo + (size_t)pix * x_ld + x_off) = lo2;
     }
 }
 
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(256) flow_im2col_kernel(const float *__restric
 //   mode 0: rh = r * h                  -> split planes (conv input of the candidate state)
 //   mode 1: h  = (1 - z) * h + z * q    -> fp32 h (in place) + split planes
 __global__ void __launch_bounds__(256) gru_gate_kernel(const float *__restrict__ zr, float *__restrict__ h, const float *__restrict__ q,
-                                                       __nv_bfloat16 *__restrict__ o_hi, __nv_bfloat16 *__restrict__ o_lo, int o_ld,
+                                                       plane_t *__restrict__ o_hi, plane_t *__restrict__ o_lo, int o_ld,
                                                        int o_off, size_t npix, int mode) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // one thread = 4 channels of one pixel
     if (i >= npix * 32) return;
@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(256) gru_gate_kernel(const float *__restrict__
         o[3] = (1.0f - z.w) * hv.w + z.w * qv.w;
         *reinterpret_cast<float4 *>(h + pix * 128 + c) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    __nv_bfloat16 hh[4], ll[4];
+    plane_t hh[4], ll[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        hh[k] = __float2bfloat16_rn(o[k]);
-        ll[k] = __float2bfloat16_rn(o[k] - __bfloat162float(hh[k]));
+        hh[k] = to_plane(o[k]);
+        ll[k] = to_plane_lo(o[k] - plane_to_float(hh[k]));
     }
     *reinterpret_cast<uint2 *>(o_hi + pix * o_ld + o_off + c) = *reinterpret_cast<uint2 *>(hh);
     *reinterpret_cast<uint2 *>(o_lo + pix * o_ld + o_off + c) = *reinterpret_cast<uint2 *>(ll);
@@ -177,7 +177,7 @@ int rpe_nchw_to_nhwc_split(const float *x, void *hi, void *lo, float *f32, int n
     if (!x || (!hi && !f32) || ((hi == nullptr) != (lo == nullptr)) || n <= 0 || C <= 0 || H <= 0 || W <= 0) return RPE_ERR_INVALID_ARG;
     const int HW = H * W;
     dim3 grid((HW + 31) / 32, (C + 31) / 32, n);
-    rpe::nchw_to_nhwc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16 *)hi, (__nv_bfloat16 *)lo, f32, C, HW, ld, off,
+    rpe::nchw_to_nhwc_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (rpe::plane_t *)hi, (rpe::plane_t *)lo, f32, C, HW, ld, off,
                                                                           f32_ld, f32_off);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
@@ -205,11 +205,11 @@ int rpe_flow_step(float *coords1, const float *delta, int delta_ld, void *col_hi
     const long long total = (long long)n * h * w * 49;
     if (total + 256 < (1ll << 32))
         rpe::flow_im2col_kernel<unsigned><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
+            coords1, (rpe::plane_t *)col_hi, (rpe::plane_t *)col_lo, col_ld, (rpe::plane_t *)x_hi, (rpe::plane_t *)x_lo, x_ld, x_off, h, w,
             total);
     else
         rpe::flow_im2col_kernel<unsigned long long><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            coords1, (__nv_bfloat16 *)col_hi, (__nv_bfloat16 *)col_lo, col_ld, (__nv_bfloat16 *)x_hi, (__nv_bfloat16 *)x_lo, x_ld, x_off, h, w,
+            coords1, (rpe::plane_t *)col_hi, (rpe::plane_t *)col_lo, col_ld, (rpe::plane_t *)x_hi, (rpe::plane_t *)x_lo, x_ld, x_off, h, w,
             total);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
@@ -229,8 +229,8 @@ int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *
                  int mode, void *stream) {
     if (!zr || !h || !out_hi || !out_lo || npix <= 0 || (mode == 1 && !q) || (out_ld % 4) || (out_off % 4)) return RPE_ERR_INVALID_ARG;
     const size_t threads = (size_t)npix * 32;
-    rpe::gru_gate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(zr, h, q, (__nv_bfloat16 *)out_hi,
-                                                                                             (__nv_bfloat16 *)out_lo, out_ld, out_off,
+    rpe::gru_gate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(zr, h, q, (rpe::plane_t *)out_hi,
+                                                                                             (rpe::plane_t *)out_lo, out_ld, out_off,
                                                                                              (size_t)npix, mode);
     RPE_LAUNCH_CHECK();
     return RPE_OK;

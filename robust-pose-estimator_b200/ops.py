@@ -9,10 +9,10 @@ from . import _lib
 from ._lib import RpeError, check
 
 __all__ = ["depth_proj", "proj", "warp8_mask", "downsample8_cat", "pose_solve", "PoseSolution", "CorrPyramid",
-           "mask_specularities", "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3", "CORR_BF16X3"]
+           "mask_specularities", "SOLVER_LBFGS_REF", "SOLVER_GN", "SOLVER_EVAL_ONLY", "CORR_TF32", "CORR_TF32X3", "CORR_F16X3"]
 
 SOLVER_LBFGS_REF, SOLVER_GN, SOLVER_EVAL_ONLY = _lib.SOLVER_LBFGS_REF, _lib.SOLVER_GN, _lib.SOLVER_EVAL_ONLY
-CORR_TF32, CORR_TF32X3, CORR_BF16X3 = _lib.CORR_TF32, _lib.CORR_TF32X3, _lib.CORR_BF16X3
+CORR_TF32, CORR_TF32X3, CORR_F16X3 = _lib.CORR_TF32, _lib.CORR_TF32X3, _lib.CORR_F16X3
 
 
 def _stream():
@@ -259,7 +259,7 @@ def pose_solve(flow, pcl1, pcl2, w1, w2, m1, m2, K, lw, mode=SOLVER_LBFGS_REF, m
     if init_pose is not None:
         _chk(init_pose, torch.float64, "init_pose", (n, 7))
     dev = flow.device
-    out = torch.zeros((n, _lib.POSE_OUT_STRIDE), dtype=torch.float64, device=dev)
+    out = torch.empty((n, _lib.POSE_OUT_STRIDE), dtype=torch.float64, device=dev)      # the kernel writes every field it defines
     pose32 = torch.empty((n, 7), dtype=torch.float32, device=dev)
     log32 = torch.empty((n, 6), dtype=torch.float32, device=dev)
     trace = torch.zeros((n, trace_cap, 16), dtype=torch.float64, device=dev) if trace_cap > 0 else None
@@ -297,6 +297,25 @@ class CorrPyramid:
                                    C.c_void_p(ws_ptr), self._ws.numel() - (ws_ptr - self._ws.data_ptr()), _stream()),
                   "rpe_corr_build")
 
+    @classmethod
+    def from_planes(cls, f1, f2, B, num_levels=4, radius=4, f1_wrap=0, f1_sub=0):
+        """rpe_corr_build_planes: the volume + pooled pyramid of B samples from feature maps that already are NHWC split planes
+        (tc.Planes views over an image list): sample s correlates f1 image (s < f1_wrap ? s : s - f1_sub) with f2 image s."""
+        self = cls.__new__(cls)
+        _, h, w, Cc = f1.shape
+        self.B, self.C, self.h, self.w = B, Cc, h, w
+        self.num_levels, self.radius = num_levels, radius
+        l = _lib.lib()
+        self.pyramid = torch.empty(l.rpe_corr_pyramid_bytes(B, h, w, num_levels) // 4, dtype=torch.float32, device=f1.hi.device)
+        self._ws = None
+        n_f1 = (B if f1_wrap <= 0 else max(f1_wrap, B - f1_sub))
+        if f1.shape[0] < n_f1 or f2.shape[0] < B or tuple(f2.shape[1:]) != tuple(f1.shape[1:]):
+            raise RpeError(f"corr planes: f1 {tuple(f1.shape)} / f2 {tuple(f2.shape)} too small for {B} samples (wrap {f1_wrap}, sub {f1_sub})")
+        with _timed("corr_build", B):
+            check(l.rpe_corr_build_planes(_p(f1.hi), _p(f1.lo), _p(f2.hi), _p(f2.lo), _p(self.pyramid), B, Cc, h, w, num_levels,
+                                          int(f1_wrap), int(f1_sub), _stream()), "rpe_corr_build_planes")
+        return self
+
     def level(self, l):
         """View of pyramid level l as (B*h*w, 1, h>>l, w>>l) like the reference's corr_pyramid[l]."""
         off = _lib.lib().rpe_corr_level_offset(self.B, self.h, self.w, l) // 4
@@ -315,11 +334,11 @@ class CorrPyramid:
 
 
 def corr_lookup_planes(pyr, coords, planes):
-    """rpe_corr_lookup_nhwc_bf16: CorrBlock.__call__ written as NHWC bf16 hi/lo planes (tc.Planes with >= 324 channels)."""
+    """rpe_corr_lookup_nhwc_split: CorrBlock.__call__ written as NHWC bf16 hi/lo planes (tc.Planes with >= 324 channels)."""
     _chk(coords, torch.float32, "coords", (pyr.B, 2, pyr.h, pyr.w))
     with _timed("corr_lookup", pyr.B):
-        check(_lib.lib().rpe_corr_lookup_nhwc_bf16(_p(pyr.pyramid), _p(coords), _p(planes.hi), _p(planes.lo), planes.c, pyr.B, pyr.h, pyr.w,
-                                                   pyr.num_levels, pyr.radius, _stream()), "rpe_corr_lookup_nhwc_bf16")
+        check(_lib.lib().rpe_corr_lookup_nhwc_split(_p(pyr.pyramid), _p(coords), _p(planes.hi), _p(planes.lo), planes.c, pyr.B, pyr.h, pyr.w,
+                                                   pyr.num_levels, pyr.radius, _stream()), "rpe_corr_lookup_nhwc_split")
     return planes
 
 
@@ -334,9 +353,9 @@ def convex_upsample8(flow, mask):
     return out
 
 
-def conv2d_bf16x3(x, weight, bias=None, activation="none", scale=1.0, stride=1, pre=None, res=None, single_pass=False):
+def conv2d_f16x3(x, weight, bias=None, activation="none", scale=1.0, stride=1, pre=None, res=None, single_pass=False):
     """Convolution ('same'-style padding k//2, stride 1 or 2) of an NCHW fp32 tensor on the tcgen05 implicit-GEMM kernel with
-    bf16x3 error compensation (rpe_conv_plan_*).  ``pre`` / ``res``: optional NCHW fp32 addend before the activation / residual
+    fp16x3 error compensation (rpe_conv_plan_*).  ``pre`` / ``res``: optional NCHW fp32 addend before the activation / residual
     after it (out = relu(act(v) * scale + res)).  Convenience / test entry: it re-packs weights and activations on every call;
     the RAFT trunk keeps persistent plans instead (core/RAFT/core/update_tc.py, encoder_tc.py)."""
     from . import tc
@@ -353,7 +372,7 @@ def conv2d_bf16x3(x, weight, bias=None, activation="none", scale=1.0, stride=1, 
     out = torch.zeros((n, OH, OW, ld), dtype=torch.float32, device=x.device)
     nhwc = lambda t: None if t is None else torch.nn.functional.pad(t.permute(0, 2, 3, 1), (0, ld - cout)).contiguous()
     b = None if bias is None else bias.float().contiguous()
-    plan = tc.ConvPlan("conv2d_bf16x3", [(planes, 0, cin, wts)], (n, H, W), kh, kw, cout, activation, bias=b, stride=stride,
+    plan = tc.ConvPlan("conv2d_f16x3", [(planes, 0, cin, wts)], (n, H, W), kh, kw, cout, activation, bias=b, stride=stride,
                        out_f32=out, scale=float(scale), pre=nhwc(pre), res=nhwc(res), single_pass=single_pass)
     plan.run()
     res_t = tc.nhwc_to_nchw(out, cout)

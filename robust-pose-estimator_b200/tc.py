@@ -1,4 +1,4 @@
-"""Plumbing of the tcgen05 convolution plans (csrc/conv.cu, include/rpe_b200.h ``rpe_conv_plan_*``): NHWC bf16 split planes,
+"""Plumbing of the tcgen05 convolution plans (csrc/conv.cu, include/rpe_b200.h ``rpe_conv_plan_*``): NHWC fp16 split planes,
 weight packing, and a plan object that keeps every buffer it points to alive.  No arithmetic happens here."""
 import ctypes as C
 
@@ -10,34 +10,72 @@ from .ops import _p, _stream, _timed, check
 ACT = {"none": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 
 
-def split_bf16(t):
-    """fp32 tensor -> (hi, lo) bf16 with hi + lo == t to 16 mantissa bits."""
-    hi = t.to(torch.bfloat16)
-    lo = (t - hi.float()).to(torch.bfloat16)
+PLANE_DTYPE = torch.float16          # both planes fp16: hi = fp16(v), lo = fp16(v - hi)
+PLANE_LO_DTYPE = torch.float16
+PLANE_MAX = 65504.0
+
+
+def split_planes(t):
+    """fp32 tensor -> (hi, lo) fp16 planes with hi + lo == t to 22 significant bits while |t| >= 2^-3 (an absolute 2^-25 below:
+    the lo plane turns subnormal); saturating like the kernels' conversions."""
+    hi = t.clamp(-PLANE_MAX, PLANE_MAX).to(PLANE_DTYPE)
+    lo = (t - hi.float()).clamp(-PLANE_MAX, PLANE_MAX).to(PLANE_LO_DTYPE)
     return hi.contiguous(), lo.contiguous()
 
 
-def pack_weight(w, c_lo, c_hi, cout_pad):
-    """(Cout, Cin, kh, kw) fp32 -> the channel window [c_lo, c_hi) as [taps][cout_pad][c_pad64] hi / lo planes."""
+def weight_scale(w):
+    """Power of two that lifts a weight tensor (typically O(0.01)) to max |w| in [2^12, 2^13): the fp16 lo plane of all but
+    vanishing weights is then a normal number, i.e. the packed weights keep 22 significant bits.  The convolution multiplies its
+    accumulators by the inverse (rpe_conv_desc.acc_scale); powers of two make both steps exact."""
+    m = float(w.detach().abs().max())
+    if not (m > 0.0) or m != m:
+        return 1.0
+    import math
+    return 2.0 ** max(-20, min(24, 12 - math.floor(math.log2(m)) - 1))
+
+
+def pack_weight(w, c_lo, c_hi, cout_pad, scale=None):
+    """(Cout, Cin, kh, kw) fp32 -> the channel window [c_lo, c_hi) as [taps][cout_pad][c_pad64] planes (hi, lo, 1 / scale) of
+    scale * w.  ``scale``: a power of two shared by every window of the same convolution (default: weight_scale of this tensor)."""
     cout, _, kh, kw = w.shape
+    if scale is None:
+        scale = weight_scale(w)
     cs = c_hi - c_lo
     cpad = (cs + 63) // 64 * 64
     out = torch.zeros((kh * kw, cout_pad, cpad), dtype=torch.float32, device=w.device)
-    out[:, :cout, :cs] = w[:, c_lo:c_hi].permute(2, 3, 0, 1).reshape(kh * kw, cout, cs)
-    return split_bf16(out)
+    out[:, :cout, :cs] = w[:, c_lo:c_hi].permute(2, 3, 0, 1).reshape(kh * kw, cout, cs) * scale
+    hi, lo = split_planes(out)
+    return hi, lo, 1.0 / scale
 
 
 class Planes:
-    """NHWC bf16 split planes (hi, lo) of shape (N, H, W, C); channels are zero-initialised so padded channels read as 0."""
+    """NHWC fp16 split planes (hi, lo) of shape (N, H, W, C); channels are zero-initialised so padded channels read as 0."""
 
     def __init__(self, n, h, w, c, device):
-        self.hi = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
-        self.lo = torch.zeros((n, h, w, c), dtype=torch.bfloat16, device=device)
+        self.hi = torch.zeros((n, h, w, c), dtype=PLANE_DTYPE, device=device)
+        self.lo = torch.zeros((n, h, w, c), dtype=PLANE_LO_DTYPE, device=device)
         self.c = c
         self.shape = (n, h, w, c)
 
     def float(self):
         return self.hi.float() + self.lo.float()
+
+    def view(self, a, b=None):
+        """Planes of the images [a, b) without copying (a contiguous slice along the batch axis)."""
+        v = Planes.__new__(Planes)
+        v.hi, v.lo, v.c = self.hi[a:b], self.lo[a:b], self.c
+        v.shape = tuple(v.hi.shape)
+        return v
+
+    def copy_(self, other):
+        self.hi.copy_(other.hi)
+        self.lo.copy_(other.lo)
+        return self
+
+    def clone(self):
+        v = Planes.__new__(Planes)
+        v.hi, v.lo, v.c, v.shape = self.hi.clone(), self.lo.clone(), self.c, self.shape
+        return v
 
 
 class ConvPlan:
@@ -56,7 +94,10 @@ class ConvPlan:
             d.aux, d.aux_ld = aux.data_ptr(), aux.shape[-1]
         if aux2 is not None:
             d.aux2, d.aux2_ld = aux2.data_ptr(), aux2.shape[-1]
-        for k, (planes, c_off, c_cnt, (w_hi, w_lo)) in enumerate(inputs):
+        inv_scales = {float(wt[2]) for _, _, _, wt in inputs}
+        assert len(inv_scales) == 1, f"{name}: the sources of one convolution must share the weight scale, got {sorted(inv_scales)}"
+        d.acc_scale = inv_scales.pop()
+        for k, (planes, c_off, c_cnt, (w_hi, w_lo, _)) in enumerate(inputs):
             assert planes.shape[1:3] == (h, w) and planes.shape[0] >= n, f"{name}: source {k} has shape {planes.shape}, expected {(n, h, w)}"
             assert w_hi.shape[1] == cout_pad, f"{name}: weight packed for cout_pad {w_hi.shape[1]}, plan needs {cout_pad}"
             s = d.src[k]

@@ -55,10 +55,10 @@ def _epe(a, b):
     return np.sqrt(((a - b) ** 2).sum(0))
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 @pytest.mark.parametrize("name", ["e2e_384x352", "full_640x512"])
 def test_tracker_matches_reference(golden_dir, name, precision):
-    """Both parity-grade modes: fp32 (cuDNN fp32 trunk) and bf16x3 (update operator on the tcgen05 kernels)."""
+    """Both parity-grade modes: fp32 (cuDNN fp32 trunk) and fp16x3 (update operator on the tcgen05 kernels)."""
     _need_ckpt()
     path = os.path.join(golden_dir, "e2e_384x352.npz") if name == "e2e_384x352" else FULL
     if not os.path.isfile(path):
@@ -177,7 +177,7 @@ def test_gauss_newton_solver_mode(golden_dir):
     assert rot < 5e-3 and trans < 5e-2
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_graphed_streaming_tracker_matches_reference(golden_dir, precision):
     """config['cuda_graph']: PoseEstimator.forward replays one captured CUDA graph per frame (latency path).  Same trajectory
     as the reference, and as the eager per-frame tracker, frame by frame; a second sequence on the same estimator re-uses
@@ -214,7 +214,7 @@ def test_infer_sequence_from_pinned_host_frames(golden_dir):
     from rpe_b200.lie import SE3
     g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
     W, H = [int(v) for v in g["size"]]
-    est = PoseEstimator(dict(SLAM, precision="bf16x3"), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    est = PoseEstimator(dict(SLAM, precision="fp16x3"), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
     idx = [0, 1, 2, 1, 0, 2]
     L8 = torch.from_numpy(np.clip(np.round(g["imgs_l"]), 0, 255).astype(np.uint8))[idx].contiguous().pin_memory()
     R8 = torch.from_numpy(np.clip(np.round(g["imgs_r"]), 0, 255).astype(np.uint8))[idx].contiguous().pin_memory()
@@ -225,8 +225,8 @@ def test_infer_sequence_from_pinned_host_frames(golden_dir):
     assert got.shape == (6, 7) and torch.equal(got, ref) and torch.equal(failed, failed_ref)
 
 
-@pytest.mark.parametrize("chunk,graphs,precision", [(1, False, "fp32"), (2, False, "fp32"), (2, True, "fp32"), (2, False, "bf16x3"),
-                                                    (3, True, "bf16x3")])
+@pytest.mark.parametrize("chunk,graphs,precision", [(1, False, "fp32"), (2, False, "fp32"), (2, True, "fp32"), (2, False, "fp16x3"),
+                                                    (3, True, "fp16x3")])
 def test_batched_engine_matches_reference(golden_dir, chunk, graphs, precision):
     """PoseEstimator.infer_sequence (chunked engine, feature reuse, optional CUDA graph, host composition through
     rpe_compose_trajectory_host) reproduces the reference trajectory."""

@@ -1,4 +1,4 @@
-"""GPU: the tcgen05 implicit-GEMM convolution (bf16x3) and the tensor-core RAFT update operator against torch fp32
+"""GPU: the tcgen05 implicit-GEMM convolution (fp16x3) and the tensor-core RAFT update operator against torch fp32
 convolutions (test-only reference of a floating-point kernel) and against the reference tracker's golden outputs."""
 import os
 
@@ -36,7 +36,7 @@ def dev(a):
     (256, 576, 1, 1, 64, 80, "none"),       # mask head: three N blocks of 192
     (98, 128, 1, 1, 64, 80, "relu"),        # im2col'ed 7x7 flow convolution
 ])
-def test_conv_bf16x3_vs_torch_fp32(ops, cin, cout, kh, kw, H, W, act):
+def test_conv_fp16x3_vs_torch_fp32(ops, cin, cout, kh, kw, H, W, act):
     n = 2
     x = dev(det_uniform((n, cin, H, W), 101, -2.0, 2.0))
     w = dev(det_uniform((cout, cin, kh, kw), 102, -1.0, 1.0)) * (1.0 / np.sqrt(cin * kh * kw))
@@ -44,7 +44,7 @@ def test_conv_bf16x3_vs_torch_fp32(ops, cin, cout, kh, kw, H, W, act):
     with torch.backends.cudnn.flags(enabled=True, benchmark=False, deterministic=False, allow_tf32=False):
         ref = F.conv2d(x.double(), w.double(), b.double(), padding=(kh // 2, kw // 2))
     ref = {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](ref).float()
-    got = ops.conv2d_bf16x3(x, w, b, activation=act)
+    got = ops.conv2d_f16x3(x, w, b, activation=act)
     err = (got - ref).abs().max().item()
     print(f"conv {cin}->{cout} {kh}x{kw} {act}: max abs err {err:.2e} (|ref| max {ref.abs().max().item():.2f})")
     assert err < 3e-5 * max(1.0, ref.abs().max().item())
@@ -63,7 +63,7 @@ def test_conv_strided_and_partial_blocks(ops, cin, cout, k, stride, H, W):
     w = dev(det_uniform((cout, cin, k, k), 112, -1.0, 1.0)) * (1.0 / np.sqrt(cin * k * k))
     b = dev(det_uniform((cout,), 113, -0.5, 0.5))
     ref = F.conv2d(x.double(), w.double(), b.double(), stride=stride, padding=k // 2).float()
-    got = ops.conv2d_bf16x3(x, w, b, stride=stride)
+    got = ops.conv2d_f16x3(x, w, b, stride=stride)
     assert got.shape == ref.shape
     err = (got - ref).abs().max().item()
     print(f"conv {cin}->{cout} {k}x{k}/{stride}: max abs err {err:.2e}")
@@ -140,10 +140,10 @@ def test_conv_addend_residual_and_single_pass(ops):
     res = dev(det_uniform((n, cout, H, W), 125, -1.0, 1.0))
     conv = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     ref = torch.relu(torch.tanh(conv + pre.double()) + res.double()).float()
-    got = ops.conv2d_bf16x3(x, w, b, activation="tanh", pre=pre, res=res)
+    got = ops.conv2d_f16x3(x, w, b, activation="tanh", pre=pre, res=res)
     assert (got - ref).abs().max().item() < 3e-5
     # single-pass bf16 (no compensation): only bf16-level agreement is expected
-    got1 = ops.conv2d_bf16x3(x, w, b, single_pass=True)
+    got1 = ops.conv2d_f16x3(x, w, b, single_pass=True)
     err1 = (got1 - conv.float()).abs().max().item()
     print(f"single-pass bf16 conv: max abs err {err1:.2e}")
     assert 1e-5 < err1 < 5e-2
@@ -158,7 +158,7 @@ def test_update_operator_vs_torch_trunk(ops):
     g = np.load(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz"))
     ck = torch.load(CKPT, map_location="cpu", weights_only=False)
     outs = {}
-    for prec in ("fp32", "bf16x3"):
+    for prec in ("fp32", "fp16x3"):
         cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision=prec)
         model = PoseNet(cfg)
         model.load_state_dict(ck["state_dict"])
@@ -167,12 +167,12 @@ def test_update_operator_vs_torch_trunk(ops):
         i2 = torch.cat((dev(g["imgs_l"][2:3].astype(np.float32)), dev(g["imgs_r"][2:3].astype(np.float32))))
         preds, net, inp = model.flow(i1, i2)
         outs[prec] = (preds[-1].clone(), net.clone())
-    epe = (outs["fp32"][0] - outs["bf16x3"][0]).pow(2).sum(1).sqrt()
-    print(f"bf16x3 update operator vs fp32 trunk: flow EPE mean {epe.mean().item():.2e} max {epe.max().item():.2e}; "
-          f"hidden state max diff {(outs['fp32'][1] - outs['bf16x3'][1]).abs().max().item():.2e}")
+    epe = (outs["fp32"][0] - outs["fp16x3"][0]).pow(2).sum(1).sqrt()
+    print(f"fp16x3 update operator vs fp32 trunk: flow EPE mean {epe.mean().item():.2e} max {epe.max().item():.2e}; "
+          f"hidden state max diff {(outs['fp32'][1] - outs['fp16x3'][1]).abs().max().item():.2e}")
     assert epe.mean().item() < 2e-4 and epe.max().item() < 5e-3
     ref = dev(np.stack((g["s_time_flow"],)))
-    epe_ref = (outs["bf16x3"][0][0:1] - ref).pow(2).sum(1).sqrt()
+    epe_ref = (outs["fp16x3"][0][0:1] - ref).pow(2).sum(1).sqrt()
     assert epe_ref.mean().item() < 1e-2                                    # north-star flow gate vs the reference itself
 
 
@@ -221,7 +221,7 @@ def test_update_operator_fused_vs_plain_flow_head(ops, monkeypatch):
     outs = {}
     for flag in ("1", "0"):
         monkeypatch.setenv("RPE_FUSED_FLOW_HEAD", flag)
-        cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision="bf16x3")
+        cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision="fp16x3")
         model = PoseNet(cfg)
         model.load_state_dict(ck["state_dict"])
         model = model.cuda().eval()
@@ -245,14 +245,14 @@ def test_encoder_tc_vs_torch_fp32(ops, which):
     ck = torch.load(CKPT, map_location="cpu", weights_only=False)
     imgs = torch.cat((dev(g["imgs_l"][0:2].astype(np.float32)), dev(g["imgs_r"][0:1].astype(np.float32))))
     outs = {}
-    for prec in ("fp32", "bf16x3"):
+    for prec in ("fp32", "fp16x3"):
         cfg = dict(ck["config"]["model"], image_shape=(512, 640), lbgfs_iters=20, use_weights=True, precision=prec)
         model = PoseNet(cfg)
         model.load_state_dict(ck["state_dict"])
         raft = model.cuda().eval().flow
         with torch.no_grad():
             outs[prec] = (raft.features(imgs),) if which == "fnet" else raft.context(imgs)
-    for a, b in zip(outs["fp32"], outs["bf16x3"]):
+    for a, b in zip(outs["fp32"], outs["fp16x3"]):
         assert a.shape == b.shape
         err = (a - b).abs().max().item()
         print(f"{which}: max abs diff {err:.2e} (|ref| max {a.abs().max().item():.2f}, mean {a.abs().mean().item():.3f})")

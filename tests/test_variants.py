@@ -75,7 +75,7 @@ def test_oracle_tracker_nw_matches_reference():
 # GPU
 # ---------------------------------------------------------------------------------------------------------------
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_gpu_nw_trajectory_and_freiburg(tmp_path, precision):
     """Per-frame tracker and the batched engine on the nw configuration; trajectory.freiburg within the pose gate."""
     ckpt = os.path.join(TRAINED, "poseNet_2xf8up4b.pth")
@@ -115,7 +115,7 @@ def test_gpu_nw_trajectory_and_freiburg(tmp_path, precision):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
 def test_gpu_only3d_1280x1024(precision):
     """Config 4: only3d checkpoint, 3-D residual only, full-resolution 1280x1024 stereo."""
     ckpt = os.path.join(TRAINED, "only3d_1a7ix98y.pth")
@@ -143,5 +143,5 @@ def test_gpu_only3d_1280x1024(precision):
     # The frame-to-frame translation of this pair is 0.27 mm, so 1e-4 relative is 27 nm; the 3-D-only objective at 1.3 Mpx
     # turns the 2e-5 px flow difference between cuDNN and oneDNN fp32 convolutions (summation order) into 1.06e-4 relative
     # (2.8e-5 mm absolute; measured on B200, profiles/r1_s6_pytest_gpu.log).  Configs 1-3 and 5 keep the 1e-4 gate.
-    # The product precision (bf16x3) keeps the north-star gate; only the cuDNN fp32 debugging mode carries the slack below.
-    assert rot < 1e-4 and trans < (1e-4 if precision == "bf16x3" else 2e-4) and np.linalg.norm(p[:3] - g["traj"][1][:3]) < 1e-4
+    # The product precision (fp16x3) keeps the north-star gate; only the cuDNN fp32 debugging mode carries the slack below.
+    assert rot < 1e-4 and trans < (1e-4 if precision == "fp16x3" else 2e-4) and np.linalg.norm(p[:3] - g["traj"][1][:3]) < 1e-4

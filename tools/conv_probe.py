@@ -1,5 +1,5 @@
 """CUDA-event timing of the tcgen05 convolution plans at the shapes of the RAFT trunk (one chunk = 16 RAFT samples at 64x80,
-24 encoder images).  Prints effective TFLOP/s (useful flops x3 for the bf16x3 split) per shape."""
+24 encoder images).  Prints effective TFLOP/s (useful flops x3 for the fp16x3 split) per shape."""
 import os
 import sys
 
@@ -49,7 +49,7 @@ def main():
             pl = tc.Planes(n, h, w, (cin + 15) // 16 * 16, dev)
             pl.hi.normal_()
             pl.lo.normal_(std=1e-3)
-            wt = tc.pack_weight(torch.randn(cout, cin, kh, kw, device=dev) / (cin * kh * kw) ** 0.5, 0, cin, cout_pad)
+            wt = tc.pack_weight(torch.randn(cout, cin, kh, kw, device=dev) / (cin * kh * kw) ** 0.5, 0, cin, cout_pad, scale=1024.0)
             srcs.append((pl, 0, cin, wt))
         oh, ow = (h + 2 * (kh // 2) - kh) // stride + 1, (w + 2 * (kw // 2) - kw) // stride + 1
         outp = tc.Planes(n, oh, ow, cout_pad, dev)

@@ -26,42 +26,64 @@ def planes(t, dtype, n):
         return t
     acc = torch.zeros_like(t)
     r = t
-    for _ in range(n):
-        p = r.to(dtype).float()
+    for k in range(n):
+        p = r.to(dtype[k] if isinstance(dtype, tuple) else dtype).float()
         acc = acc + p
         r = t - acc
     return acc
 
 
-def run(golden, act, wgt):
-    """act, wgt: (dtype, n_planes)."""
-    g = np.load(golden)
+def run(golden, act, wgt, corr=None, only_layers=None):
+    """act, wgt: (dtype, n_planes).  corr: (dtype, n_planes) rounding of the feature maps entering the all-pairs correlation
+    (None = fp32 matmul).  only_layers: substring filter -- only convolutions whose name contains one of them are rounded."""
+    g = dict(np.load(golden))
     W, H = [int(v) for v in g["size"]]
+    if "order" in g:                                   # config-1 fixture golden: two distinct frames + the frame order, masks all true
+        order = [int(k) for k in g["order"]]
+        g["imgs_l"], g["imgs_r"] = g["imgs_l"][order], g["imgs_r"][order]
+        g["masks_in"] = np.stack([np.packbits(np.ones(H * W, bool))] * len(order))
+        g["s_time_flow"] = None
+    sel = (lambda name: True) if not only_layers else (lambda name: any(t in name for t in only_layers))
     sd = torch.load(os.path.join(ROOT, "oracle", "_ref", "trained", "poseNet_2xf8up4b.pth"), map_location="cpu", weights_only=False)["state_dict"]
     sd = {k: v.clone() for k, v in sd.items()}
     for k in sd:
-        if k.startswith("flow.") and k.endswith(".weight") and sd[k].dim() == 4:
+        if k.startswith("flow.") and k.endswith(".weight") and sd[k].dim() == 4 and sel(k):
             sd[k] = planes(sd[k].float(), *wgt)
     orig = pipeline_ref._conv
 
     def conv(x, sd_, name, stride=1, padding=0):
-        if name.startswith("flow."):
+        if name.startswith("flow.") and sel(name):
             x = planes(x, *act)
         return orig(x, sd_, name, stride, padding)
 
+    orig_pyr = pipeline_ref.corr_pyramid
+
+    def pyr(f1, f2, levels=4):
+        return orig_pyr(planes(f1, *corr), planes(f2, *corr), levels)
+
     pipeline_ref._conv = conv
+    if corr is not None:
+        pipeline_ref.corr_pyramid = pyr
     try:
         trk = pipeline_ref.RefTracker(sd, g["K"], float(g["bf"]))
         poses = [trk.step(torch.from_numpy(g["imgs_l"][i].astype(np.float32))[None], torch.from_numpy(g["imgs_r"][i].astype(np.float32))[None],
                           torch.from_numpy(unpack(g["masks_in"][i], (1, 1, H, W)))) for i in range(3)]
     finally:
         pipeline_ref._conv = orig
+        pipeline_ref.corr_pyramid = orig_pyr
     out = []
     for k in (1, 2):
         a, b = poses[k], g["traj"][k]
         d = se3_np.mul(se3_np.inv(a.astype(np.float64)), b.astype(np.float64))
         out.append((np.linalg.norm(se3_np.log(d)[3:]), np.linalg.norm(a[:3] - b[:3]) / max(np.linalg.norm(b[:3]), 1e-12)))
-    epe = np.sqrt(((trk.last["time_flow"][0].numpy() - g["s_time_flow"]) ** 2).sum(0))
+    if g["s_time_flow"] is None:
+        epe = np.sqrt(((trk.last["time_flow"][0, :, ::4, ::4].numpy() - g["s_time_flow_ds4"]) ** 2).sum(0))
+        # trajectory error of frame 2 is meaningless when the sequence returns to its start: report the per-pair relative pose
+        a, b = trk.last["rel"], g["rel_pose"][1]
+        d = se3_np.mul(se3_np.inv(a.astype(np.float64)), b.astype(np.float64))
+        out[1] = (np.linalg.norm(se3_np.log(d)[3:]), np.linalg.norm(a[:3] - b[:3]) / max(np.linalg.norm(b[:3]), 1e-12))
+    else:
+        epe = np.sqrt(((trk.last["time_flow"][0].numpy() - g["s_time_flow"]) ** 2).sum(0))
     return out, epe.mean(), epe.max()
 
 
@@ -69,12 +91,15 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--golden", default=os.path.join(ROOT, "tests", "golden", "e2e_384x352.npz"))
     ap.add_argument("--only", default="")
+    ap.add_argument("--corr", action="store_true", help="also round the feature maps of the correlation to 2 bf16 planes")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     bf, fh, f32 = torch.bfloat16, torch.float16, torch.float32
     variants = {
         "fp32 (oracle itself)": ((f32, 0), (f32, 0)),
         "bf16x3: act 2 x bf16, wgt 2 x bf16": ((bf, 2), (bf, 2)),
+        "f16+bf16 x3: fp16 hi + bf16 lo planes": (((fh, bf), 2), ((fh, bf), 2)),
+        "fp16x3: act 2 x fp16, wgt 2 x fp16": ((fh, 2), (fh, 2)),
         "fp16x2: act 2 x fp16, wgt 1 x fp16": ((fh, 2), (fh, 1)),
         "fp16x2': act 1 x fp16, wgt 2 x fp16": ((fh, 1), (fh, 2)),
         "fp16x1: act 1 x fp16, wgt 1 x fp16": ((fh, 1), (fh, 1)),
@@ -84,5 +109,5 @@ if __name__ == "__main__":
     for name, (act, wgt) in variants.items():
         if a.only and a.only not in name:
             continue
-        errs, em, ex = run(a.golden, act, wgt)
+        errs, em, ex = run(a.golden, act, wgt, corr=(act[0], 2) if a.corr and act[1] else None)
         print(f"{name:40s} pose err (rot rad, rel trans): " + "  ".join(f"({r:.2e}, {t:.2e})" for r, t in errs) + f"   flow EPE mean {em:.2e} max {ex:.2e}", flush=True)

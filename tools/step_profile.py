@@ -1,5 +1,5 @@
 """Kernel-level time breakdown of one engine step (torch.profiler / CUPTI; no ncu replay cost).
-    python tools/step_profile.py [--precision bf16x3] [--pairs 16] [--chunk 8]"""
+    python tools/step_profile.py [--precision fp16x3] [--pairs 16] [--chunk 8]"""
 import argparse
 import collections
 import os
@@ -14,7 +14,7 @@ import bench  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--precision", default="bf16x3")
+    ap.add_argument("--precision", default="fp16x3")
     ap.add_argument("--pairs", type=int, default=16)
     ap.add_argument("--chunk", type=int, default=8)
     ap.add_argument("--top", type=int, default=45)
