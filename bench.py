@@ -5,7 +5,7 @@
 
 A step = one pass of the hot path over one batch of synthetic input: a 65-frame 640x512 stereo sequence
 (64 frame pairs) per rank (weak scaling; pairs are independent in f2f).
-  value  pairs/s with the frames resident in HBM (float32 0..255 like the reference's tensors), device-timed.
+  value  pairs/s with the frames resident in HBM (uint8 RGB as decoded), device-timed.
   e2e    pairs/s through PoseEstimator.infer_sequence with HOST buffers: pinned uint8 frames copied to the device
          and the poses copied back + composed into the trajectory inside the timed region.
 For N > 1 (torchrun) each rank owns a contiguous shard; the per-pair poses are all-gathered over NCCL inside the
@@ -327,7 +327,8 @@ def main():
         torch.cuda.synchronize()
 
     class Shard:
-        """This rank's frames of a `total_pairs`-pair sequence: pinned uint8 host copies and float32 device copies."""
+        """This rank's frames of a `total_pairs`-pair sequence: pinned uint8 host copies and uint8 device copies (the kernels
+        that read the image convert on load)."""
 
         def __init__(self, total_pairs):
             self.total = total_pairs
@@ -335,7 +336,7 @@ def main():
             fa, fb = parallel.frames_of((self.a, self.b))
             idx = frame_indices(fa, fb)
             self.h = [torch.from_numpy(np.ascontiguousarray(x[idx])).pin_memory() for x in (bL, bR, bM)]
-            self.d = [self.h[0].to(dev).float(), self.h[1].to(dev).float(), self.h[2].to(dev)]
+            self.d = [t.to(dev) for t in self.h]
             self.h2d = sum(t.numel() for t in self.h)
             self.pairs = self.b - self.a
             self.pending = None
@@ -472,7 +473,7 @@ def main():
         nwarm = 20
         order = frame_indices(0, args.latency_pairs + nwarm + 1)
         fL, fR, fM = (torch.from_numpy(np.ascontiguousarray(x)).to(dev) for x in (bL, bR, bM))
-        fL, fR = fL.float(), fR.float()
+        fL, fR = fL.float(), fR.float()                        # the per-frame API takes the reference's float32 0..255 tensors
 
         def run_leg():
             est.frame = est.last_frame = None
@@ -515,16 +516,28 @@ def main():
             traj, failed = parallel.infer_sequence_sharded(est5, load5, nf, chunk=args.chunk, use_graphs=args.graphs)
             if rank == 0:
                 save_trajectory_array(traj, list(range(nf)), outdir)
-            return failed
+            return failed, traj
         run5()                                               # warm-up (plans of the shard shapes)
         sync_all()
         t0 = time.perf_counter()
-        failed5 = run5()
+        failed5, traj5 = run5()
         sync_all()
         dt5 = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt5, op=dist.ReduceOp.MAX)
-        config5 = {"workload": "infer_f2f_nw (conf_weighing False, lbgfs_iters 20)", "frames": nf, "pairs": nf - 1, "n_gpus": world,
+        ate = None
+        if rank == 0:                                        # accuracy of the written trajectory against the renderer's ground truth
+            from rpe_b200.core.metrics.trajectory_metrics import absolute_trajectory_error, relative_pose_error
+            from rpe_b200.lie import SE3
+            gt = np.stack([np.block([[seq._extr[b][0].T, -seq._extr[b][0].T @ seq._extr[b][1][:, None]], [np.zeros((1, 3)), np.ones((1, 1))]])
+                           for b in frame_indices(0, nf)])
+            pred = SE3(traj5.double()).matrix().numpy()
+            ate_rmse, _ = absolute_trajectory_error(gt, pred)
+            rpe_t, rpe_r = relative_pose_error(gt, pred)
+            ate = {"ate_rmse_mm": float(ate_rmse), "rpe_trans_mm": float(rpe_t.mean()), "rpe_rot_rad": float(rpe_r.mean()),
+                   "path_length_mm": float(np.linalg.norm(np.diff(gt[:, :3, 3], axis=0), axis=1).sum()),
+                   "against": "camera poses of the synthetic renderer (core/metrics/trajectory_metrics.py, the reference's ATE / RPE)"}
+        config5 = {"workload": "infer_f2f_nw (conf_weighing False, lbgfs_iters 20)", "frames": nf, "pairs": nf - 1, "n_gpus": world, "accuracy": ate,
                    "seconds": float(dt5[0]), "pairs_per_s": (nf - 1) / float(dt5[0]), "failed_pairs": int(failed5.sum()),
                    "h2d_bytes_per_rank": int(sum(t.numel() for t in h5)),
                    "includes": "H2D of pinned uint8 frames, sharded solve, all_gather of (P,13) records, host composition, trajectory.freiburg write"}

@@ -85,6 +85,9 @@ int rpe_proj(const float *depth, const float *K, float *pcl, int rescale, float 
  * mask2 (n,1,H,W) u8 with  mask2w = (warped > 0) & warped.  Sampling coordinates follow the
  * reference's fp32 operation order exactly so that mask2w is bit-exact.
  * Any of the (src, dst) pairs may be NULL to skip that tensor. */
+int rpe_warp8_mask_u8(const float *pcl2, const unsigned char *img2, const float *sflow2, const uint8_t *mask2,
+                      const float *flow, float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w, int n,
+                      int H, int W, void *stream);      /* img2 as uint8 (n,3,H,W); img2w stays fp32 */
 int rpe_warp8_mask(const float *pcl2, const float *img2, const float *sflow2, const uint8_t *mask2,
                    const float *flow, float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w,
                    int n, int H, int W, void *stream);
@@ -167,6 +170,15 @@ int rpe_pose_solve(const rpe_pose_problem *problem_host, int mode, int max_iter,
  *   abs_out_host (n+1,7): init pose followed by the pose after every pair; failed_out_host (n) or NULL. */
 int rpe_compose_trajectory_host(const float *rel_host, const float *log_host, int n, const float *init_pose_host,
                                 float inv_scale, float *abs_out_host, unsigned char *failed_out_host);
+
+/* Input pipeline -- replaces ResizeStereo (/root/reference/dataset/transforms.py:20-39: torchvision resize that
+ * conserves the aspect ratio, then centre crop) on frames that are already on the device.
+ *   src (n,C,Hi,Wi) uint8 (src_u8 = 1) or fp32; dst (n,C,H,W) fp32 = crop(resize(src, (rh, rw)))[top : top + H, left : left + W]
+ *   mode 0: bilinear, align_corners = False, anti-aliased when down-scaling (ATen _upsample_bilinear2d_aa: triangle filter of
+ *           support max(scale, 1), weights normalised, rows first then columns) -- images
+ *   mode 1: nearest (ATen upsample_nearest2d: src = floor(dst * in / out)) -- masks; dst is then uint8 (n,C,H,W) */
+int rpe_resize_crop(const void *src, int src_u8, void *dst, int n, int C, int Hi, int Wi, int rh, int rw, int top, int left, int H,
+                    int W, int mode, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Stage 1 -- RAFT CorrBlock: all-pairs correlation GEMM (tcgen05 + TMA), pyramid, radius lookup.
@@ -296,6 +308,9 @@ int rpe_gru_gate(const float *zr, float *h, const float *q, void *out_hi, void *
  * rpe_norm_act_split: y = [relu]((a - mean_a) * rstd_a), optionally y = relu(y + (b - mean_b) * rstd_b) (stats may be NULL =
  *   identity); writes fp32 NHWC and / or fp16 split planes with channel pitch ld. */
 int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream);
+/* The same with the frames as uint8 RGB (n,3,H,W), the way a camera delivers them (ship uint8, convert on the GPU):
+ * the uint8 -> float conversion of dataset/stereo_dataset.py:36-37 happens inside the kernels that read the image. */
+int rpe_im2col7s2_split_u8(const unsigned char *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream);
 size_t rpe_instnorm_workspace_bytes(int n, int C);
 int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float eps, void *workspace, size_t workspace_bytes,
                        void *stream);
@@ -318,8 +333,8 @@ int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const f
  *                           transposed convolution as 4 groups of c_up channels, group dy * 2 + dx, valid origin (uy0, ux0)
  *   rpe_resize_sigmoid      sigmoid(F.interpolate(logits, (H, W), mode='bilinear')) of channel ch of the valid region
  *                           (y0, x0, ih, iw) -> out (n,1,H,W) fp32 */
-int rpe_downsample8_planes(const float *src0, int c0, const float *src1, int c1, const float *src2, int c2, void *out_hi, void *out_lo,
-                           int ld, int ch_offset, int n, int H, int W, void *stream);
+int rpe_downsample8_planes(const void *src0, int c0, const void *src1, int c1, const void *src2, int c2, int src_u8_mask, void *out_hi,
+                           void *out_lo, int ld, int ch_offset, int n, int H, int W, void *stream);   /* bit s of src_u8_mask: source s is uint8 */
 int rpe_pool2_planes(const float *x, int H, int W, int ld_in, int c_in_off, int y0, int x0, void *out_hi, void *out_lo, int oh, int ow,
                      int ld_out, int C, int n, void *stream);
 int rpe_upcat_planes(const float *up, int Hu, int Wu, int ld_u, int uy0, int ux0, int c_up, const float *skip, int Hk, int Wk, int ld_k,

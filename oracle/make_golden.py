@@ -456,8 +456,61 @@ def tartan_frames(size=(640, 512), mm_per_unit=60.0, bf=2200.0):
     return np.stack(L), np.stack(R), K, bf
 
 
+def metrics_golden():
+    """The reference's own evaluate_ate_freiburg.eval (evaluation/evaluate_ate_freiburg.py:6-33 -> core/metrics/trajectory_metrics.py)
+    on a deterministic ground-truth / estimate pair written with the reference's save_trajectory."""
+    import tempfile
+    from lietorch import SE3
+    from core.utils.trajectory import save_trajectory
+    from evaluation.evaluate_ate_freiburg import eval as ref_eval
+    n = 40
+    xi = det_uniform((n, 6), 77, -0.05, 0.05).astype(np.float64)
+    xi[:, :3] *= 40.0                                                       # millimetres
+    poses_gt, poses_pr = [], []
+    T_gt = SE3.Identity(1).double()
+    T_pr = SE3.exp(torch.tensor([[3.0, -2.0, 1.0, 0.02, -0.01, 0.03]], dtype=torch.float64))      # a rigid offset the alignment removes
+    noise = det_uniform((n, 6), 78, -1.0, 1.0).astype(np.float64) * np.array([0.3, 0.3, 0.3, 2e-3, 2e-3, 2e-3])
+    for k in range(n):
+        step = SE3.exp(torch.tensor(xi[k:k + 1]))
+        T_gt = T_gt * step
+        T_pr = T_pr * SE3.exp(torch.tensor(xi[k:k + 1] + (noise[k:k + 1] if k % 7 else 0.0)))
+        poses_gt.append(T_gt), poses_pr.append(T_pr)
+    poses_pr[20] = poses_pr[19]                                              # one "failed" pair: the pose is repeated
+    out = {}
+    with tempfile.TemporaryDirectory() as a, tempfile.TemporaryDirectory() as b:
+        save_trajectory([{"camera-pose": p.float(), "timestamp": k} for k, p in enumerate(poses_gt)], a)
+        save_trajectory([{"camera-pose": p.float(), "timestamp": k} for k, p in enumerate(poses_pr)], b)
+        fa, fb = os.path.join(a, "trajectory.freiburg"), os.path.join(b, "trajectory.freiburg")
+        out["gt_file"] = np.frombuffer(open(fa, "rb").read(), dtype=np.uint8)
+        out["pred_file"] = np.frombuffer(open(fb, "rb").read(), dtype=np.uint8)
+        for name, kw in (("plain", {}), ("delta3", {"delta": 3}), ("offset", {"offset": -4}), ("ignore", {"ignore_failed_pos": True})):
+            r = ref_eval(fa, fb, **kw)
+            out[name + "_scalars"] = np.array([float(r[0]), float(r[1]), float(r[2])])
+            out[name + "_trans_error"] = np.asarray(r[3], dtype=np.float64)
+            out[name + "_rpe_trans"] = np.asarray(r[4], dtype=np.float64)
+            out[name + "_rpe_rot"] = np.asarray(r[5], dtype=np.float64)
+    return out
+
+
+def resize_golden():
+    """The reference's own ResizeStereo (dataset/transforms.py:20-39, torchvision resize + center_crop) on deterministic frames:
+    up-scaling with crop, exact 2:1 down-scaling, a non-integer down-scaling, and the nearest-neighbour mask path."""
+    from dataset.transforms import ResizeStereo
+    g = {}
+    for k, ((Hi, Wi), (W, H)) in enumerate((((120, 160), (160, 128)), ((256, 320), (160, 128)), ((135, 240), (160, 128)), ((90, 100), (64, 96)))):
+        left = torch.from_numpy(det_uniform((3, Hi, Wi), 500 + k, 0.0, 255.0)).floor()           # integer-valued like decoded frames
+        right = torch.from_numpy(det_uniform((3, Hi, Wi), 520 + k, 0.0, 255.0)).floor()
+        mask = torch.from_numpy((det_uniform((1, Hi, Wi), 540 + k, 0.0, 1.0) > 0.3).astype(np.uint8))
+        l, r, m = ResizeStereo((W, H))(left, right, mask)
+        g[f"in_shape{k}"], g[f"size{k}"] = np.array([Hi, Wi]), np.array([W, H])
+        g[f"left{k}"], g[f"right{k}"], g[f"mask{k}"] = l.numpy(), r.numpy(), m.numpy()
+    return g
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--resize", action="store_true", help="only tests/golden/resize_stereo.npz (reference dataset/transforms.ResizeStereo)")
+    ap.add_argument("--metrics", action="store_true", help="only tests/golden/metrics.npz (reference evaluate_ate_freiburg.eval)")
     ap.add_argument("--config1", action="store_true",
                     help="only tests/golden/e2e_cfg1_tartan.npz: the reference run on its own tests/test_data/tartan_air fixtures")
     ap.add_argument("--bench64", action="store_true",
@@ -470,6 +523,14 @@ def main():
     ap.add_argument("--mask-spec", action="store_true", help="only tests/golden/mask_specularities.npz (reference dataset function)")
     args = ap.parse_args()
     assert os.path.isdir(REF), "reference not mounted"
+    if args.resize:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "resize_stereo.npz"), **resize_golden())
+        print("tests/golden/resize_stereo.npz written")
+        return
+    if args.metrics:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "metrics.npz"), **metrics_golden())
+        print("tests/golden/metrics.npz written")
+        return
     if args.mask_spec:
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mask_specularities.npz"), **mask_spec_golden())
         print("tests/golden/mask_specularities.npz written")

@@ -80,7 +80,10 @@ SIGNATURES = {
     "rpe_instnorm_stats": (_I, [_P, _P, _I, _I, _I, _F, _P, _Z, _P]),
     "rpe_norm_act_split": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_tap_gather3x3": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
-    "rpe_downsample8_planes": (_I, [_P, _I, _P, _I, _P, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_downsample8_planes": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "rpe_im2col7s2_split_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "rpe_warp8_mask_u8": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "rpe_resize_crop": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rpe_pool2_planes": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_upcat_planes": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_resize_sigmoid": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),

@@ -22,12 +22,15 @@ STEM_LD = 176
 
 
 def stem_planes(images, out=None):
-    """im2col of the 7x7 / 2 stem for NCHW fp32 images in 0..255 -> split planes (n, H/2, W/2, STEM_LD)."""
+    """im2col of the 7x7 / 2 stem for NCHW images in 0..255 (fp32, or uint8 as the camera delivers them) -> split planes
+    (n, H/2, W/2, STEM_LD)."""
+    import torch
     n, _, H, W = images.shape
     if out is None:
         out = Planes(n, (H - 1) // 2 + 1, (W - 1) // 2 + 1, STEM_LD, images.device)
+    fn = _lib.lib().rpe_im2col7s2_split_u8 if images.dtype == torch.uint8 else _lib.lib().rpe_im2col7s2_split
     with _timed("im2col_stem", n):
-        check(_lib.lib().rpe_im2col7s2_split(_p(images), _p(out.hi), _p(out.lo), n, H, W, STEM_LD, _stream()), "rpe_im2col7s2_split")
+        check(fn(_p(images), _p(out.hi), _p(out.lo), n, H, W, STEM_LD, _stream()), "rpe_im2col7s2_split")
     return out
 
 

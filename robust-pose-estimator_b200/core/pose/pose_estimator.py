@@ -208,7 +208,7 @@ class PoseEstimator(torch.nn.Module):
             main.wait_event(ev)
             for x in (l, r, m):
                 x.record_stream(main)
-            p, lg, e = self._engine.infer_sequence(l.float(), r.float(), m.bool(), sequence_start)
+            p, lg, e = self._engine.infer_sequence(l, r, m.bool(), sequence_start)        # uint8 frames are consumed as they are
             rel.append(p), log.append(lg), evals.append(e)
         return torch.cat(rel), torch.cat(log), torch.cat(evals)
 

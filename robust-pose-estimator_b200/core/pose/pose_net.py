@@ -81,8 +81,8 @@ class PoseNet(nn.Module):
                         gru_hidden_state, context, state_planes=None):
         """-> conf1, conf2, pcl2 warped, mask2 warped   (pose_net.py:102-119).  ``state_planes``: (gru, ctx) as the update
         operator's NHWC split planes (batched engine); then ``gru_hidden_state`` / ``context`` may be None."""
-        pcl2w, img2w, sflow2w, mask2w = ops.warp8_mask(pcl2, image2l.float().contiguous(), stereo_flow2,
-                                                       mask2.bool().contiguous(), time_flow)
+        as_img = lambda t: t.contiguous() if t.dtype == torch.uint8 else t.float().contiguous()      # uint8 frames are read in place
+        pcl2w, img2w, sflow2w, mask2w = ops.warp8_mask(pcl2, as_img(image2l), stereo_flow2, mask2.bool().contiguous(), time_flow)
         if self.use_weights and self.flow.precision == "fp16x3":
             # both TinyUNets on the tcgen05 convolution kernels (core/unet/unet_tc.py); the 264 / 272-channel inputs are never
             # assembled: the first convolution reads the down-sampled geometry, the GRU state and the context as separate sources
@@ -100,7 +100,7 @@ class PoseNet(nn.Module):
                 gru_p, ctx_p = self._head_planes[key]
                 nchw_to_planes(gru_hidden_state.float().contiguous(), gru_p)
                 nchw_to_planes(context.float().contiguous(), ctx_p)
-            conf1, conf2 = self._heads_tc.forward([stereo_flow1.float().contiguous(), image1l.float().contiguous(), pcl1],
+            conf1, conf2 = self._heads_tc.forward([stereo_flow1.float().contiguous(), as_img(image1l), pcl1],
                                                   [sflow2w, img2w, pcl2w], gru_p, ctx_p, n, self.image_shape)
         elif self.use_weights:
             n = pcl1.shape[0]

@@ -169,8 +169,9 @@ class HeadsTC:
             for k, srcs in enumerate((inp1_srcs, inp2_srcs)):
                 a = list(srcs) + [None] * (3 - len(srcs))
                 ch = [0 if t is None else t.shape[1] for t in a]
-                check(l.rpe_downsample8_planes(_p(a[0]), ch[0], _p(a[1]), ch[1], _p(a[2]), ch[2], _p(st["ds"].hi), _p(st["ds"].lo), 16, 8 * k,
-                                               n, H, W, s), "rpe_downsample8_planes")
+                u8 = sum(1 << i for i, t in enumerate(a) if t is not None and t.dtype == torch.uint8)      # uint8 frames are read as they are
+                check(l.rpe_downsample8_planes(_p(a[0]), ch[0], _p(a[1]), ch[1], _p(a[2]), ch[2], u8, _p(st["ds"].hi), _p(st["ds"].lo), 16,
+                                               8 * k, n, H, W, s), "rpe_downsample8_planes")
             for step in st["steps"]:
                 if step[0] == "conv":
                     step[1].run("conv_tc_heads")

@@ -26,18 +26,19 @@ __device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
 // shared memory with coalesced loads (normalised on the way in, zeros outside the image), then thread (pixel, ky) assembles
 // its 24 values in a second shared tile and the CTA copies its contiguous 32 x 352-byte output range in 16-byte chunks.
 constexpr int kStemPx = 32, kStemCols = 2 * kStemPx + 5, kStemPitch = 72, kStemLd = 176;
-__global__ void __launch_bounds__(256) im2col7s2_kernel(const float *__restrict__ img, plane_t *__restrict__ hi,
+template <typename T>      // float (the reference's 0..255 float tensors) or uint8_t (camera frames as they are: same values)
+__global__ void __launch_bounds__(256) im2col7s2_kernel(const T *__restrict__ img, plane_t *__restrict__ hi,
                                                         plane_t *__restrict__ lo, int H, int W, int OH, int OW, int ld) {
     __shared__ float tile[7][3][kStemPitch];
     const int ox0 = blockIdx.x * kStemPx, oy = blockIdx.y, n = blockIdx.z;
     const int x0 = 2 * ox0 - 3, y0 = 2 * oy - 3;
-    const float *base = img + (size_t)n * 3 * H * W;
+    const T *base = img + (size_t)n * 3 * H * W;
     for (int i = threadIdx.x; i < 7 * 3 * kStemPitch; i += blockDim.x) {
         const int col = i % kStemPitch, rc = i / kStemPitch;
         const int c = rc % 3, r = rc / 3;
         const int y = y0 + r, x = x0 + col;
         float v = 0.0f;
-        if (col < kStemCols && y >= 0 && y < H && x >= 0 && x < W) v = 2.0f * (__ldg(base + ((size_t)c * H + y) * W + x) / 255.0f) - 1.0f;
+        if (col < kStemCols && y >= 0 && y < H && x >= 0 && x < W) v = 2.0f * ((float)__ldg(base + ((size_t)c * H + y) * W + x) / 255.0f) - 1.0f;
         tile[r][c][col] = v;
     }
     __syncthreads();
@@ -213,15 +214,28 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__
 
 extern "C" {
 
-int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream) {
+static int im2col7s2_impl(const void *img, int is_u8, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream) {
     if (!img || !out_hi || !out_lo || n <= 0 || H <= 0 || W <= 0 || ld < 168 || (ld % 8)) return RPE_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(out_hi) & 15u) || (reinterpret_cast<uintptr_t>(out_lo) & 15u)) return RPE_ERR_ALIGNMENT;
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
     if (OH > 65535 || n > 65535 || ld != rpe::kStemLd) return RPE_ERR_INVALID_ARG;      // the staged copy assumes the 176-channel pitch
     dim3 grid((OW + rpe::kStemPx - 1) / rpe::kStemPx, OH, n);
-    rpe::im2col7s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, H, W, OH, OW, ld);
+    if (is_u8)
+        rpe::im2col7s2_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)img, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo,
+                                                                               H, W, OH, OW, ld);
+    else
+        rpe::im2col7s2_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)img, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, H,
+                                                                             W, OH, OW, ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
+}
+
+int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream) {
+    return im2col7s2_impl(img, 0, out_hi, out_lo, n, H, W, ld, stream);
+}
+
+int rpe_im2col7s2_split_u8(const unsigned char *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream) {
+    return im2col7s2_impl(img, 1, out_hi, out_lo, n, H, W, ld, stream);
 }
 
 size_t rpe_instnorm_workspace_bytes(int n, int C) { return (size_t)n * rpe::kStatBlocks * C * 2 * sizeof(double); }

@@ -116,7 +116,11 @@ struct WarpSrc {
     const float *src[3];
     float *dst[3];
     int ch[3];
+    int u8_mask;          // bit s: source s holds uint8 values (a camera frame as it is); its warped output is fp32 all the same
 };
+__device__ __forceinline__ float warp_ld(const float *p, int o, bool u8) {
+    return u8 ? (float)__ldg(reinterpret_cast<const uint8_t *>(p) + o) : __ldg(p + o);
+}
 
 __global__ void __launch_bounds__(256) warp8_mask_kernel(WarpSrc t, const uint8_t *__restrict__ mask2,
                                                          const float *__restrict__ flow, uint8_t *__restrict__ mask2w,
@@ -153,13 +157,15 @@ __global__ void __launch_bounds__(256) warp8_mask_kernel(WarpSrc t, const uint8_
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
         if (t.src[s] == nullptr) continue;
+        const bool u8 = (t.u8_mask >> s) & 1;
         for (int c = 0; c < t.ch[s]; ++c) {
-            const float *p = t.src[s] + ((size_t)b * t.ch[s] + c) * HW;
+            const float *p = u8 ? reinterpret_cast<const float *>(reinterpret_cast<const uint8_t *>(t.src[s]) + ((size_t)b * t.ch[s] + c) * HW)
+                                : t.src[s] + ((size_t)b * t.ch[s] + c) * HW;
             float acc = 0.0f;
-            if (in_n && in_w) acc = __ldg(p + o_nw) * w_nw;
-            if (in_n && in_e) acc += __ldg(p + o_nw + 1) * w_ne;
-            if (in_s && in_w) acc += __ldg(p + o_nw + W) * w_sw;
-            if (in_s && in_e) acc += __ldg(p + o_nw + W + 1) * w_se;
+            if (in_n && in_w) acc = warp_ld(p, o_nw, u8) * w_nw;
+            if (in_n && in_e) acc += warp_ld(p, o_nw + 1, u8) * w_ne;
+            if (in_s && in_w) acc += warp_ld(p, o_nw + W, u8) * w_sw;
+            if (in_s && in_e) acc += warp_ld(p, o_nw + W + 1, u8) * w_se;
             t.dst[s][((size_t)b * t.ch[s] + c) * HW + i] = acc;
         }
     }
@@ -247,16 +253,30 @@ int rpe_proj(const float *depth, const float *K, float *pcl, int rescale, float 
     return RPE_OK;
 }
 
+static int warp8_mask_impl(const float *pcl2, const void *img2, int img_u8, const float *sflow2, const uint8_t *mask2, const float *flow,
+                           float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w, int n, int H, int W, void *stream);
+
 int rpe_warp8_mask(const float *pcl2, const float *img2, const float *sflow2, const uint8_t *mask2, const float *flow,
                    float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w, int n, int H, int W, void *stream) {
+    return warp8_mask_impl(pcl2, img2, 0, sflow2, mask2, flow, pcl2w, img2w, sflow2w, mask2w, n, H, W, stream);
+}
+
+int rpe_warp8_mask_u8(const float *pcl2, const unsigned char *img2, const float *sflow2, const uint8_t *mask2, const float *flow,
+                      float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w, int n, int H, int W, void *stream) {
+    return warp8_mask_impl(pcl2, img2, 1, sflow2, mask2, flow, pcl2w, img2w, sflow2w, mask2w, n, H, W, stream);
+}
+
+static int warp8_mask_impl(const float *pcl2, const void *img2, int img_u8, const float *sflow2, const uint8_t *mask2, const float *flow,
+                           float *pcl2w, float *img2w, float *sflow2w, uint8_t *mask2w, int n, int H, int W, void *stream) {
     if (!flow || n <= 0 || H <= 1 || W <= 1) return RPE_ERR_INVALID_ARG;
     if ((pcl2 == nullptr) != (pcl2w == nullptr) || (img2 == nullptr) != (img2w == nullptr) ||
         (sflow2 == nullptr) != (sflow2w == nullptr) || (mask2 == nullptr) != (mask2w == nullptr))
         return RPE_ERR_INVALID_ARG;
     rpe::WarpSrc t;
     t.src[0] = pcl2, t.dst[0] = pcl2w, t.ch[0] = 3;
-    t.src[1] = img2, t.dst[1] = img2w, t.ch[1] = 3;
+    t.src[1] = reinterpret_cast<const float *>(img2), t.dst[1] = img2w, t.ch[1] = 3;
     t.src[2] = sflow2, t.dst[2] = sflow2w, t.ch[2] = 2;
+    t.u8_mask = img_u8 ? 2 : 0;
     dim3 grid((H * W + 255) / 256, n);
     rpe::warp8_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, mask2, flow, mask2w, H, W);
     RPE_LAUNCH_CHECK();
@@ -269,6 +289,7 @@ int rpe_remap_bilinear(const float *x, int C, const float *flow, float *out, int
     t.src[0] = x, t.dst[0] = out, t.ch[0] = C;
     t.src[1] = nullptr, t.dst[1] = nullptr, t.ch[1] = 0;
     t.src[2] = nullptr, t.dst[2] = nullptr, t.ch[2] = 0;
+    t.u8_mask = 0;
     dim3 grid((H * W + 255) / 256, n);
     rpe::warp8_mask_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, nullptr, flow, nullptr, H, W);
     RPE_LAUNCH_CHECK();

@@ -24,6 +24,7 @@ __device__ __forceinline__ void hd_split_store(float v, plane_t *hi, plane_t *lo
 struct HdCatSrc {
     const float *src[3];
     int ch[3];
+    int u8_mask;          // bit s: source s holds uint8 values
 };
 
 __global__ void __launch_bounds__(256) downsample8_planes_kernel(HdCatSrc t, plane_t *__restrict__ hi, plane_t *__restrict__ lo, int ld,
@@ -35,20 +36,20 @@ __global__ void __launch_bounds__(256) downsample8_planes_kernel(HdCatSrc t, pla
     if (idx >= ctot * h8 * w8) return;
     const int cc = idx % ctot;                                  // channel fastest: contiguous NHWC stores
     const int j = (idx / ctot) % w8, i = idx / (ctot * w8);
-    int c = cc;
-    const float *p;
-    if (c < t.ch[0]) {
-        p = t.src[0] + ((size_t)b * t.ch[0] + c) * H * W;
-    } else if (c < t.ch[0] + t.ch[1]) {
-        c -= t.ch[0];
-        p = t.src[1] + ((size_t)b * t.ch[1] + c) * H * W;
+    int c = cc, s = 0;
+    if (c >= t.ch[0]) c -= t.ch[0], s = 1;
+    if (s == 1 && c >= t.ch[1]) c -= t.ch[1], s = 2;
+    const size_t o = ((size_t)b * t.ch[s] + c) * H * W + (size_t)(8 * i + 3) * W + 8 * j + 3;
+    float2 a, d;
+    if ((t.u8_mask >> s) & 1) {
+        const uint8_t *p = reinterpret_cast<const uint8_t *>(t.src[s]) + o;
+        a = make_float2((float)__ldg(p), (float)__ldg(p + 1));
+        d = make_float2((float)__ldg(p + W), (float)__ldg(p + W + 1));
     } else {
-        c -= t.ch[0] + t.ch[1];
-        p = t.src[2] + ((size_t)b * t.ch[2] + c) * H * W;
+        const float *p = t.src[s] + o;
+        a = make_float2(__ldg(p), __ldg(p + 1));
+        d = make_float2(__ldg(p + W), __ldg(p + W + 1));
     }
-    p += (size_t)(8 * i + 3) * W + 8 * j + 3;
-    const float2 a = make_float2(__ldg(p), __ldg(p + 1));
-    const float2 d = make_float2(__ldg(p + W), __ldg(p + W + 1));
     // ATen upsample_bilinear2d, align_corners=False, scale 8: source index 8i + 3.5 -> weights 0.5 / 0.5 on both axes
     const float top = __fadd_rn(__fmul_rn(0.5f, a.x), __fmul_rn(0.5f, a.y));
     const float bot = __fadd_rn(__fmul_rn(0.5f, d.x), __fmul_rn(0.5f, d.y));
@@ -120,13 +121,14 @@ __global__ void __launch_bounds__(256) resize_sigmoid_kernel(const float *__rest
 
 extern "C" {
 
-int rpe_downsample8_planes(const float *src0, int c0, const float *src1, int c1, const float *src2, int c2, void *out_hi, void *out_lo,
-                           int ld, int ch_offset, int n, int H, int W, void *stream) {
+int rpe_downsample8_planes(const void *src0, int c0, const void *src1, int c1, const void *src2, int c2, int src_u8_mask, void *out_hi,
+                           void *out_lo, int ld, int ch_offset, int n, int H, int W, void *stream) {
     if (!out_hi || !out_lo || n <= 0 || H < 8 || W < 8 || (H % 8) || (W % 8)) return RPE_ERR_INVALID_ARG;
     rpe::HdCatSrc t;
-    t.src[0] = src0, t.ch[0] = src0 ? c0 : 0;
-    t.src[1] = src1, t.ch[1] = src1 ? c1 : 0;
-    t.src[2] = src2, t.ch[2] = src2 ? c2 : 0;
+    t.src[0] = (const float *)src0, t.ch[0] = src0 ? c0 : 0;
+    t.src[1] = (const float *)src1, t.ch[1] = src1 ? c1 : 0;
+    t.src[2] = (const float *)src2, t.ch[2] = src2 ? c2 : 0;
+    t.u8_mask = src_u8_mask;
     const int ctot = t.ch[0] + t.ch[1] + t.ch[2];
     if (ctot <= 0 || ch_offset < 0 || ch_offset + ctot > ld) return RPE_ERR_INVALID_ARG;
     const int total = ctot * (H / 8) * (W / 8);

@@ -80,7 +80,8 @@ class F2FEngine:
         utc = raft.update_tc()
         st = utc.state(1, h8, w8, dev)
         feat = raft.feature_list(("first", h8, w8, dev.index), 3, h8, w8, dev)
-        imgs = torch.cat((limg, rimg), 0).float().contiguous()
+        imgs = torch.cat((limg, rimg), 0)
+        imgs = imgs.contiguous() if imgs.dtype == torch.uint8 else imgs.float().contiguous()
         raft.encode_into(imgs, 1, feat.view(0, 2), st["h"], st["hp"], st["inp"])
         new = _FrameState()
         new.fmap_hi, new.fmap_lo = feat.hi[0:1].clone(), feat.lo[0:1].clone()
@@ -171,7 +172,8 @@ class F2FEngine:
         utc = raft.update_tc()
         st = utc.state(B, h8, w8, dev)
         feat = raft.feature_list(("chunk", n_img, first, h8, w8, dev.index), off + 2 * n_img + 1, h8, w8, dev)
-        imgs = torch.cat((limg, rimg), 0).float().contiguous()
+        imgs = torch.cat((limg, rimg), 0)                         # uint8 frames stay uint8: the kernels convert on load
+        imgs = imgs.contiguous() if imgs.dtype == torch.uint8 else imgs.float().contiguous()
         raft.encode_into(imgs, n_img, feat.view(off, off + 2 * n_img), st["h"][C:], st["hp"].view(C, B), st["inp"].view(C, B))
         # temporal sample k reads the context of frame k-1: copies of the stereo slots (and the carried frame on a later chunk)
         n_shift = C - off
@@ -263,11 +265,14 @@ class F2FEngine:
 
     # ------------------------------------------------------------------------------------------------
     def infer_sequence(self, limgs, rimgs, masks, sequence_start=True):
-        """limgs, rimgs (T,3,H,W) float 0..255 on the device, masks (T,1,H,W) bool.
+        """limgs, rimgs (T,3,H,W) 0..255 on the device -- float like the reference's tensors, or uint8 as decoded (the tensor-core
+        path reads uint8 directly; the other precisions convert) --, masks (T,1,H,W) bool.
         -> relative poses (T-1,7) f32 (normalised units, frame k-1 -> k), tangents (T-1,6), evals (T-1,).
         Continues from the previous call's last frame if ``reset()`` was not called."""
         T = limgs.shape[0]
         poses, logs, evals = [], [], []
+        if limgs.dtype == torch.uint8 and self.model.flow.precision != "fp16x3":
+            limgs, rimgs = limgs.float(), rimgs.float()
         with torch.no_grad():
             start = 0
             if self.prev is None:

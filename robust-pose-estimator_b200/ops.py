@@ -130,18 +130,20 @@ def warp8_mask(pcl2, img2, sflow2, mask2, flow):
     n, _, H, W = flow.shape
     _chk(flow, torch.float32, "flow", (n, 2, H, W))
     outs = []
+    img_u8 = img2 is not None and img2.dtype == torch.uint8       # camera frames as they are; the warped image is fp32 all the same
     for t, c, name in ((pcl2, 3, "pcl2"), (img2, 3, "img2"), (sflow2, 2, "sflow2")):
         if t is None:
             outs.append(None)
         else:
-            _chk(t, torch.float32, name, (n, c, H, W))
-            outs.append(torch.empty_like(t))
+            _chk(t, torch.uint8 if (name == "img2" and img_u8) else torch.float32, name, (n, c, H, W))
+            outs.append(torch.empty(t.shape, dtype=torch.float32, device=t.device))
     m_out = None
     if mask2 is not None:
         _chk(mask2, torch.bool, "mask2", (n, 1, H, W))
         m_out = torch.empty_like(mask2)
+    fn = _lib.lib().rpe_warp8_mask_u8 if img_u8 else _lib.lib().rpe_warp8_mask
     with _timed("warp8_mask", n):
-        check(_lib.lib().rpe_warp8_mask(_p(pcl2), _p(img2), _p(sflow2), _p(mask2), _p(flow), _p(outs[0]), _p(outs[1]),
+        check(fn(_p(pcl2), _p(img2), _p(sflow2), _p(mask2), _p(flow), _p(outs[0]), _p(outs[1]),
                                         _p(outs[2]), _p(m_out), n, H, W, _stream()), "rpe_warp8_mask")
     return outs[0], outs[1], outs[2], m_out
 

@@ -20,8 +20,11 @@ from oracle import pipeline_ref, se3_np  # noqa: E402
 from oracle.detrand import unpack  # noqa: E402
 
 
-def run(g, sd, eps, seed):
+def run(g, sd, eps, seed, lw_mask=None):
     W, H = [int(v) for v in g["size"]]
+    if lw_mask is not None:                              # config 4: the 3-D-only objective (loss_weight[1] = 0)
+        sd = dict(sd)
+        sd["loss_weight"] = sd["loss_weight"] * torch.tensor(lw_mask, dtype=sd["loss_weight"].dtype)
     gen = torch.Generator().manual_seed(seed)
     orig = pipeline_ref._conv
 
@@ -49,6 +52,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--golden", default=os.path.join(ROOT, "tests", "golden", "e2e_cfg1_tartan.npz"))
     ap.add_argument("--seeds", type=int, default=3)
+    ap.add_argument("--ckpt", default="poseNet_2xf8up4b.pth")
+    ap.add_argument("--only3d", action="store_true", help="zero the 2-D loss weight (BASELINE config 4)")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     g = dict(np.load(a.golden))
@@ -57,12 +62,13 @@ if __name__ == "__main__":
         order = [int(k) for k in g["order"]]
         g["imgs_l"], g["imgs_r"] = g["imgs_l"][order], g["imgs_r"][order]
         g["masks_in"] = np.stack([np.packbits(np.ones(H * W, bool))] * len(order))
-    sd = torch.load(os.path.join(ROOT, "oracle", "_ref", "trained", "poseNet_2xf8up4b.pth"), map_location="cpu", weights_only=False)["state_dict"]
-    base, ev0 = run(g, sd, 0.0, 0)
+    sd = torch.load(os.path.join(ROOT, "oracle", "_ref", "trained", a.ckpt), map_location="cpu", weights_only=False)["state_dict"]
+    lw = (1.0, 0.0) if a.only3d else None
+    base, ev0 = run(g, sd, 0.0, 0, lw)
     print("unperturbed evaluations per pair:", ev0)
     for eps in (6e-8, 1e-6, 1e-5):
         for seed in range(a.seeds):
-            rels, ev = run(g, sd, eps, seed)
+            rels, ev = run(g, sd, eps, seed, lw)
             out = []
             for r, b in zip(rels, base):
                 d = se3_np.mul(se3_np.inv(r), b)
