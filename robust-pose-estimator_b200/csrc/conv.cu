@@ -94,6 +94,8 @@ struct alignas(64) ConvParams {
     int corr_h, corr_w, corr_nbx, corr_levels;
     int corr_vec;                                     // bit l: level l rows may be written with vector stores
     int corr_a_wrap, corr_a_sub;                      // query-side image of sample s: s < wrap ? s : s - sub (target side: image s)
+    int resident_a;                                   // kind 7: the query tile (all K blocks) stays in shared memory while the CTA walks
+                                                      // every target block of its image; only the target tiles stream
 };
 
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
@@ -378,13 +380,15 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
         for (int it = 0; it < 4; ++it)
             if ((inside_mask >> it) & 1u) {
                 float *p = P.corr_lvl[0] + (size_t)pix[it] * n0 + (size_t)gy * w0 + gx;
+                // streaming stores (evict-first): the 139 MB per sample written here must not push the feature-map operands, which
+                // every CTA re-reads 20 times, out of the L2
                 if (P.corr_vec & 1) {
-                    *reinterpret_cast<float4 *>(p) = o[it];
+                    __stcs(reinterpret_cast<float4 *>(p), o[it]);
                 } else {
-                    p[0] = o[it].x;
-                    if (gx + 1 < w0) p[1] = o[it].y;
-                    if (gx + 2 < w0) p[2] = o[it].z;
-                    if (gx + 3 < w0) p[3] = o[it].w;
+                    __stcs(p, o[it].x);
+                    if (gx + 1 < w0) __stcs(p + 1, o[it].y);
+                    if (gx + 2 < w0) __stcs(p + 2, o[it].z);
+                    if (gx + 3 < w0) __stcs(p + 3, o[it].w);
                 }
             }
     }
@@ -408,10 +412,10 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
             if ((inside_mask >> it) & 1u) {
                 float *p = P.corr_lvl[1] + (size_t)pix[it] * n1 + (size_t)y1 * w1 + x1;
                 if (P.corr_vec & 2) {
-                    *reinterpret_cast<float2 *>(p) = l1[it];
+                    __stcs(reinterpret_cast<float2 *>(p), l1[it]);
                 } else {
-                    p[0] = l1[it].x;
-                    if (x1 + 1 < w1) p[1] = l1[it].y;
+                    __stcs(p, l1[it].x);
+                    if (x1 + 1 < w1) __stcs(p + 1, l1[it].y);
                 }
             }
     }
@@ -430,7 +434,7 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
         const size_t n2 = (size_t)h2 * w2;
 #pragma unroll
         for (int it = 0; it < 4; ++it)
-            if ((inside_mask >> it) & 1u) P.corr_lvl[2][(size_t)pix[it] * n2 + (size_t)y2 * w2 + x2] = l2[it];
+            if ((inside_mask >> it) & 1u) __stcs(P.corr_lvl[2] + (size_t)pix[it] * n2 + (size_t)y2 * w2 + x2, l2[it]);
     }
     if ((c & 7) == 3) {
 #pragma unroll
@@ -444,7 +448,7 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
         const float top_r = __shfl_xor_sync(0xffffffffu, st.l2p[it], 1), bot_r = __shfl_xor_sync(0xffffffffu, l2[it], 1);
         if (!(lane & 1) && y3 < h3 && x3 < w3 && ((inside_mask >> it) & 1u)) {
             const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(st.l2p[it], top_r), l2[it]), bot_r), 0.25f);
-            P.corr_lvl[3][(size_t)pix[it] * ((size_t)h3 * w3) + (size_t)y3 * w3 + x3] = v;
+            __stcs(P.corr_lvl[3] + (size_t)pix[it] * ((size_t)h3 * w3) + (size_t)y3 * w3 + x3, v);
         }
     }
 }
@@ -563,6 +567,14 @@ __device__ __forceinline__ void cv_release_acc(uint64_t *bar, uint32_t cluster_a
     }
 }
 
+// k-th work unit of this CTA (pair).  Default: units first, first + step, ...  Correlation kind with a resident query tile:
+// the CTA owns query-tile pairs first, first + step, ... and visits all n_blocks target blocks of each one consecutively.
+template <int kK>
+__device__ __forceinline__ int cv_unit(const ConvParams &P, int k, int first, int step) {
+    if (kK == kKCorr && P.resident_a) return (first + (k / P.n_blocks) * step) * P.n_blocks + (k % P.n_blocks);
+    return first + k * step;
+}
+
 // In pair mode (cta_group::2) two CTAs of a cluster own two adjacent pixel tiles: each loads its own activations and HALF of
 // the weight tile, the leader (rank 0) issues M = 256 MMAs that read both shared memories and write both tensor memories,
 // and every TMA load of either CTA counts its bytes on the leader's "full" barrier; the MMA commits are multicast to the
@@ -642,8 +654,9 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         if (!(RPE_CV_DBG(P) & 1) && elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int u = u_first; u < num_units; u += u_step) {
+            for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
                 const CvTile t = cv_decode<kPair>(P, u, rank);
+                if (kK == kKCorr && P.resident_a && t.nb != 0) continue;        // the query tile is already resident
                 for (int s = 0; s < P.n_src; ++s)
                     for (int cb = 0; cb < P.cblocks[s]; ++cb)
                         for (int tm = 0; tm < P.kmin; ++tm)
@@ -688,7 +701,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
             } else {
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int u = u_first; u < num_units; u += u_step) {
+                for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
                     const int nb = u % P.n_blocks;
                     const int img = kK == kKCorr ? cv_decode<kPair>(P, u, rank).img : 0;
                     const int cby = kK == kKCorr ? nb / P.corr_nbx : 0, cbx = kK == kKCorr ? nb - cby * P.corr_nbx : 0;
@@ -739,7 +752,9 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         const int n_a = P.n_a_stages, n_b = P.n_b_stages, kmin = P.kmin, kmaj = P.kmaj, taps = P.kmin * P.kmaj;
         uint32_t sa = 0, sb = 0, pa = 0, pb = 0, acc = 0, acc_phase = 0;
         bool b_ready = no_load;
-        for (int u = u_first; u < num_units; u += u_step) {
+        for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
+            // resident query tile (kind 7): its stages are released (and the parity advances) only after the last target block
+            const bool a_release = !(kK == kKCorr && P.resident_a) || (u % P.n_blocks) == P.n_blocks - 1;
             mbar_wait_u32(t_empty_u + acc * 8u, acc_phase ^ 1u);
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + acc * (uint32_t)kCvMaxBN;
@@ -791,8 +806,11 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                             }
                             accumulate = 1;
                             if (!reuse || tj == kmaj - 1) {
-                                if (leader && !no_load) cv_commit_u32<kPair>(a_empty_u + sa * 8u);
-                                if (++sa == (uint32_t)n_a) sa = 0, pa ^= 1u;
+                                if (leader && !no_load && a_release) cv_commit_u32<kPair>(a_empty_u + sa * 8u);
+                                if (++sa == (uint32_t)n_a) {
+                                    sa = 0;
+                                    if (a_release) pa ^= 1u;
+                                }
                             }
                         }
                 }
@@ -810,7 +828,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         float *stage = sstage + (warp - 4) * (32 * 16);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int u = u_first; u < num_units; u += u_step) {
+        for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
             const CvTile t = cv_decode<kPair>(P, u, rank);
             uint32_t pix[4];
             uint32_t inside_mask = 0;
@@ -952,12 +970,13 @@ static int cv_load_encode() {
 
 // Probe / A-B switches from the environment, read once per process (not on every plan creation).
 struct CvEnv {
-    bool no_pair, generic;
+    bool no_pair, generic, corr_resident_a;
     int a_stages, dbg;
     CvEnv() {
         const char *e = getenv("RPE_CONV_PAIR");
         no_pair = e && e[0] == '0';
         generic = getenv("RPE_CONV_GENERIC") != nullptr;
+        corr_resident_a = getenv("RPE_CORR_RESIDENT_A") != nullptr;  // A-B switch: keep the query tile of the correlation kernel resident
         e = getenv("RPE_CONV_ASTAGES");
         a_stages = e ? atoi(e) : 0;
         e = getenv("RPE_CONV_DEBUG");
@@ -1230,6 +1249,17 @@ int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_h
     p.resident_b = 0;
     p.n_a_stages = 2;
     if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
+    // Resident query tile (A-B switch RPE_CORR_RESIDENT_A, off by default): all K blocks of the CTA's 128 queries (C / 64 stages of
+    // 32 KB) stay in shared memory while it visits the target blocks of the image, so that per unit only the target tiles stream
+    // (half the L2 -> SM operand traffic).  Measured on B200 (64 samples, profiles/r2_corr_probe.txt): 4.59 ms against 2.95 ms
+    // with both operands streaming -- the 128 KB tile leaves room for only 4 target-tile ring entries (two K blocks of
+    // look-ahead), and the exposed TMA latency costs more than the saved bandwidth.
+    p.resident_a = 0;
+    if (pair && p.cblocks[0] <= kCvMaxAStages && cv_env().corr_resident_a &&
+        (size_t)p.cblocks[0] * p.a_stage_bytes + 4 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) {
+        p.resident_a = 1;
+        p.n_a_stages = p.cblocks[0];
+    }
     p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
     if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
     p.corr_h = h, p.corr_w = w, p.corr_nbx = (w + 15) / 16, p.corr_levels = num_levels;
