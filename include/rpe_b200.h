@@ -155,7 +155,7 @@ typedef struct rpe_pose_problem {
 size_t rpe_pose_workspace_bytes(int n_pairs);
 /* Tuning (results never depend on it: the reduction tree is fixed by the pixel index).  rpe_pose_set_groups: upper bound on the
  * pairs solved concurrently by disjoint CTA groups (1..64; default: as many as fit).  rpe_pose_set_group_size: CTAs per group when
- * a batch is solved (power of two <= 128, default 32).  Process-wide settings, not thread-safe -- like the rest of the library's
+ * a batch is solved (power of two <= 128, default 16).  Process-wide settings, not thread-safe -- like the rest of the library's
  * state (cached function attributes, last-error code): the reference contract is one host thread per process. */
 int rpe_pose_set_groups(int groups);
 int rpe_pose_set_group_size(int ctas);

@@ -363,9 +363,15 @@ struct CvCorrState {
     float2 l1p[4];
     float l2p[4];
 };
+template <typename T>
+__device__ __forceinline__ void cv_corr_st(T *p, const T v, bool streaming) {
+    if (streaming) __stcs(p, v);
+    else *p = v;
+}
 __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const float *stage, int c, int by, int bx, const uint32_t *pix,
                                                  uint32_t inside_mask, int lane, CvCorrState &st) {
     const int h0 = P.corr_h, w0 = P.corr_w;
+    const bool cs = (P.corr_vec & 16) != 0;
     const int gy = by * 16 + c, gx = bx * 16 + ((lane & 3) << 2);
     float4 o[4];
 #pragma unroll
@@ -383,12 +389,12 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
                 // streaming stores (evict-first): the 139 MB per sample written here must not push the feature-map operands, which
                 // every CTA re-reads 20 times, out of the L2
                 if (P.corr_vec & 1) {
-                    __stcs(reinterpret_cast<float4 *>(p), o[it]);
+                    cv_corr_st(reinterpret_cast<float4 *>(p), o[it], cs);
                 } else {
-                    __stcs(p, o[it].x);
-                    if (gx + 1 < w0) __stcs(p + 1, o[it].y);
-                    if (gx + 2 < w0) __stcs(p + 2, o[it].z);
-                    if (gx + 3 < w0) __stcs(p + 3, o[it].w);
+                    cv_corr_st(p, o[it].x, cs);
+                    if (gx + 1 < w0) cv_corr_st(p + 1, o[it].y, cs);
+                    if (gx + 2 < w0) cv_corr_st(p + 2, o[it].z, cs);
+                    if (gx + 3 < w0) cv_corr_st(p + 3, o[it].w, cs);
                 }
             }
     }
@@ -412,10 +418,10 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
             if ((inside_mask >> it) & 1u) {
                 float *p = P.corr_lvl[1] + (size_t)pix[it] * n1 + (size_t)y1 * w1 + x1;
                 if (P.corr_vec & 2) {
-                    __stcs(reinterpret_cast<float2 *>(p), l1[it]);
+                    cv_corr_st(reinterpret_cast<float2 *>(p), l1[it], cs);
                 } else {
-                    __stcs(p, l1[it].x);
-                    if (x1 + 1 < w1) __stcs(p + 1, l1[it].y);
+                    cv_corr_st(p, l1[it].x, cs);
+                    if (x1 + 1 < w1) cv_corr_st(p + 1, l1[it].y, cs);
                 }
             }
     }
@@ -434,7 +440,7 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
         const size_t n2 = (size_t)h2 * w2;
 #pragma unroll
         for (int it = 0; it < 4; ++it)
-            if ((inside_mask >> it) & 1u) __stcs(P.corr_lvl[2] + (size_t)pix[it] * n2 + (size_t)y2 * w2 + x2, l2[it]);
+            if ((inside_mask >> it) & 1u) cv_corr_st(P.corr_lvl[2] + (size_t)pix[it] * n2 + (size_t)y2 * w2 + x2, l2[it], cs);
     }
     if ((c & 7) == 3) {
 #pragma unroll
@@ -448,7 +454,7 @@ __device__ __forceinline__ void cv_epilogue_corr(const ConvParams &P, const floa
         const float top_r = __shfl_xor_sync(0xffffffffu, st.l2p[it], 1), bot_r = __shfl_xor_sync(0xffffffffu, l2[it], 1);
         if (!(lane & 1) && y3 < h3 && x3 < w3 && ((inside_mask >> it) & 1u)) {
             const float v = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(st.l2p[it], top_r), l2[it]), bot_r), 0.25f);
-            __stcs(P.corr_lvl[3] + (size_t)pix[it] * ((size_t)h3 * w3) + (size_t)y3 * w3 + x3, v);
+            cv_corr_st(P.corr_lvl[3] + (size_t)pix[it] * ((size_t)h3 * w3) + (size_t)y3 * w3 + x3, v, cs);
         }
     }
 }
@@ -970,12 +976,13 @@ static int cv_load_encode() {
 
 // Probe / A-B switches from the environment, read once per process (not on every plan creation).
 struct CvEnv {
-    bool no_pair, generic, corr_resident_a;
+    bool no_pair, generic, corr_resident_a, corr_plain_stores;
     int a_stages, dbg;
     CvEnv() {
         const char *e = getenv("RPE_CONV_PAIR");
         no_pair = e && e[0] == '0';
         generic = getenv("RPE_CONV_GENERIC") != nullptr;
+        corr_plain_stores = getenv("RPE_CORR_PLAIN_STORES") != nullptr;   // A-B switch: default cache operator for the pyramid stores
         corr_resident_a = getenv("RPE_CORR_RESIDENT_A") != nullptr;  // A-B switch: keep the query tile of the correlation kernel resident
         e = getenv("RPE_CONV_ASTAGES");
         a_stages = e ? atoi(e) : 0;
@@ -1279,6 +1286,7 @@ int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_h
         p.corr_vec = 0;
         if ((w % 4) == 0 && (((size_t)h * w) % 4) == 0) p.corr_vec |= 1;
         if (num_levels > 1 && ((w >> 1) % 2) == 0 && (((size_t)(h >> 1) * (w >> 1)) % 2) == 0 && (w % 2) == 0) p.corr_vec |= 2;
+        if (!cv_env().corr_plain_stores) p.corr_vec |= 16;         // streaming (evict-first) stores for the pyramid
     }
     for (int pln = 0; pln < 2; ++pln) {
         const cuuint64_t pix = (cuuint64_t)C * 2, row = pix * w;

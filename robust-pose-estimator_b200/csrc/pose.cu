@@ -523,7 +523,7 @@ __device__ void write_result(const PoseParams &P, int pair, const SolverState &S
 }
 
 template <bool kHess>
-__global__ void __launch_bounds__(kPoseThreads) pose_solve_kernel(PoseParams P) {
+__global__ void __launch_bounds__(kPoseThreads, kHess ? 1 : 2) pose_solve_kernel(PoseParams P) {
     __shared__ SolverState S;
     __shared__ double s_red[(kPoseThreads / 32) * kAccHess];
     __shared__ PixelConsts C;
@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kPoseThreads) pose_solve_kernel(PoseParams P) 
 }
 
 static int g_pose_groups = 0;    // upper bound on concurrently solved pairs; 0 = as many as the CTA slots allow
-static int g_pose_bpg = 32;      // CTAs per group in batch mode (power of two <= kVirt)
+static int g_pose_bpg = 16;      // CTAs per group in batch mode (power of two <= kVirt)
 
 }  // namespace rpe
 
