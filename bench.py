@@ -396,7 +396,8 @@ def main():
             for name, evs in timers.items():
                 t = [a.elapsed_time(b) for a, b, _ in evs]
                 units = sum(u for _, _, u in evs)
-                stage[name] = {"launches": len(evs), "total_ms": float(np.sum(t)), "avg_us": 1e3 * float(np.mean(t)), "units": units}
+                stage[name] = {"launches": len(evs), "total_ms": float(np.sum(t)), "avg_us": 1e3 * float(np.mean(t)),
+                               "min_us": 1e3 * float(np.min(t)), "max_us": 1e3 * float(np.max(t)), "units": units}
             ops.enable_timers(False)
         for _ in range(max(1, min(2, args.warmup))):
             e2e_step()

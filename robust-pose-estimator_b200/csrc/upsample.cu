@@ -1,14 +1,14 @@
 // RAFT convex 8x flow up-sampling (reference: /root/reference/core/RAFT/core/raft.py:66-77).
 //   out[b, c, 8y+i, 8x+j] = sum_k softmax_k(mask[b, k*64 + i*8 + j, y, x]) * 8 * flow[b, c, y+ky-1, x+kx-1]
 // with k = 3*ky + kx over the zero-padded 3x3 neighbourhood (F.unfold(8*flow, 3, padding=1)).
-// CTA = one coarse row y, 32 coarse columns: the 576 x 32 mask tile is staged through shared memory
-// with 128-byte coalesced reads; each thread owns one of the 256 fine columns and walks the 8 fine rows,
-// so the (B,2,8h,8w) output is written in full 1 KB row segments.
+// CTA = one coarse row y, 8 coarse columns: the 576 x 8 mask tile (18 KB, so ~10 CTAs per SM keep the loads of one tile
+// behind the arithmetic of the others; the first version staged 32 columns = 76 KB and ran at 2 CTAs per SM, 0.18 of HBM) is
+// staged through shared memory with coalesced reads; thread = (cell, pair of fine rows, fine column).
 #include "common.cuh"
 
 namespace rpe {
 
-constexpr int kUpCells = 32;
+constexpr int kUpCells = 8;
 
 __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float *__restrict__ flow, const float *__restrict__ mask,
                                                                float *__restrict__ out, int h, int w, int mask_nhwc_ld) {
@@ -39,11 +39,11 @@ __global__ void __launch_bounds__(256) convex_upsample8_kernel(const float *__re
         s_flow[e] = v;
     }
     __syncthreads();
-    const int xl = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int xl = threadIdx.x >> 5, i0 = ((threadIdx.x >> 3) & 3) * 2, j = threadIdx.x & 7;
     if (xl >= ncell) return;
     const int W8 = 8 * w;
-#pragma unroll 1
-    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int i = i0; i < i0 + 2; ++i) {
         float m[9];
         float mx = -INFINITY;
 #pragma unroll
