@@ -232,7 +232,7 @@ int rpe_convex_upsample8_nhwc(const float *flow, const float *mask, int mask_ld,
  * ---------------------------------------------------------------------------------------------- */
 typedef struct rpe_conv_source {
     const void *act_hi;  /* fp16 NHWC (N,H,W,c_total): hi plane                                       */
-    const void *act_lo;  /* lo plane, or NULL for single-pass fp16 (then w_lo must be NULL too)       */
+    const void *act_lo;  /* lo plane, or NULL: activations exact in one fp16 plane (w_lo may still be set)   */
     int c_total;         /* channel stride of the activation tensor (multiple of 8)                   */
     int c_offset;        /* first channel read (multiple of 8)                                        */
     int c_count;         /* channels read (multiple of 16); channels past the window read as zero     */
@@ -311,6 +311,10 @@ int rpe_im2col7s2_split(const float *img, void *out_hi, void *out_lo, int n, int
 /* The same with the frames as uint8 RGB (n,3,H,W), the way a camera delivers them (ship uint8, convert on the GPU):
  * the uint8 -> float conversion of dataset/stereo_dataset.py:36-37 happens inside the kernels that read the image. */
 int rpe_im2col7s2_split_u8(const unsigned char *img, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream);
+/*   out_lo = NULL selects the RAW single-plane form: the window holds the pixel values themselves (integers 0..255 are exact in one
+ *   fp16 plane; positions outside the image hold 127.5, whose normalisation is the reference's zero padding) and the caller folds
+ *   2 v / 255 - 1 into the stem weights (w' = 2 w / 255, b' = b - sum w).  The convolution then reads one activation plane and
+ *   two weight planes (rpe_conv_source.act_lo = NULL, w_lo set): two tensor-core products per multiply-add instead of three. */
 size_t rpe_instnorm_workspace_bytes(int n, int C);
 int rpe_instnorm_stats(const float *x, float *stats, int n, int HW, int C, float eps, void *workspace, size_t workspace_bytes,
                        void *stream);

@@ -21,16 +21,19 @@ STEM_K = 168            # 7 filter rows x 24 (21 real taps*channels + 3 zeros)
 STEM_LD = 176
 
 
-def stem_planes(images, out=None):
+def stem_planes(images, out=None, raw=False):
     """im2col of the 7x7 / 2 stem for NCHW images in 0..255 (fp32, or uint8 as the camera delivers them) -> split planes
-    (n, H/2, W/2, STEM_LD)."""
+    (n, H/2, W/2, STEM_LD) of the normalised image.  ``raw`` (uint8 only): ONE plane of the raw pixel values (exact in fp16), for
+    the stem plans whose weights carry the normalisation (``EncoderTC(raw_stem=True)``)."""
     import torch
     n, _, H, W = images.shape
     if out is None:
         out = Planes(n, (H - 1) // 2 + 1, (W - 1) // 2 + 1, STEM_LD, images.device)
-    fn = _lib.lib().rpe_im2col7s2_split_u8 if images.dtype == torch.uint8 else _lib.lib().rpe_im2col7s2_split
+    u8 = images.dtype == torch.uint8
+    assert u8 or not raw, "the raw stem form needs uint8 frames"
+    fn = _lib.lib().rpe_im2col7s2_split_u8 if u8 else _lib.lib().rpe_im2col7s2_split
     with _timed("im2col_stem", n):
-        check(fn(_p(images), _p(out.hi), _p(out.lo), n, H, W, STEM_LD, _stream()), "rpe_im2col7s2_split")
+        check(fn(_p(images), _p(out.hi), _p(None if raw else out.lo), n, H, W, STEM_LD, _stream()), "rpe_im2col7s2_split")
     return out
 
 
@@ -53,10 +56,13 @@ class EncoderTC:
             b = (b - W[p + bn + ".running_mean"].float()) * s + W[p + bn + ".bias"].float()
         return w, b
 
-    def _wb(self, conv, bn, c_lo=None, c_hi=None):
-        key = (conv, c_lo, c_hi)
+    def _wb(self, conv, bn, c_lo=None, c_hi=None, raw=False):
+        key = (conv, c_lo, c_hi, raw)
         if key not in self._packed:
             w, b = self._folded(conv, bn) if bn else (self.W[self.prefix + conv + ".weight"].float(), self.W[self.prefix + conv + ".bias"].float())
+            if raw:                                               # conv(2 v / 255 - 1) = conv'(v): w' = 2 w / 255, b' = b - sum w (raft.py:82-83)
+                b = b - w.double().sum((1, 2, 3)).float()
+                w = w * (2.0 / 255.0)
             if conv == "conv1":                                   # stem: K = ky*24 + kx*3 + c
                 wk = torch.zeros((w.shape[0], 7, 24), dtype=torch.float32, device=w.device)
                 wk[:, :, :21] = w.permute(0, 2, 3, 1).reshape(w.shape[0], 7, 21)
@@ -68,12 +74,12 @@ class EncoderTC:
         return self._packed[key]
 
     # ---- per-shape state -------------------------------------------------------------------------------
-    def _state(self, n, H, W, device, shared_col=None, dests=None):
+    def _state(self, n, H, W, device, shared_col=None, dests=None, raw_stem=False):
         """dests: per output head a dict(out_f32=fp32 NHWC tensor or None, out_planes=Planes or None) the head convolution writes
         to directly (the batched tracker points them into the correlation / update-operator buffers); default: own fp32 tensors."""
         dkey = None if dests is None else tuple((None if d.get("out_f32") is None else d["out_f32"].data_ptr(),
                                                  None if d.get("out_planes") is None else d["out_planes"].hi.data_ptr()) for d in dests)
-        key = (n, H, W, device.index, None if shared_col is None else shared_col.hi.data_ptr(), dkey)
+        key = (n, H, W, device.index, None if shared_col is None else shared_col.hi.data_ptr(), dkey, raw_stem)
         st = self._shapes.get(key)
         if st is not None:
             return st
@@ -105,13 +111,14 @@ class EncoderTC:
             st["steps"].append(("norm", a, sa, relu_a, b, sb, out, planes, hw, c))
 
         def conv(name, bn, src, dims, k, cout, act, stride=1, out_f32=None, out_planes=None, res=None):
-            (wts, bias) = self._wb(name, bn)
+            raw = raw_stem and name == "conv1"
+            (wts, bias) = self._wb(name, bn, raw=raw)
             cin = src.c if name != "conv1" else STEM_K
             oh, ow = (dims[1] - 1) // stride + 1, (dims[2] - 1) // stride + 1
             want_stats = (fused_stats and out_f32 is not None and out_planes is None and res is None and act == "none" and cout % 16 == 0
                           and n * tiles_of(oh, ow) * 4 * cout * 2 <= part.numel())
             plan = ConvPlan(self.prefix + name, [(src, 0, min(cin, wts[0].shape[-1]), wts)], dims, k, k, cout, act, bias=bias, stride=stride,
-                            out_f32=out_f32, out_planes=out_planes, res=res, stat_partials=part if want_stats else None)
+                            out_f32=out_f32, out_planes=out_planes, res=res, stat_partials=part if want_stats else None, act_single=raw)
             if want_stats:
                 assert plan.tiles_per_image == tiles_of(oh, ow), (plan.tiles_per_image, oh, ow)
                 pending[out_f32.data_ptr()] = plan
@@ -187,16 +194,16 @@ class EncoderTC:
         return st
 
     # ---- execution ---------------------------------------------------------------------------------------
-    def forward(self, images, col=None, dests=None):
+    def forward(self, images, col=None, dests=None, raw_stem=False):
         """images (n,3,H,W) fp32 in 0..255 -> list of fp32 NHWC outputs, one per head (buffers reused by the next call).
         ``col``: already filled im2col planes from ``stem_planes`` whose first n images are these images (the context encoder
         reads the same left images as the feature encoder); the plans are then bound to that buffer.  ``dests``: see ``_state``."""
         n, _, H, W = images.shape
-        st = self._state(n, H, W, images.device, col, dests)
+        st = self._state(n, H, W, images.device, col, dests, raw_stem)
         l = _lib.lib()
         s = _stream()
         if col is None:
-            stem_planes(images, st["col"])
+            stem_planes(images, st["col"], raw=raw_stem)
         for step in st["steps"]:
             kind = step[0]
             if kind == "conv":

@@ -131,10 +131,11 @@ class RAFT(nn.Module):
         (planes) and relu(inp) into ``inp_dst`` (planes) -- the update operator's own state buffers.  No NCHW round trip."""
         assert self.precision == "fp16x3"
         fe, ce = self._encoders()
-        key = tuple(imgs.shape) + (imgs.device.index,)
-        col = self._col[key] = stem_planes(imgs, self._col.get(key))
-        fe.forward(imgs, col, dests=[{"out_planes": feat_dst}])
-        ce.forward(imgs[:n_left], col, dests=[{"out_f32": h_dst, "out_planes": hp_dst}, {"out_planes": inp_dst}])
+        raw = imgs.dtype == torch.uint8                # raw single-plane stem: the normalisation lives in the stem weights
+        key = tuple(imgs.shape) + (imgs.device.index, raw)
+        col = self._col[key] = stem_planes(imgs, self._col.get(key), raw=raw)
+        fe.forward(imgs, col, dests=[{"out_planes": feat_dst}], raw_stem=raw)
+        ce.forward(imgs[:n_left], col, dests=[{"out_f32": h_dst, "out_planes": hp_dst}, {"out_planes": inp_dst}], raw_stem=raw)
 
     def features(self, images):
         """fnet over (N,3,H,W) images in 0..255 -> (N,256,H/8,W/8) float32."""

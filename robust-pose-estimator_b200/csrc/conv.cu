@@ -59,7 +59,7 @@ struct alignas(64) ConvParams {
     CUtensorMap wmap[kCvMaxSrc][2];
     int cblocks[kCvMaxSrc];
     int ksteps_last[kCvMaxSrc];                       // 16-channel MMA steps of the last K block (1..4)
-    int n_src, n_planes;
+    int n_src, n_planes, w_planes;                    // planes of the activations (1 or 2) and of the weights (1 or 2)
     int N, OH, OW, tiles_min, tiles_maj;
     int orient;                                       // 0: minor axis = x, 1: minor axis = y
     int kmin, kmaj, pad_min, pad_maj, stride, kw;
@@ -620,9 +620,9 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < P.n_src; ++s)
-            for (int p = 0; p < P.n_planes; ++p) {
-                prefetch_tmap(&P.amap[s][p]);
-                prefetch_tmap(&P.wmap[s][p]);
+            for (int p = 0; p < 2; ++p) {
+                if (p < P.n_planes) prefetch_tmap(&P.amap[s][p]);
+                if (p < P.w_planes) prefetch_tmap(&P.wmap[s][p]);
             }
     }
     if (warp == 1 && lane == 0) {
@@ -692,14 +692,14 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
             if (P.resident_b) {
                 // the whole weight set fits: one load per CTA, [source K block][tap][plane] tiles
                 uint32_t total = 0;
-                for (int s = 0; s < P.n_src; ++s) total += (uint32_t)P.cblocks[s] * taps * P.n_planes * P.b_plane_bytes;
+                for (int s = 0; s < P.n_src; ++s) total += (uint32_t)P.cblocks[s] * taps * P.w_planes * P.b_plane_bytes;
                 if (u_first < num_units) {
                     if (rank == 0) mbar_expect_tx(&b_full[0], total * load_mult);
                     for (int s = 0; s < P.n_src; ++s)
                         for (int cb = 0; cb < P.cblocks[s]; ++cb)
                             for (int tap = 0; tap < taps; ++tap)
-                                for (int p = 0; p < P.n_planes; ++p) {
-                                    uint8_t *dst = sB + (size_t)(((P.cb_base[s] + cb) * taps + tap) * P.n_planes + p) * P.b_plane_bytes;
+                                for (int p = 0; p < P.w_planes; ++p) {
+                                    uint8_t *dst = sB + (size_t)(((P.cb_base[s] + cb) * taps + tap) * P.w_planes + p) * P.b_plane_bytes;
                                     if (kPair) tma_load_3d_pair(dst, &P.wmap[s][p], mapa_shared(smem_u32(&b_full[0]), 0), cb * kCvBK, brow, tap);
                                     else tma_load_3d(dst, &P.wmap[s][p], &b_full[0], cb * kCvBK, 0, tap);
                                 }
@@ -716,7 +716,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                             for (int tm = 0; tm < P.kmin; ++tm)
                                 for (int tj = 0; tj < P.kmaj; ++tj) {
                                     const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
-                                    for (int p = 0; p < P.n_planes; ++p) {          // one ring entry per plane tile
+                                    for (int p = 0; p < P.w_planes; ++p) {          // one ring entry per plane tile
                                         mbar_wait(&b_empty[stage], phase ^ 1);
                                         if (rank == 0) mbar_expect_tx(&b_full[stage], P.b_plane_bytes * load_mult);
                                         uint8_t *dst = sB + (size_t)stage * P.b_plane_bytes;
@@ -749,7 +749,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         const uint32_t idesc = (1u << 4) | ((uint32_t)(P.bn >> 3) << 17) |
                                ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);
         const bool no_load = (RPE_CV_DBG(P) & 1) != 0, no_mma = (RPE_CV_DBG(P) & 2) != 0;
-        const bool planes2 = P.n_planes == 2, reuse = P.reuse != 0, resident = P.resident_b != 0;
+        // products per tap: a_hi * w_hi, + a_lo * w_hi with two activation planes, + a_hi * w_lo with two weight planes
+        const bool a2 = P.n_planes == 2, w2 = P.w_planes == 2, reuse = P.reuse != 0, resident = P.resident_b != 0;
         // shared-memory descriptors = constant upper word | (address >> 4); ring positions advance the low word only
         const uint32_t a_base16 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16), b_base16 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
         const uint32_t a_stage16 = P.a_stage_bytes >> 4, a_plane16 = P.a_plane_bytes >> 4, b_plane16 = P.b_plane_bytes >> 4;
@@ -780,13 +781,11 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                 }
                                 tcgen05_fence_after();
                                 const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
-                                const uint32_t b_hi = b_base16 + (uint32_t)(((P.cb_base[s] + cb) * taps + tap) * P.n_planes) * b_plane16;
+                                const uint32_t b_hi = b_base16 + (uint32_t)(((P.cb_base[s] + cb) * taps + tap) * P.w_planes) * b_plane16;
                                 if (leader && !no_mma) {
                                     cv_mma_k<kPair>(d_tmem, a_hi, b_hi, idesc, accumulate, ksteps);
-                                    if (planes2) {
-                                        cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
-                                        cv_mma_k<kPair>(d_tmem, a_hi, b_hi + b_plane16, idesc, 1u, ksteps);
-                                    }
+                                    if (a2) cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
+                                    if (w2) cv_mma_k<kPair>(d_tmem, a_hi, b_hi + b_plane16, idesc, 1u, ksteps);
                                 }
                             } else {
                                 if (!no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
@@ -795,12 +794,12 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                 if (leader) {
                                     if (!no_mma) {
                                         cv_mma_k<kPair>(d_tmem, a_hi, b_hi, idesc, accumulate, ksteps);
-                                        if (planes2) cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
+                                        if (a2) cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
                                     }
                                     if (!no_load) cv_commit_u32<kPair>(b_empty_u + sb * 8u);
                                 }
                                 if (++sb == (uint32_t)n_b) sb = 0, pb ^= 1u;
-                                if (planes2) {
+                                if (w2) {
                                     if (!no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
                                     tcgen05_fence_after();
                                     if (leader) {
@@ -1061,6 +1060,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     const int slab_rows = p.reuse ? 16 + p.kmaj - 1 : 16;
     p.n_src = d->n_sources;
     p.n_planes = d->src[0].act_lo ? 2 : 1;
+    p.w_planes = d->src[0].w_lo ? 2 : 1;              // (1 activation plane x 2 weight planes: exact 16-bit inputs such as raw uint8 frames)
     // CTA pairs (cta_group::2): each CTA of a 2-cluster loads half of every weight tile.  RPE_CONV_PAIR=0 disables.
     const int px_tiles = d->N * (((orient == 0 ? OW : OH) + 7) / 8) * (((orient == 0 ? OH : OW) + 15) / 16);
     pl->pair = !cv_env().no_pair && (bn % 32 == 0) && px_tiles >= 2 && sm_count() >= 2;
@@ -1068,12 +1068,12 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.a_plane_bytes = (uint32_t)slab_rows * 8 * 128;
     p.a_stage_bytes = p.a_plane_bytes * p.n_planes;
     p.b_plane_bytes = (uint32_t)b_rows * 128;
-    p.b_stage_bytes = p.b_plane_bytes * p.n_planes;
+    p.b_stage_bytes = p.b_plane_bytes * p.w_planes;
     const int taps = d->kh * d->kw;
     // Weights resident in shared memory when the whole set fits beside two activation stages (small layers: every tile would
     // otherwise re-stream them); else a ring whose entries are single plane tiles, so that many small loads are in flight.
     size_t total_b = 0;
-    for (int s = 0; s < d->n_sources; ++s) total_b += (size_t)((d->src[s].c_count + kCvBK - 1) / kCvBK) * taps * p.n_planes * p.b_plane_bytes;
+    for (int s = 0; s < d->n_sources; ++s) total_b += (size_t)((d->src[s].c_count + kCvBK - 1) / kCvBK) * taps * p.w_planes * p.b_plane_bytes;
     p.resident_b = (n_blocks == 1 && total_b + 2 * (size_t)p.a_stage_bytes <= (size_t)kCvSmemData) ? 1 : 0;
     if (p.resident_b) {
         p.n_a_stages = (int)(((size_t)kCvSmemData - total_b) / p.a_stage_bytes);
@@ -1096,7 +1096,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     double macs = 0.0;
     for (int s = 0; s < d->n_sources; ++s) {
         const rpe_conv_source &sc = d->src[s];
-        if (!sc.act_hi || !sc.w_hi || ((sc.act_lo != nullptr) != (p.n_planes == 2)) || ((sc.w_lo != nullptr) != (p.n_planes == 2)) ||
+        if (!sc.act_hi || !sc.w_hi || ((sc.act_lo != nullptr) != (p.n_planes == 2)) || ((sc.w_lo != nullptr) != (p.w_planes == 2)) ||
             sc.c_count <= 0 || (sc.c_count % 16) || (sc.c_offset % 8) || (sc.c_total % 8) || sc.c_offset + sc.c_count > sc.c_total ||
             sc.w_cstride < sc.c_count || (sc.w_cstride % 8)) {
             delete pl;
@@ -1106,14 +1106,14 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         p.cb_base[s] = s == 0 ? 0 : p.cb_base[s - 1] + p.cblocks[s - 1];
         p.ksteps_last[s] = (sc.c_count - (p.cblocks[s] - 1) * kCvBK) / 16;
         macs += (double)sc.c_count * taps;
-        for (int pln = 0; pln < p.n_planes; ++pln) {
+        for (int pln = 0; pln < 2; ++pln) {
             const void *act = pln == 0 ? sc.act_hi : sc.act_lo;
             const void *wgt = pln == 0 ? sc.w_hi : sc.w_lo;
             if ((reinterpret_cast<uintptr_t>(act) & 15u) || (reinterpret_cast<uintptr_t>(wgt) & 15u)) {
                 delete pl;
                 return RPE_ERR_ALIGNMENT;
             }
-            {   // activations: (C, minor, major, N) fp16; the channel window starts at c_offset, channels beyond it read as zero
+            if (pln < p.n_planes) {   // activations: (C, minor, major, N) fp16; the channel window starts at c_offset, channels beyond it read as zero
                 const char *base = reinterpret_cast<const char *>(act) + (size_t)sc.c_offset * 2;
                 const cuuint64_t pix = (cuuint64_t)sc.c_total * 2, row = pix * d->W;
                 cuuint64_t dims[4] = {(cuuint64_t)sc.c_count, (cuuint64_t)(orient == 0 ? d->W : d->H),
@@ -1130,7 +1130,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
                     return RPE_ERR_CUDA;
                 }
             }
-            {   // weights: (Cin_s, Cout_pad, taps) fp16 with row pitch w_cstride, box (64, bn, 1)
+            if (pln < p.w_planes) {   // weights: (Cin_s, Cout_pad, taps) fp16 with row pitch w_cstride, box (64, bn, 1)
                 cuuint64_t dims[3] = {(cuuint64_t)sc.c_count, (cuuint64_t)d->cout_pad, (cuuint64_t)taps};
                 cuuint64_t strides[2] = {(cuuint64_t)sc.w_cstride * 2, (cuuint64_t)sc.w_cstride * 2 * d->cout_pad};
                 cuuint32_t box[3] = {kCvBK, (cuuint32_t)b_rows, 1};
@@ -1173,7 +1173,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
             return RPE_ERR_INVALID_ARG;
         }
     }
-    pl->flops = 2.0 * macs * (double)d->cout * (double)d->N * OH * OW * (p.n_planes == 2 ? 3.0 : 1.0);
+    pl->flops = 2.0 * macs * (double)d->cout * (double)d->N * OH * OW * (double)(1 + (p.n_planes == 2) + (p.w_planes == 2));
     if (pl->pair) {
         const int units = ((px_tiles + 1) / 2) * p.n_blocks;
         int clusters = sm_count() / 2;
@@ -1242,7 +1242,7 @@ int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_h
     if (rc != RPE_OK) return rc;
     ConvParams p;
     memset(&p, 0, sizeof(p));
-    p.n_src = 1, p.n_planes = 2;
+    p.n_src = 1, p.n_planes = 2, p.w_planes = 2;
     p.cblocks[0] = C / kCvBK, p.cb_base[0] = 0, p.ksteps_last[0] = kCvBK / 16;
     p.N = B, p.OH = h, p.OW = w;
     p.orient = 0, p.kmin = 1, p.kmaj = 1, p.pad_min = 0, p.pad_maj = 0, p.stride = 1, p.kw = 1, p.reuse = 1;

@@ -26,7 +26,11 @@ __device__ __forceinline__ void split4(const float *v, uint2 &hi, uint2 &lo) {
 // shared memory with coalesced loads (normalised on the way in, zeros outside the image), then thread (pixel, ky) assembles
 // its 24 values in a second shared tile and the CTA copies its contiguous 32 x 352-byte output range in 16-byte chunks.
 constexpr int kStemPx = 32, kStemCols = 2 * kStemPx + 5, kStemPitch = 72, kStemLd = 176;
-template <typename T>      // float (the reference's 0..255 float tensors) or uint8_t (camera frames as they are: same values)
+// kRaw (uint8 frames only): the window holds the RAW pixel values -- integers 0..255 are exact in ONE fp16 plane, so no lo plane
+// is written -- and positions outside the image hold 127.5, the raw value whose normalisation 2 v / 255 - 1 is the zero the
+// reference pads with; the affine map itself is folded into the stem weights (w' = 2 w / 255, b' = b - sum w; encoder_tc.py).
+// Half the bytes of the split form and two tensor-core products per multiply-add instead of three.
+template <typename T, bool kRaw>      // T: float (the reference's 0..255 float tensors) or uint8_t (camera frames as they are)
 __global__ void __launch_bounds__(256) im2col7s2_kernel(const T *__restrict__ img, plane_t *__restrict__ hi,
                                                         plane_t *__restrict__ lo, int H, int W, int OH, int OW, int ld) {
     __shared__ float tile[7][3][kStemPitch];
@@ -37,8 +41,11 @@ __global__ void __launch_bounds__(256) im2col7s2_kernel(const T *__restrict__ im
         const int col = i % kStemPitch, rc = i / kStemPitch;
         const int c = rc % 3, r = rc / 3;
         const int y = y0 + r, x = x0 + col;
-        float v = 0.0f;
-        if (col < kStemCols && y >= 0 && y < H && x >= 0 && x < W) v = 2.0f * ((float)__ldg(base + ((size_t)c * H + y) * W + x) / 255.0f) - 1.0f;
+        float v = kRaw ? 127.5f : 0.0f;
+        if (col < kStemCols && y >= 0 && y < H && x >= 0 && x < W) {
+            v = (float)__ldg(base + ((size_t)c * H + y) * W + x);
+            if (!kRaw) v = 2.0f * (v / 255.0f) - 1.0f;
+        }
         tile[r][c][col] = v;
     }
     __syncthreads();
@@ -59,21 +66,26 @@ __global__ void __launch_bounds__(256) im2col7s2_kernel(const T *__restrict__ im
             uint2 h, l;
             split4(v + g * 4, h, l);
             *reinterpret_cast<uint2 *>(&s_hi[p][ky * 24 + g * 4]) = h;
-            *reinterpret_cast<uint2 *>(&s_lo[p][ky * 24 + g * 4]) = l;
+            if (!kRaw) *reinterpret_cast<uint2 *>(&s_lo[p][ky * 24 + g * 4]) = l;
         }
         if (ky == 0) {                                       // channels 168..175: padding of the K axis, kept at zero
             *reinterpret_cast<uint4 *>(&s_hi[p][168]) = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4 *>(&s_lo[p][168]) = make_uint4(0, 0, 0, 0);
+            if (!kRaw) *reinterpret_cast<uint4 *>(&s_lo[p][168]) = make_uint4(0, 0, 0, 0);
         }
     }
     __syncthreads();
     const size_t pix0 = ((size_t)n * OH + oy) * OW + ox0;
-    uint4 *ghi = reinterpret_cast<uint4 *>(hi + pix0 * kStemLd), *glo = reinterpret_cast<uint4 *>(lo + pix0 * kStemLd);
+    uint4 *ghi = reinterpret_cast<uint4 *>(hi + pix0 * kStemLd);
     const uint4 *shi = reinterpret_cast<const uint4 *>(&s_hi[0][0]), *slo = reinterpret_cast<const uint4 *>(&s_lo[0][0]);
     const int chunks = npx * (kStemLd * 2 / 16);
-    for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
-        ghi[i] = shi[i];
-        glo[i] = slo[i];
+    if (kRaw) {
+        for (int i = threadIdx.x; i < chunks; i += blockDim.x) ghi[i] = shi[i];
+    } else {
+        uint4 *glo = reinterpret_cast<uint4 *>(lo + pix0 * kStemLd);
+        for (int i = threadIdx.x; i < chunks; i += blockDim.x) {
+            ghi[i] = shi[i];
+            glo[i] = slo[i];
+        }
     }
 }
 
@@ -215,17 +227,20 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__
 extern "C" {
 
 static int im2col7s2_impl(const void *img, int is_u8, void *out_hi, void *out_lo, int n, int H, int W, int ld, void *stream) {
-    if (!img || !out_hi || !out_lo || n <= 0 || H <= 0 || W <= 0 || ld < 168 || (ld % 8)) return RPE_ERR_INVALID_ARG;
+    if (!img || !out_hi || (!out_lo && !is_u8) || n <= 0 || H <= 0 || W <= 0 || ld < 168 || (ld % 8)) return RPE_ERR_INVALID_ARG;
     if ((reinterpret_cast<uintptr_t>(out_hi) & 15u) || (reinterpret_cast<uintptr_t>(out_lo) & 15u)) return RPE_ERR_ALIGNMENT;
     const int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
     if (OH > 65535 || n > 65535 || ld != rpe::kStemLd) return RPE_ERR_INVALID_ARG;      // the staged copy assumes the 176-channel pitch
     dim3 grid((OW + rpe::kStemPx - 1) / rpe::kStemPx, OH, n);
-    if (is_u8)
-        rpe::im2col7s2_kernel<uint8_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)img, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo,
-                                                                               H, W, OH, OW, ld);
+    if (is_u8 && !out_lo)        // raw single-plane form (out_lo = NULL)
+        rpe::im2col7s2_kernel<uint8_t, true><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)img, (rpe::plane_t *)out_hi, nullptr, H, W,
+                                                                                     OH, OW, ld);
+    else if (is_u8)
+        rpe::im2col7s2_kernel<uint8_t, false><<<grid, 256, 0, (cudaStream_t)stream>>>((const uint8_t *)img, (rpe::plane_t *)out_hi,
+                                                                                      (rpe::plane_t *)out_lo, H, W, OH, OW, ld);
     else
-        rpe::im2col7s2_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)img, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, H,
-                                                                             W, OH, OW, ld);
+        rpe::im2col7s2_kernel<float, false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)img, (rpe::plane_t *)out_hi,
+                                                                                    (rpe::plane_t *)out_lo, H, W, OH, OW, ld);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
 }

@@ -82,7 +82,8 @@ class ConvPlan:
     """One convolution bound to its input / output buffers.  ``inputs``: [(Planes, c_offset, c_count, (w_hi, w_lo))]."""
 
     def __init__(self, name, inputs, dims, kh, kw, cout, act="none", bias=None, stride=1, out_f32=None, f32_off=0, out_planes=None,
-                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None, stat_partials=None):
+                 bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None, stat_partials=None,
+                 act_single=False):
         n, h, w = dims
         cout_pad = (cout + 15) // 16 * 16
         d = _lib.ConvDesc()
@@ -101,7 +102,8 @@ class ConvPlan:
             assert planes.shape[1:3] == (h, w) and planes.shape[0] >= n, f"{name}: source {k} has shape {planes.shape}, expected {(n, h, w)}"
             assert w_hi.shape[1] == cout_pad, f"{name}: weight packed for cout_pad {w_hi.shape[1]}, plan needs {cout_pad}"
             s = d.src[k]
-            s.act_hi, s.act_lo = planes.hi.data_ptr(), (0 if single_pass else planes.lo.data_ptr())
+            # act_single: the activations are exact in their hi plane (raw uint8 frames); the weights keep both planes
+            s.act_hi, s.act_lo = planes.hi.data_ptr(), (0 if (single_pass or act_single) else planes.lo.data_ptr())
             s.c_total, s.c_offset, s.c_count = planes.c, c_off, (c_cnt + 15) // 16 * 16
             s.w_hi, s.w_lo, s.w_cstride = w_hi.data_ptr(), (0 if single_pass else w_lo.data_ptr()), w_hi.shape[-1]
             self._keep += [planes, w_hi, w_lo]

@@ -219,10 +219,15 @@ def test_infer_sequence_from_pinned_host_frames(golden_dir):
     L8 = torch.from_numpy(np.clip(np.round(g["imgs_l"]), 0, 255).astype(np.uint8))[idx].contiguous().pin_memory()
     R8 = torch.from_numpy(np.clip(np.round(g["imgs_r"]), 0, 255).astype(np.uint8))[idx].contiguous().pin_memory()
     M = torch.from_numpy(np.stack([unpack(g["masks_in"][i], (1, H, W)) for i in range(3)]))[idx].contiguous().pin_memory()
-    ref, failed_ref = est.infer_sequence(L8.cuda().float(), R8.cuda().float(), M.cuda(), chunk=2)
+    ref, failed_ref = est.infer_sequence(L8.cuda(), R8.cuda(), M.cuda(), chunk=2)              # device-resident uint8 frames
     est.last_pose = SE3.Identity(1, device="cuda")
     got, failed = est.infer_sequence(L8, R8, M, chunk=2)
     assert got.shape == (6, 7) and torch.equal(got, ref) and torch.equal(failed, failed_ref)
+    # float frames (the reference's tensors) take the normalised two-plane stem instead of the raw single-plane one: same poses
+    # up to fp32 rounding
+    est.last_pose = SE3.Identity(1, device="cuda")
+    flt, _ = est.infer_sequence(L8.cuda().float(), R8.cuda().float(), M.cuda(), chunk=2)
+    assert float((flt - ref).abs().max()) < 1e-4 * float(ref.abs().max())
 
 
 @pytest.mark.parametrize("chunk,graphs,precision", [(1, False, "fp32"), (2, False, "fp32"), (2, True, "fp32"), (2, False, "fp16x3"),

@@ -36,3 +36,28 @@ feat.hi.normal_()
 feat.lo.normal_(std=1e-3)
 ms = timeit(lambda: ops.CorrPyramid.from_planes(feat, feat.view(B), B))
 print(f"corr_build planes in       B={B}: {ms:7.3f} ms  {alg / ms / 1e6:7.1f} GB/s pyramid write  {2 * B * 5120 * 5120 * 256 / ms / 1e9:7.1f} TFLOP/s algorithmic")
+
+# sustained: the same launch back to back for ~1.5 s (the bench runs under the power cap; a 20 ms burst does not)
+def sustained(fn, seconds=1.5):
+    fn(); torch.cuda.synchronize()
+    import time
+    t_end = time.time() + seconds
+    n = 0
+    while time.time() < t_end:
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        n += 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 20, n
+
+
+ms, n = sustained(lambda: ops.CorrPyramid.from_planes(feat, feat.view(B), B))
+print(f"corr_build planes in, SUSTAINED after {n} back-to-back launches: {ms:7.3f} ms  {alg / ms / 1e6:7.1f} GB/s pyramid write")
+import subprocess
+print(subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw,clocks_event_reasons.sw_power_cap", "--format=csv,noheader"], capture_output=True, text=True).stdout.strip())

@@ -92,6 +92,7 @@ if __name__ == "__main__":
     ap.add_argument("--golden", default=os.path.join(ROOT, "tests", "golden", "e2e_384x352.npz"))
     ap.add_argument("--only", default="")
     ap.add_argument("--corr", action="store_true", help="also round the feature maps of the correlation to 2 bf16 planes")
+    ap.add_argument("--layers", default="", help="comma-separated substrings: only these convolutions are rounded (the others stay fp32)")
     a = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     bf, fh, f32 = torch.bfloat16, torch.float16, torch.float32
@@ -109,5 +110,6 @@ if __name__ == "__main__":
     for name, (act, wgt) in variants.items():
         if a.only and a.only not in name:
             continue
-        errs, em, ex = run(a.golden, act, wgt, corr=(act[0], 2) if a.corr and act[1] else None)
+        errs, em, ex = run(a.golden, act, wgt, corr=(act[0], 2) if a.corr and act[1] else None,
+                           only_layers=[t for t in a.layers.split(",") if t] or None)
         print(f"{name:40s} pose err (rot rad, rel trans): " + "  ".join(f"({r:.2e}, {t:.2e})" for r, t in errs) + f"   flow EPE mean {em:.2e} max {ex:.2e}", flush=True)
