@@ -279,6 +279,10 @@ typedef struct rpe_conv_desc {
      * inverse, a power of two chosen so that their fp16 lo plane is a normal number (|w| >= 2^-3): exact, and it keeps ~22
      * significant bits on small weights. */
     float acc_scale;
+    /* The residual as fp16 split planes (hi + lo, channel pitch res_ld) instead of the fp32 tensor `res` (one or the other):
+     * out = relu(act(v) * scale + (res_hi + res_lo)).  They may be the output planes of the same plan (BasicBlock /
+     * ResidualBlock outputs of extractor.py:45-56 updated in place). */
+    const void *res_hi, *res_lo;
 } rpe_conv_desc;
 
 int rpe_conv_plan_create(const rpe_conv_desc *desc, void **plan_out);   /* encodes the TMA descriptors once */
@@ -324,6 +328,12 @@ int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n,
                                      void *workspace, size_t workspace_bytes, void *stream);   /* rpe_instnorm_workspace_bytes(n, C) */
 int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
                        void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream);
+/* The same with the residual addend given as fp16 split planes (b_hi + b_lo, channel pitch b_ld; excludes b / stats_b): the
+ * skip connection of extractor.py:45-56 read from the planes the next convolution consumes anyway, so that the encoder keeps no
+ * fp32 copy of its residual stream.  The addend planes may be the output planes (in-place block output). */
+int rpe_norm_act_split_res(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, const void *b_hi,
+                           const void *b_lo, int b_ld, float *out_f32, void *out_hi, void *out_lo, int ld, int n, int HW, int C,
+                           void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * "Next" row: the confidence heads (TinyUNet, /root/reference/core/unet/unet.py:8-82, wrapped with Sigmoid at

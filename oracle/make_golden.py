@@ -507,8 +507,66 @@ def resize_golden():
     return g
 
 
+def filedata_golden():
+    """The reference's own ``get_data`` (dataset/dataset_utils.py:10-35) on the on-disk fixtures of oracle/file_fixture.py: the
+    StereoDataset frame folder with an .ini calibration, the StereoVideoDataset folder with a .yaml calibration, ground truth
+    and time stamps, and the rectified calibration of a camcal.json."""
+    import hashlib
+    import tempfile
+    import cv2
+    import file_fixture as ff
+    from dataset.dataset_utils import get_data
+    from dataset.rectification import StereoRectifier
+    g = {}
+
+    def put_calib(prefix, calib):
+        g[prefix + "K_left"], g[prefix + "K_right"] = np.asarray(calib["intrinsics"]["left"]), np.asarray(calib["intrinsics"]["right"])
+        g[prefix + "extrinsics"], g[prefix + "bf"] = np.asarray(calib["extrinsics"]), np.float64(calib["bf"])
+        g[prefix + "bf_orig"], g[prefix + "img_size"] = np.float64(calib["bf_orig"]), np.asarray(calib["img_size"])
+
+    with tempfile.TemporaryDirectory() as tmp:
+        folder = ff.write_frame_folder(os.path.join(tmp, "frames"))
+        dataset, calib = get_data(folder, ff.IMG_SIZE)
+        assert type(dataset).__name__ == "StereoDataset" and len(dataset) == ff.N_FRAMES
+        put_calib("frames_", calib)
+        items = [dataset[k] for k in range(len(dataset))]
+        # images: every third row / column only (file size); masks in full, bit-packed
+        g["frames_left"] = np.stack([it[0].numpy() for it in items])[..., 1::3, 2::3]
+        g["frames_right"] = np.stack([it[1].numpy() for it in items])[..., 1::3, 2::3]
+        g["frames_mask"] = pack(np.stack([it[2].numpy() for it in items]))
+        g["frames_number"] = np.array([it[3] for it in items])
+        for mode in ("conventional", "pseudo"):
+            rect = StereoRectifier(ff.write_json_calibration(os.path.join(tmp, "json")), img_size_new=ff.IMG_SIZE, mode=mode)
+            put_calib(f"json_{mode}_", rect.get_rectified_calib())
+
+    vdir = os.path.join(ROOT, "tests", "golden", "file_video")
+    ff.write_video_folder(vdir, encode=not os.path.isfile(os.path.join(vdir, "video.mp4")))
+    cap = cv2.VideoCapture(os.path.join(vdir, "video.mp4"))
+    sha = hashlib.sha1()
+    while True:
+        ok, fr = cap.read()
+        if not ok:
+            break
+        sha.update(fr.tobytes())
+    g["video_decoded_sha1"] = np.array(sha.hexdigest())
+    for mode in ("conventional", "pseudo"):
+        dataset, calib = get_data(vdir, ff.IMG_SIZE, rect_mode=mode)
+        assert type(dataset).__name__ == "StereoVideoDataset"
+        put_calib(f"video_{mode}_", calib)
+        items = list(dataset)
+        g[f"video_{mode}_left"] = np.stack([np.asarray(it[0]) for it in items])[..., 1::3, 2::3]
+        g[f"video_{mode}_right"] = np.stack([np.asarray(it[1]) for it in items])[..., 1::3, 2::3]
+        g[f"video_{mode}_mask"] = pack(np.stack([np.asarray(it[2]) for it in items]))
+        g[f"video_{mode}_pose"] = np.stack([np.asarray(it[3]) for it in items])
+        g[f"video_{mode}_number"] = np.array([it[4] for it in items])
+        g[f"video_{mode}_len"] = np.array(len(dataset))
+    return g
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--filedata", action="store_true",
+                    help="only tests/golden/file_dataset.npz (+ tests/golden/file_video/): the reference's get_data on file fixtures")
     ap.add_argument("--resize", action="store_true", help="only tests/golden/resize_stereo.npz (reference dataset/transforms.ResizeStereo)")
     ap.add_argument("--metrics", action="store_true", help="only tests/golden/metrics.npz (reference evaluate_ate_freiburg.eval)")
     ap.add_argument("--config1", action="store_true",
@@ -523,6 +581,10 @@ def main():
     ap.add_argument("--mask-spec", action="store_true", help="only tests/golden/mask_specularities.npz (reference dataset function)")
     args = ap.parse_args()
     assert os.path.isdir(REF), "reference not mounted"
+    if args.filedata:
+        np.savez_compressed(os.path.join(ROOT, "tests", "golden", "file_dataset.npz"), **filedata_golden())
+        print("tests/golden/file_dataset.npz written")
+        return
     if args.resize:
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", "resize_stereo.npz"), **resize_golden())
         print("tests/golden/resize_stereo.npz written")

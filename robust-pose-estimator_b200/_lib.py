@@ -34,7 +34,8 @@ class ConvDesc(C.Structure):
                 ("activation", C.c_int), ("out_scale", C.c_float), ("out_f32", C.c_void_p), ("f32_ld", C.c_int),
                 ("f32_offset", C.c_int), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("bf_ld", C.c_int),
                 ("bf_offset", C.c_int), ("mode", C.c_int), ("aux", C.c_void_p), ("aux_ld", C.c_int), ("aux2", C.c_void_p),
-                ("aux2_ld", C.c_int), ("stat_partials", C.c_void_p), ("acc_scale", C.c_float)]
+                ("aux2_ld", C.c_int), ("stat_partials", C.c_void_p), ("acc_scale", C.c_float),
+                ("res_hi", C.c_void_p), ("res_lo", C.c_void_p)]
 
 
 _P, _I, _F, _Z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -79,6 +80,7 @@ SIGNATURES = {
     "rpe_instnorm_workspace_bytes": (_Z, [_I, _I]),
     "rpe_instnorm_stats": (_I, [_P, _P, _I, _I, _I, _F, _P, _Z, _P]),
     "rpe_norm_act_split": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "rpe_norm_act_split_res": (_I, [_P, _P, _I, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_tap_gather3x3": (_I, [_P, _I, _P, _P, _I, _I, _I, _I, _P]),
     "rpe_downsample8_planes": (_I, [_P, _I, _P, _I, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_im2col7s2_split_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

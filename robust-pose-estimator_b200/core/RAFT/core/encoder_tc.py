@@ -4,9 +4,11 @@ Same arithmetic graph as ``extractor.encoder_forward`` (reference: /root/referen
 ``BasicEncoder``, :6-56 ``ResidualBlock``) with every convolution evaluated as an error-compensated fp16x3 implicit GEMM:
   * the 7x7 / 2 stem is a 1x1 convolution over an im2col of the normalised image (rpe_im2col7s2_split);
   * stride-2 convolutions read their input through strided TMA boxes;
-  * fnet (InstanceNorm2d): convolution -> raw fp32, rpe_instnorm_stats, rpe_norm_act_split (normalise / relu / residual);
+  * fnet (InstanceNorm2d): convolution -> raw fp32 + partial sums, rpe_instnorm_stats_from_partials, rpe_norm_act_split_res
+    (normalise / relu / residual);
   * cnet (eval-mode BatchNorm2d): the affine map is folded into the convolution weights and the relu / residual run in the
-    convolution epilogue.
+    convolution epilogue;
+  * the residual stream exists as split planes only: block outputs overwrite them in place and the skip connections read them.
 All buffers and plans are created once per input shape."""
 import os
 
@@ -107,36 +109,38 @@ class EncoderTC:
                 st["steps"].append(("stats", raw, s, hw, c, ws))
             return s
 
-        def norm_act(a, sa, relu_a, b, sb, out, planes, hw, c):
-            st["steps"].append(("norm", a, sa, relu_a, b, sb, out, planes, hw, c))
+        def norm_act(a, sa, relu_a, b, sb, planes, hw, c, b_planes=None):
+            st["steps"].append(("norm", a, sa, relu_a, b, sb, b_planes, planes, hw, c))
 
-        def conv(name, bn, src, dims, k, cout, act, stride=1, out_f32=None, out_planes=None, res=None):
+        def conv(name, bn, src, dims, k, cout, act, stride=1, out_f32=None, out_planes=None, res_planes=None):
             raw = raw_stem and name == "conv1"
             (wts, bias) = self._wb(name, bn, raw=raw)
             cin = src.c if name != "conv1" else STEM_K
             oh, ow = (dims[1] - 1) // stride + 1, (dims[2] - 1) // stride + 1
-            want_stats = (fused_stats and out_f32 is not None and out_planes is None and res is None and act == "none" and cout % 16 == 0
+            want_stats = (fused_stats and out_f32 is not None and out_planes is None and res_planes is None and act == "none" and cout % 16 == 0
                           and n * tiles_of(oh, ow) * 4 * cout * 2 <= part.numel())
             plan = ConvPlan(self.prefix + name, [(src, 0, min(cin, wts[0].shape[-1]), wts)], dims, k, k, cout, act, bias=bias, stride=stride,
-                            out_f32=out_f32, out_planes=out_planes, res=res, stat_partials=part if want_stats else None, act_single=raw)
+                            out_f32=out_f32, out_planes=out_planes, res_planes=res_planes, stat_partials=part if want_stats else None,
+                            act_single=raw)
             if want_stats:
                 assert plan.tiles_per_image == tiles_of(oh, ow), (plan.tiles_per_image, oh, ow)
                 pending[out_f32.data_ptr()] = plan
             st["steps"].append(("conv", plan))
             return plan
 
+        # The residual stream lives in its split planes only (hi + lo = 22 mantissa bits): block outputs are written as planes, in
+        # place, and the skip connection of the next block reads them back -- no fp32 copy of the stream is written or re-read.
         # ---- stem
         col = shared_col if shared_col is not None else Planes(n, h, w, STEM_LD, device)
         st["col"] = col
-        x = f32(h, w, 64)
         xp = Planes(n, h, w, 64, device)
         raw = f32(h, w, 64)
         if inst:
             conv("conv1", None, col, (n, h, w), 1, 64, "none", out_f32=raw)
             s = stats_of(raw, 64, h * w)
-            norm_act(raw, s, 1, None, None, x, xp, h * w, 64)
+            norm_act(raw, s, 1, None, None, xp, h * w, 64)
         else:
-            conv("conv1", "norm1", col, (n, h, w), 1, 64, "relu", out_f32=x, out_planes=xp)
+            conv("conv1", "norm1", col, (n, h, w), 1, 64, "relu", out_planes=xp)
         cin = 64
         for layer, dim, stride in _STAGES:
             for blk in (0, 1):
@@ -147,15 +151,15 @@ class EncoderTC:
                     h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
                 hw = h * w
                 yp = Planes(n, h, w, dim, device)
-                if s_ != 1 or raw.shape[-1] != dim:
+                if inst and (s_ != 1 or raw.shape[-1] != dim):
                     raw = f32(h, w, dim)
-                x_in, xp_in = x, xp
+                xp_in = xp
                 if s_ != 1:
-                    x, xp = f32(h, w, dim), Planes(n, h, w, dim, device)
+                    xp = Planes(n, h, w, dim, device)
                 if inst:
                     conv(p + "conv1", None, xp_in, (n, ih, iw), 3, dim, "none", stride=s_, out_f32=raw)
                     s1 = stats_of(raw, dim, hw)
-                    norm_act(raw, s1, 1, None, None, None, yp, hw, dim)
+                    norm_act(raw, s1, 1, None, None, yp, hw, dim)
                     raw2 = f32(h, w, dim) if s_ != 1 else raw
                     if s_ != 1:                                     # projection of the skip path first (raw2 is reused below)
                         rawd = f32(h, w, dim)
@@ -164,16 +168,16 @@ class EncoderTC:
                     conv(p + "conv2", None, yp, (n, h, w), 3, dim, "none", out_f32=raw2)
                     s2 = stats_of(raw2, dim, hw)
                     if s_ != 1:
-                        norm_act(raw2, s2, 1, rawd, sd, x, xp, hw, dim)
+                        norm_act(raw2, s2, 1, rawd, sd, xp, hw, dim)
                     else:
-                        norm_act(raw2, s2, 1, x_in, None, x, xp, hw, dim)
+                        norm_act(raw2, s2, 1, None, None, xp, hw, dim, b_planes=xp_in)
                 else:
-                    res = x_in
+                    res = xp_in
                     if s_ != 1:
-                        res = f32(h, w, dim)
-                        conv(p + "downsample.0", p + "downsample.1", xp_in, (n, ih, iw), 1, dim, "none", stride=s_, out_f32=res)
+                        res = Planes(n, h, w, dim, device)
+                        conv(p + "downsample.0", p + "downsample.1", xp_in, (n, ih, iw), 1, dim, "none", stride=s_, out_planes=res)
                     conv(p + "conv1", p + "norm1", xp_in, (n, ih, iw), 3, dim, "relu", stride=s_, out_planes=yp)
-                    conv(p + "conv2", p + "norm2", yp, (n, h, w), 3, dim, "relu", out_f32=x, out_planes=xp, res=res)
+                    conv(p + "conv2", p + "norm2", yp, (n, h, w), 3, dim, "relu", out_planes=xp, res_planes=res)
                 cin = dim
         # ---- output heads (slices of the final 1x1 convolution)
         outs = []
@@ -218,11 +222,11 @@ class EncoderTC:
                 with _timed("instnorm_stats", n):
                     check(l.rpe_instnorm_stats(_p(raw), _p(stats), n, hw, c, 1e-5, _p(ws), ws.numel(), s), "rpe_instnorm_stats")
             else:
-                _, a, sa, relu_a, b, sb, out, planes, hw, c = step
+                _, a, sa, relu_a, b, sb, bp, planes, hw, c = step
                 with _timed("norm_act", n):
-                    check(l.rpe_norm_act_split(_p(a), _p(sa), relu_a, _p(b), _p(sb), _p(out), _p(None if planes is None else planes.hi),
-                                               _p(None if planes is None else planes.lo), 0 if planes is None else planes.c, n, hw, c, s),
-                          "rpe_norm_act_split")
+                    check(l.rpe_norm_act_split_res(_p(a), _p(sa), relu_a, _p(b), _p(sb), _p(None if bp is None else bp.hi),
+                                                   _p(None if bp is None else bp.lo), 0 if bp is None else bp.c, None, _p(planes.hi),
+                                                   _p(planes.lo), planes.c, n, hw, c, s), "rpe_norm_act_split_res")
         return st["outs"]
 
     def forward_nchw(self, images, col=None):

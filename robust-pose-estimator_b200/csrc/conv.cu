@@ -73,6 +73,7 @@ struct alignas(64) ConvParams {
     const float *pre;
     int pre_ld;
     const float *res;
+    const plane_t *res_hi, *res_lo;                   // the residual as split planes (channel pitch res_ld) instead of fp32
     int res_ld;
     int act;
     float scale;
@@ -167,6 +168,8 @@ __device__ __noinline__ void cv_epilogue_tail(const ConvParams &P, int act, floa
         if (P.pre) r += __ldg(P.pre + (size_t)pix * P.pre_ld + co + k);
         r = cv_activate_rt(r, act) * P.scale;
         if (P.res) r = fmaxf(r + __ldg(P.res + (size_t)pix * P.res_ld + co + k), 0.0f);
+        if (P.res_hi)
+            r = fmaxf(r + (plane_to_float(P.res_hi[(size_t)pix * P.res_ld + co + k]) + plane_to_float(P.res_lo[(size_t)pix * P.res_ld + co + k])), 0.0f);
         if (P.out_f32) P.out_f32[(size_t)pix * P.f32_ld + P.f32_off + co + k] = r;
         if (P.out_hi) {
             const plane_t h = to_plane(r);
@@ -190,6 +193,13 @@ __device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, in
     if (kK == kKGeneric) {
         if (P.pre) sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
         if (P.res) sd.a = __ldg(reinterpret_cast<const float4 *>(P.res + (pix * (uint32_t)P.res_ld + co)));
+        if (P.res_hi) {      // (plain loads: the residual planes may be the output planes of this very convolution)
+            const uint2 h = *reinterpret_cast<const uint2 *>(P.res_hi + (pix * (uint32_t)P.res_ld + co));
+            const uint2 l = *reinterpret_cast<const uint2 *>(P.res_lo + (pix * (uint32_t)P.res_ld + co));
+            const float2 h01 = __half22float2(*reinterpret_cast<const plane2_t *>(&h.x)), h23 = __half22float2(*reinterpret_cast<const plane2_t *>(&h.y));
+            const float2 l01 = __half22float2(*reinterpret_cast<const plane2_t *>(&l.x)), l23 = __half22float2(*reinterpret_cast<const plane2_t *>(&l.y));
+            sd.a = make_float4(h01.x + l01.x, h01.y + l01.y, h23.x + l23.x, h23.y + l23.y);
+        }
     } else if (kK == kKGates) {
         sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
         const int half = P.cout >> 1;
@@ -233,7 +243,7 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
             for (int k = 0; k < 4; ++k) o[k] *= P.scale;
         }
         if (kK == kKGeneric) {
-            if (P.res) {
+            if (P.res || P.res_hi) {
                 o[0] = fmaxf(o[0] + sd.a.x, 0.0f), o[1] = fmaxf(o[1] + sd.a.y, 0.0f);
                 o[2] = fmaxf(o[2] + sd.a.z, 0.0f), o[3] = fmaxf(o[3] + sd.a.w, 0.0f);
             }
@@ -1035,6 +1045,9 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         return RPE_ERR_ALIGNMENT;
     if (d->pre && ((d->pre_ld % 4) || !aligned16(d->pre))) return RPE_ERR_ALIGNMENT;
     if (d->res && ((d->res_ld % 4) || !aligned16(d->res))) return RPE_ERR_ALIGNMENT;
+    if ((d->res_hi == nullptr) != (d->res_lo == nullptr) || (d->res_hi && d->res)) return RPE_ERR_INVALID_ARG;
+    if (d->res_hi && ((d->res_ld % 4) || (reinterpret_cast<uintptr_t>(d->res_hi) & 7u) || (reinterpret_cast<uintptr_t>(d->res_lo) & 7u)))
+        return RPE_ERR_ALIGNMENT;
     int rc = cv_load_encode();
     if (rc != RPE_OK) return rc;
     ConvPlan *pl = new ConvPlan();
@@ -1153,6 +1166,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.bias = d->bias, p.act = d->activation, p.scale = d->out_scale;
     p.acc_scale = d->acc_scale != 0.0f ? d->acc_scale : 1.0f;
     p.pre = d->pre, p.pre_ld = d->pre_ld, p.res = d->res, p.res_ld = d->res_ld;
+    p.res_hi = reinterpret_cast<const rpe::plane_t *>(d->res_hi), p.res_lo = reinterpret_cast<const rpe::plane_t *>(d->res_lo);
     p.out_f32 = d->out_f32, p.f32_ld = d->f32_ld, p.f32_off = d->f32_offset;
     p.out_hi = reinterpret_cast<rpe::plane_t *>(d->out_hi), p.out_lo = reinterpret_cast<rpe::plane_t *>(d->out_lo);
     p.bf_ld = d->bf_ld, p.bf_off = d->bf_offset;
@@ -1190,7 +1204,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     }
     {   // 32-bit element offsets in the epilogue: no tensor row index times leading dimension may reach 2^32
         int max_ld = d->f32_ld > d->bf_ld ? d->f32_ld : d->bf_ld;
-        const int lds[4] = {d->pre ? d->pre_ld : 0, d->res ? d->res_ld : 0, d->aux ? d->aux_ld : 0, (d->aux2 && p.mode == 2) ? d->aux2_ld : 0};
+        const int lds[4] = {d->pre ? d->pre_ld : 0, (d->res || d->res_hi) ? d->res_ld : 0, d->aux ? d->aux_ld : 0, (d->aux2 && p.mode == 2) ? d->aux2_ld : 0};
         for (int k = 0; k < 4; ++k) max_ld = lds[k] > max_ld ? lds[k] : max_ld;
         if ((double)d->N * OH * OW * (double)max_ld >= 4294967296.0) {
             delete pl;
@@ -1200,7 +1214,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     // kernel kind: the GRU / projection modes have their own epilogues; mode 0 runs a lean epilogue when it only writes split
     // planes or only fp32 (the convolutions of the motion encoder and of the instance-norm encoder), else the generic one
     pl->kind = p.mode;
-    if (p.mode == 0 && !d->pre && !d->res && d->activation <= 1 && !cv_env().generic) {
+    if (p.mode == 0 && !d->pre && !d->res && !d->res_hi && d->activation <= 1 && !cv_env().generic) {
         if (d->out_hi && d->out_lo && !d->out_f32 && d->out_scale == 1.0f) pl->kind = kKPlanes;
         else if (d->out_f32 && !d->out_hi) pl->kind = kKF32;
     }

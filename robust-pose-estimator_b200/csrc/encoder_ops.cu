@@ -179,12 +179,15 @@ __global__ void __launch_bounds__(256) instnorm_from_partials_kernel(const float
 //   ya = stats_a ? (a - mean_a) * rstd_a : a;   if relu_a: ya = max(ya, 0)
 //   y  = b ? max(ya + (stats_b ? (b - mean_b) * rstd_b : b), 0) : ya
 // a, b fp32 NHWC with C channels (dense); y -> optional fp32 NHWC (dense) and / or split planes with channel pitch ld.
+// The addend may instead be given as split planes (b_hi + b_lo, channel pitch b_ld, no statistics): the residual stream of the
+// encoder then lives in its planes only (hi + lo carries 22 mantissa bits) and no fp32 copy of it is written or read.  The
+// addend planes may alias the output planes (every thread reads its 4 channels before it writes them).
 // ------------------------------------------------------------------------------------------------
 template <typename idx_t>
 __global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__ a, const float *__restrict__ sa, int relu_a,
-                                                       const float *__restrict__ b, const float *__restrict__ sb, float *__restrict__ out,
-                                                       plane_t *__restrict__ hi, plane_t *__restrict__ lo, int ld, int HW, int C,
-                                                       long long total4) {
+                                                       const float *__restrict__ b, const float *__restrict__ sb,
+                                                       const plane_t *b_hi, const plane_t *b_lo, int b_ld, float *__restrict__ out,
+                                                       plane_t *hi, plane_t *lo, int ld, int HW, int C, long long total4) {
     const idx_t i = (idx_t)blockIdx.x * (idx_t)blockDim.x + threadIdx.x;
     if ((long long)i >= total4) return;
     const int c4n = C / 4;
@@ -212,6 +215,12 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const float *__restrict__
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) y[k] = fmaxf(y[k] + z[k], 0.0f);
+    } else if (b_hi) {
+        const uint2 h = *reinterpret_cast<const uint2 *>(b_hi + pix * b_ld + c), l = *reinterpret_cast<const uint2 *>(b_lo + pix * b_ld + c);
+        const float2 h01 = __half22float2(*reinterpret_cast<const plane2_t *>(&h.x)), h23 = __half22float2(*reinterpret_cast<const plane2_t *>(&h.y));
+        const float2 l01 = __half22float2(*reinterpret_cast<const plane2_t *>(&l.x)), l23 = __half22float2(*reinterpret_cast<const plane2_t *>(&l.y));
+        y[0] = fmaxf(y[0] + (h01.x + l01.x), 0.0f), y[1] = fmaxf(y[1] + (h01.y + l01.y), 0.0f);
+        y[2] = fmaxf(y[2] + (h23.x + l23.x), 0.0f), y[3] = fmaxf(y[3] + (h23.y + l23.y), 0.0f);
     }
     if (out) *reinterpret_cast<float4 *>(out + pix * C + c) = make_float4(y[0], y[1], y[2], y[3]);
     if (hi) {
@@ -285,23 +294,36 @@ int rpe_instnorm_stats_from_partials(const float *partials, float *stats, int n,
     return RPE_OK;
 }
 
-int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
-                       void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream) {
+int rpe_norm_act_split_res(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, const void *b_hi,
+                           const void *b_lo, int b_ld, float *out_f32, void *out_hi, void *out_lo, int ld, int n, int HW, int C,
+                           void *stream) {
     if (!a || n <= 0 || HW <= 0 || C <= 0 || (C % 4) || (!out_f32 && !out_hi) || ((out_hi == nullptr) != (out_lo == nullptr)))
         return RPE_ERR_INVALID_ARG;
     if (out_hi && (ld < C || (ld % 4))) return RPE_ERR_INVALID_ARG;
+    if ((b_hi == nullptr) != (b_lo == nullptr) || (b_hi && (b || stats_b || b_ld < C || (b_ld % 4)))) return RPE_ERR_INVALID_ARG;
     if (!rpe::aligned16(a) || (b && !rpe::aligned16(b)) || (out_f32 && !rpe::aligned16(out_f32))) return RPE_ERR_ALIGNMENT;
+    if ((reinterpret_cast<uintptr_t>(b_hi) & 7u) || (reinterpret_cast<uintptr_t>(b_lo) & 7u) || (reinterpret_cast<uintptr_t>(out_hi) & 7u) ||
+        (reinterpret_cast<uintptr_t>(out_lo) & 7u))
+        return RPE_ERR_ALIGNMENT;
     const long long total4 = (long long)n * HW * (C / 4);
-    // 32-bit element offsets when every tensor has fewer than 2^32 elements (pix * max(C, ld) below)
-    const long long elems = (long long)n * HW * (long long)(ld > C ? ld : C);
+    // 32-bit element offsets when every tensor has fewer than 2^32 elements (pix * max(C, ld, b_ld) below)
+    const int max_ld = b_hi && b_ld > ld ? b_ld : ld;
+    const long long elems = (long long)n * HW * (long long)(max_ld > C ? max_ld : C);
     if (elems + 1024 < (1ll << 32))
         rpe::norm_act_kernel<unsigned><<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            a, stats_a, relu_a, b, stats_b, out_f32, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, ld, HW, C, total4);
+            a, stats_a, relu_a, b, stats_b, (const rpe::plane_t *)b_hi, (const rpe::plane_t *)b_lo, b_ld, out_f32, (rpe::plane_t *)out_hi,
+            (rpe::plane_t *)out_lo, ld, HW, C, total4);
     else
         rpe::norm_act_kernel<unsigned long long><<<(unsigned)((total4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-            a, stats_a, relu_a, b, stats_b, out_f32, (rpe::plane_t *)out_hi, (rpe::plane_t *)out_lo, ld, HW, C, total4);
+            a, stats_a, relu_a, b, stats_b, (const rpe::plane_t *)b_hi, (const rpe::plane_t *)b_lo, b_ld, out_f32, (rpe::plane_t *)out_hi,
+            (rpe::plane_t *)out_lo, ld, HW, C, total4);
     RPE_LAUNCH_CHECK();
     return RPE_OK;
+}
+
+int rpe_norm_act_split(const float *a, const float *stats_a, int relu_a, const float *b, const float *stats_b, float *out_f32,
+                       void *out_hi, void *out_lo, int ld, int n, int HW, int C, void *stream) {
+    return rpe_norm_act_split_res(a, stats_a, relu_a, b, stats_b, nullptr, nullptr, 0, out_f32, out_hi, out_lo, ld, n, HW, C, stream);
 }
 
 }  // extern "C"

@@ -1,7 +1,11 @@
-"""Input contract of the tracker (reference: /root/reference/dataset/dataset_utils.py:10-55).  The
-reference's file-based datasets (OpenCV rectification, video decoding) are CPU preprocessing outside the
-hot path; this module provides the same ``get_data`` entry point for the synthetic sequences used by the
-tests and the benchmark (``synthetic:<n_frames>[:seed]`` as input path) and the sequential sub-sampler."""
+"""Input contract of the tracker (reference: /root/reference/dataset/dataset_utils.py:10-55): ``get_data`` resolves an input
+folder to (dataset, rectified calibration) -- a folder of stereo PNG frames (``video_frames*/*l.png`` + ``masks*``) or a
+top/bottom stereo ``*.mp4`` with ``groundtruth.txt`` -- plus the synthetic sequences used by the tests and the benchmark
+(``synthetic:<n_frames>[:seed]`` as input path), and the sequential sub-sampler.  OpenCV only decodes; the per-frame
+preprocessing runs on the device (dataset/stereo_dataset.py)."""
+import glob
+import os
+
 import torch
 from torch.utils.data import Dataset, Sampler
 
@@ -41,8 +45,9 @@ class SequentialSubSampler(Sampler):
         return max(0, (self.stop - self.start + self.step - 1) // self.step)
 
 
-def get_data(input_path, img_size, sample_video=1, rect_mode="conventional", force_video=False):
-    """-> (dataset, calib) with calib = {'intrinsics': {'left': 3x3}, 'bf': float}."""
+def get_data(input_path, img_size, sample_video=1, rect_mode="conventional", force_video=False, raw=False):
+    """-> (dataset, calib) with calib = {'intrinsics': {'left': 3x3, ...}, 'bf': float, ...}.  raw=True: the file datasets
+    return decoded uint8 host frames and leave ``dataset.preprocess`` (device) to the consumer."""
     if isinstance(input_path, SyntheticStereoSequence):
         seq = input_path
     elif isinstance(input_path, str) and input_path.startswith("synthetic:"):
@@ -50,6 +55,24 @@ def get_data(input_path, img_size, sample_video=1, rect_mode="conventional", for
         seq = SyntheticStereoSequence(int(parts[1]), tuple(img_size), seed=int(parts[2]) if len(parts) > 2 else 0,
                                       smooth_walk=True)
     else:
-        raise NotImplementedError("file-based StereoMIS/SCARED datasets are CPU preprocessing outside the f2f hot path; "
-                                  "use 'synthetic:<frames>[:seed]'")
+        return _file_data(input_path, tuple(img_size), sample_video, rect_mode, force_video, raw)
     return SyntheticStereoDataset(seq), seq.calib
+
+
+def _file_data(input_path, img_size, sample_video, rect_mode, force_video, raw):
+    from .rectification import StereoRectifier, find_calibration_file
+    from .stereo_dataset import StereoDataset
+    from .video_dataset import StereoVideoDataset
+    rect = StereoRectifier(find_calibration_file(input_path), img_size_new=img_size, mode=rect_mode)
+    calib = rect.get_rectified_calib()
+    if not force_video:
+        try:
+            return StereoDataset(input_path, img_size=calib["img_size"], raw=raw), calib
+        except AssertionError:
+            pass                                     # no frame folder: fall through to the video, like the reference
+    videos = glob.glob(os.path.join(input_path, "*.mp4"))
+    if not videos:
+        raise RuntimeError(f"neither video_frames*/*l.png nor an .mp4 found in {input_path}")
+    dataset = StereoVideoDataset(videos[0], os.path.join(input_path, "groundtruth.txt"), img_size=calib["img_size"], sample=sample_video,
+                                 rectify=rect, raw=raw)
+    return dataset, calib

@@ -11,6 +11,7 @@ from torch.utils.data import DataLoader
 from ..core.pose.pose_estimator import PoseEstimator
 from ..core.utils.trajectory import read_freiburg, save_trajectory
 from ..dataset.dataset_utils import SequentialSubSampler, get_data
+from ..dataset.video_dataset import StereoVideoDataset
 from ..lie import SE3
 
 
@@ -26,22 +27,38 @@ def main(args, config):
         args.outpath = os.path.join(os.getcwd(), "infer_trajectory")
     os.makedirs(args.outpath, exist_ok=True)
 
-    dataset, calib = get_data(args.input, config["img_size"], rect_mode=config.get("rect_mode", "conventional"))
+    # file datasets: the loader worker only decodes (raw uint8 frames); mask, resize and rectification run on the device
+    dataset, calib = get_data(args.input, config["img_size"], rect_mode=config.get("rect_mode", "conventional"),
+                              force_video=getattr(args, "force_video", False), raw=True)
+    is_video = isinstance(dataset, StereoVideoDataset)
     gt_file = os.path.join(args.input, "groundtruth.txt") if isinstance(args.input, str) else ""
     gt_trajectory = read_freiburg(gt_file) if os.path.isfile(gt_file) else None
     init_pose = gt_trajectory[None, args.start] if gt_trajectory is not None else SE3.Identity(1)
 
     estimator = PoseEstimator(config["slam"], torch.tensor(calib["intrinsics"]["left"]).to(device), baseline=calib["bf"],
                               checkpoint=args.checkpoint, img_shape=config["img_size"], init_pose=init_pose).to(device)
-    sampler = SequentialSubSampler(dataset, args.start, args.stop, args.step)
+    if is_video:
+        warnings.warn("start/stop arguments not supported for video dataset. ignored.", UserWarning)
+        sampler = None
+    else:
+        sampler = SequentialSubSampler(dataset, args.start, args.stop, args.step)
     loader = DataLoader(dataset, num_workers=0 if config["slam"].get("debug", False) else 1, pin_memory=True, sampler=sampler)
 
     trajectory = [{"camera-pose": init_pose, "timestamp": args.start}]
     with torch.no_grad():
-        for limg, rimg, mask, img_number in loader:
-            pose, _, _, _ = estimator(limg.to(device, non_blocking=True), rimg.to(device, non_blocking=True),
-                                      mask.to(device, non_blocking=True))
-            trajectory.append({"camera-pose": pose, "timestamp": int(img_number[0])})
+        for data in loader:
+            if is_video:
+                limg, rimg, _, img_number = data
+                mask = None
+            else:
+                limg, rimg, mask, img_number = data
+            limg, rimg = limg.to(device, non_blocking=True), rimg.to(device, non_blocking=True)
+            mask = mask.to(device, non_blocking=True) if mask is not None else None
+            if hasattr(dataset, "preprocess"):
+                limg, rimg, mask = dataset.preprocess(limg, rimg, mask)
+            pose, _, _, _ = estimator(limg, rimg, mask)
+            stamp = img_number[0]
+            trajectory.append({"camera-pose": pose, "timestamp": stamp if isinstance(stamp, str) else int(stamp)})
     failed = estimator.check_failures()
     if failed:
         warnings.warn(f"{len(failed)} pairs did not converge", RuntimeWarning)

@@ -83,11 +83,11 @@ class ConvPlan:
 
     def __init__(self, name, inputs, dims, kh, kw, cout, act="none", bias=None, stride=1, out_f32=None, f32_off=0, out_planes=None,
                  bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None, stat_partials=None,
-                 act_single=False):
+                 act_single=False, res_planes=None):
         n, h, w = dims
         cout_pad = (cout + 15) // 16 * 16
         d = _lib.ConvDesc()
-        self._keep = [bias, pre, res, out_f32, out_planes, aux, aux2, stat_partials]
+        self._keep = [bias, pre, res, out_f32, out_planes, aux, aux2, stat_partials, res_planes]
         if stat_partials is not None:               # instance-norm partial sums (conv.cu kind 6), fp32 [N * tiles * 4][cout_pad][2]
             d.stat_partials = stat_partials.data_ptr()
         d.mode = mode
@@ -115,6 +115,9 @@ class ConvPlan:
             d.pre, d.pre_ld = pre.data_ptr(), pre.shape[-1]
         if res is not None:
             d.res, d.res_ld = res.data_ptr(), res.shape[-1]
+        if res_planes is not None:                  # residual read from split planes (may be out_planes: in-place block output)
+            assert res is None
+            d.res_hi, d.res_lo, d.res_ld = res_planes.hi.data_ptr(), res_planes.lo.data_ptr(), res_planes.c
         d.activation, d.out_scale = ACT[act], scale
         if out_f32 is not None:
             d.out_f32, d.f32_ld, d.f32_offset = out_f32.data_ptr(), out_f32.shape[-1], f32_off

@@ -149,6 +149,49 @@ def test_conv_addend_residual_and_single_pass(ops):
     assert 1e-5 < err1 < 5e-2
 
 
+def test_residual_read_from_split_planes_in_place(ops):
+    """The encoders keep their residual stream in fp16 split planes only: the block-output convolution (cnet, folded BN) and
+    rpe_norm_act_split_res (fnet, instance norm) read the skip connection from planes and write the block output over them."""
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib, tc
+    from rpe_b200.ops import _p, _stream, check
+    n, C, H, W = 2, 96, 36, 44
+    x = dev(det_uniform((n, H, W, C), 131, -2.0, 2.0))                       # conv input, NHWC
+    skip = torch.relu(dev(det_uniform((n, H, W, C), 132, -1.0, 3.0)))        # residual stream (a relu output, like the encoder's)
+    w = dev(det_uniform((C, C, 3, 3), 133, -1.0, 1.0)) * (1.0 / np.sqrt(C * 9))
+    b = dev(det_uniform((C,), 134, -0.5, 0.5))
+    xin, stream = tc.Planes(n, H, W, C, x.device), tc.Planes(n, H, W, C, x.device)
+    xin.hi, xin.lo = tc.split_planes(x)
+    stream.hi, stream.lo = tc.split_planes(skip)
+    skip_seen = stream.float().double()                                      # what the planes hold (22 bits of `skip`)
+    assert (skip_seen - skip.double()).abs().max().item() < 1e-6
+    conv = F.conv2d(xin.float().double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1).permute(0, 2, 3, 1)
+    # (1) convolution epilogue: out planes == residual planes
+    plan = tc.ConvPlan("res_planes", [(xin, 0, C, tc.pack_weight(w, 0, C, C))], (n, H, W), 3, 3, C, "relu", bias=b, out_planes=stream,
+                       res_planes=stream)
+    plan.run()
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.relu(conv) + skip_seen)
+    err = (stream.float().double() - ref).abs().max().item()
+    print(f"conv + residual from planes, in place: max abs err {err:.2e}")
+    assert err < 3e-5
+    # (2) norm_act: relu((a - mean) * rstd) + planes, in place
+    stream.hi, stream.lo = tc.split_planes(skip)
+    a = conv.float().contiguous()
+    mean, var = a.double().mean((1, 2)), a.double().var((1, 2), unbiased=False)
+    stats = torch.stack((mean, 1.0 / torch.sqrt(var + 1e-5)), -1).float().contiguous()        # (n, C, 2) = mean, rstd
+    check(_lib.lib().rpe_norm_act_split_res(_p(a), _p(stats), 1, None, None, _p(stream.hi), _p(stream.lo), C, None, _p(stream.hi), _p(stream.lo),
+                                            C, n, H * W, C, _stream()), "rpe_norm_act_split_res")
+    torch.cuda.synchronize()
+    ref = torch.relu(torch.relu((a.double() - stats[:, None, None, :, 0].double()) * stats[:, None, None, :, 1].double()) + skip_seen)
+    err = (stream.float().double() - ref).abs().max().item()
+    print(f"norm_act + residual from planes, in place: max abs err {err:.2e}")
+    assert err < 3e-6
+    # both an fp32 and a plane addend: rejected
+    assert _lib.lib().rpe_norm_act_split_res(_p(a), _p(stats), 1, _p(a), None, _p(stream.hi), _p(stream.lo), C, None, _p(stream.hi),
+                                             _p(stream.lo), C, n, H * W, C, _stream()) != 0
+
+
 def test_update_operator_vs_torch_trunk(ops):
     """12 GRU iterations on the tensor-core path vs the torch fp32 trunk, trained weights, real feature maps."""
     if not os.path.isfile(CKPT) or not os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "golden_full.npz")):
