@@ -51,6 +51,7 @@ constexpr int kCvMaxBN = 256;
 constexpr int kCvMaxAStages = 4, kCvMaxBStages = 16;
 constexpr int kCvSmemData = 205 * 1024;               // budget for the two rings
 constexpr int kCvMaxCout = 1024;                      // bias staged in shared memory
+constexpr uint32_t kCvGroupMaxTile = 8 * 1024;          // weight plane tiles up to this size are grouped per ring entry (see the plan)
 constexpr int kCvStageBytes = kCvEpiWarps * 32 * 16 * 4;   // epilogue transpose tiles: one [32 rows][16 floats] per warp
 constexpr int kCvSmem = kCvSmemData + 1024 + 512 + kCvMaxCout * 4 + kCvStageBytes;   // + alignment slack + barriers + bias + staging
 
@@ -66,6 +67,7 @@ struct alignas(64) ConvParams {
     int reuse;                                        // 1: one slab per filter column serves all kmaj taps (stride 1)
     uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes;
     int n_a_stages, n_b_stages;
+    int b_group;                                      // plane tiles per weight-ring entry: 1, w_planes (one tap) or kmaj * w_planes (one filter column)
     int resident_b;                                   // 1: the whole weight set stays in shared memory (loaded once per CTA)
     int cb_base[kCvMaxSrc];                           // first K block of each source in the resident weight array
     int cout, bn, n_blocks;
@@ -715,8 +717,11 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                 }
                 }
             } else {
-                int stage = 0;
+                // ring entries of b_group plane tiles (one barrier round trip per entry): a single tile for the wide layers, the
+                // planes of a tap or of a whole filter column for the narrow ones, whose MMAs are too short to hide per-tile barriers
+                int stage = 0, in_entry = 0;
                 uint32_t phase = 0;
+                const uint32_t entry_bytes = P.b_plane_bytes * (uint32_t)P.b_group;
                 for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
                     const int nb = u % P.n_blocks;
                     const int img = kK == kKCorr ? cv_decode<kPair>(P, u, rank).img : 0;
@@ -726,10 +731,12 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                             for (int tm = 0; tm < P.kmin; ++tm)
                                 for (int tj = 0; tj < P.kmaj; ++tj) {
                                     const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
-                                    for (int p = 0; p < P.w_planes; ++p) {          // one ring entry per plane tile
-                                        mbar_wait(&b_empty[stage], phase ^ 1);
-                                        if (rank == 0) mbar_expect_tx(&b_full[stage], P.b_plane_bytes * load_mult);
-                                        uint8_t *dst = sB + (size_t)stage * P.b_plane_bytes;
+                                    for (int p = 0; p < P.w_planes; ++p) {
+                                        if (in_entry == 0) {
+                                            mbar_wait(&b_empty[stage], phase ^ 1);
+                                            if (rank == 0) mbar_expect_tx(&b_full[stage], entry_bytes * load_mult);
+                                        }
+                                        uint8_t *dst = sB + (size_t)stage * entry_bytes + (size_t)in_entry * P.b_plane_bytes;
                                         if (kK == kKCorr) {
                                             // 16x16 block of target positions of image `img` (this CTA's 8 rows of it in pair mode): the
                                             // box lands as [row][x][64 ch] = accumulator column row * 16 + x; outside the map reads zero
@@ -743,7 +750,10 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                                              nb * P.bn + brow, tap);
                                         else
                                             tma_load_3d(dst, &P.wmap[s][p], &b_full[stage], cb * kCvBK, nb * P.bn, tap);
-                                        if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                                        if (++in_entry == P.b_group) {
+                                            in_entry = 0;
+                                            if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                                        }
                                     }
                                 }
                 }
@@ -766,7 +776,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         const uint32_t a_stage16 = P.a_stage_bytes >> 4, a_plane16 = P.a_plane_bytes >> 4, b_plane16 = P.b_plane_bytes >> 4;
         const uint32_t a_full_u = smem_u32(a_full), a_empty_u = smem_u32(a_empty), b_full_u = smem_u32(b_full), b_empty_u = smem_u32(b_empty);
         const uint32_t t_full_u = smem_u32(tmem_full), t_empty_u = smem_u32(tmem_empty);
-        const int n_a = P.n_a_stages, n_b = P.n_b_stages, kmin = P.kmin, kmaj = P.kmaj, taps = P.kmin * P.kmaj;
+        const int n_a = P.n_a_stages, n_b = P.n_b_stages, kmin = P.kmin, kmaj = P.kmaj, taps = P.kmin * P.kmaj, b_group = P.b_group;
+        const uint32_t b_entry16 = b_plane16 * (uint32_t)P.b_group;
         uint32_t sa = 0, sb = 0, pa = 0, pb = 0, acc = 0, acc_phase = 0;
         bool b_ready = no_load;
         for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
@@ -797,7 +808,7 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                     if (a2) cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
                                     if (w2) cv_mma_k<kPair>(d_tmem, a_hi, b_hi + b_plane16, idesc, 1u, ksteps);
                                 }
-                            } else {
+                            } else if (b_group == 1) {
                                 if (!no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
                                 tcgen05_fence_after();
                                 const uint32_t b_hi = b_base16 + sb * b_plane16;
@@ -816,6 +827,21 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                                         if (!no_mma) cv_mma_k<kPair>(d_tmem, a_hi, b_base16 + sb * b_plane16, idesc, 1u, ksteps);
                                         if (!no_load) cv_commit_u32<kPair>(b_empty_u + sb * 8u);
                                     }
+                                    if (++sb == (uint32_t)n_b) sb = 0, pb ^= 1u;
+                                }
+                            } else {
+                                // grouped entries: both planes of the tap (or of every tap of the filter column) behind one barrier
+                                const bool col = b_group != (w2 ? 2 : 1);
+                                if ((!col || tj == 0) && !no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
+                                tcgen05_fence_after();
+                                const uint32_t b_hi = b_base16 + sb * b_entry16 + (col ? (uint32_t)tj * (w2 ? 2u : 1u) * b_plane16 : 0u);
+                                if (leader && !no_mma) {
+                                    cv_mma_k<kPair>(d_tmem, a_hi, b_hi, idesc, accumulate, ksteps);
+                                    if (a2) cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_hi, idesc, 1u, ksteps);
+                                    if (w2) cv_mma_k<kPair>(d_tmem, a_hi, b_hi + b_plane16, idesc, 1u, ksteps);
+                                }
+                                if (!col || tj == kmaj - 1) {
+                                    if (leader && !no_load) cv_commit_u32<kPair>(b_empty_u + sb * 8u);
                                     if (++sb == (uint32_t)n_b) sb = 0, pb ^= 1u;
                                 }
                             }
@@ -986,7 +1012,7 @@ static int cv_load_encode() {
 // Probe / A-B switches from the environment, read once per process (not on every plan creation).
 struct CvEnv {
     bool no_pair, generic, corr_resident_a, corr_plain_stores;
-    int a_stages, dbg;
+    int a_stages, dbg, b_group;
     CvEnv() {
         const char *e = getenv("RPE_CONV_PAIR");
         no_pair = e && e[0] == '0';
@@ -997,6 +1023,8 @@ struct CvEnv {
         a_stages = e ? atoi(e) : 0;
         e = getenv("RPE_CONV_DEBUG");
         dbg = e ? atoi(e) : 0;
+        e = getenv("RPE_CONV_BGROUP");          // A-B switch: weight-ring entries of 1 = a plane tile, 2 = a tap, 3 = a filter column; unset = auto
+        b_group = e ? atoi(e) : 0;
     }
 };
 static const CvEnv &cv_env() {
@@ -1092,6 +1120,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         p.n_a_stages = (int)(((size_t)kCvSmemData - total_b) / p.a_stage_bytes);
         if (p.n_a_stages > kCvMaxAStages) p.n_a_stages = kCvMaxAStages;
         p.n_b_stages = 1;
+        p.b_group = 1;
     } else {
         p.n_a_stages = 2;
         if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
@@ -1099,7 +1128,16 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
             const int v = cv_env().a_stages;
             if (v >= 1 && v <= kCvMaxAStages && (size_t)v * p.a_stage_bytes + 2 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = v;
         }
-        p.n_b_stages = (int)((kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes) / p.b_plane_bytes);
+        // Ring entries: narrow layers (short MMAs) cannot hide one barrier round trip per plane tile in the issuer's instruction
+        // stream, so their entries hold both planes of a tap, or of all taps of a filter column when three such entries fit.
+        const size_t ring = (size_t)kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes;
+        const int tap_tiles = p.w_planes, col_tiles = p.kmaj * p.w_planes;
+        int mode = cv_env().b_group;
+        if (mode == 0) mode = p.b_plane_bytes <= kCvGroupMaxTile ? 3 : 1;
+        if (mode == 3 && ring / ((size_t)col_tiles * p.b_plane_bytes) < 3) mode = 2;
+        if (mode == 2 && ring / ((size_t)tap_tiles * p.b_plane_bytes) < 3) mode = 1;
+        p.b_group = mode == 3 ? col_tiles : mode == 2 ? tap_tiles : 1;
+        p.n_b_stages = (int)(ring / ((size_t)p.b_group * p.b_plane_bytes));
         if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
         if (p.n_b_stages < 2) {
             delete pl;
@@ -1268,6 +1306,7 @@ int rpe_corr_build_planes(const void *f1_hi, const void *f1_lo, const void *f2_h
     p.a_plane_bytes = 16 * 8 * 128, p.a_stage_bytes = 2 * p.a_plane_bytes;
     p.b_plane_bytes = (uint32_t)b_rows * 128, p.b_stage_bytes = 2 * p.b_plane_bytes;
     p.resident_b = 0;
+    p.b_group = 1;
     p.n_a_stages = 2;
     if (3 * (size_t)p.a_stage_bytes + 8 * (size_t)p.b_plane_bytes <= (size_t)kCvSmemData) p.n_a_stages = 3;
     // Resident query tile (A-B switch RPE_CORR_RESIDENT_A, off by default): all K blocks of the CTA's 128 queries (C / 64 stages of
