@@ -58,6 +58,7 @@ constexpr int kCvSmem = kCvSmemData + 1024 + 512 + kCvMaxCout * 4 + kCvStageByte
 struct alignas(64) ConvParams {
     CUtensorMap amap[kCvMaxSrc][2];
     CUtensorMap wmap[kCvMaxSrc][2];
+    CUtensorMap wmapx[kCvMaxSrc][2];                  // merged-N mode: the same weight planes with a box of bn (not bn / 2) rows
     int cblocks[kCvMaxSrc];
     int ksteps_last[kCvMaxSrc];                       // 16-channel MMA steps of the last K block (1..4)
     int n_src, n_planes, w_planes;                    // planes of the activations (1 or 2) and of the weights (1 or 2)
@@ -67,6 +68,7 @@ struct alignas(64) ConvParams {
     int reuse;                                        // 1: one slab per filter column serves all kmaj taps (stride 1)
     uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes;
     int n_a_stages, n_b_stages;
+    int merge_n;                                      // 1: hi and lo weight planes side by side as ONE N = 2 bn operand (see conv_body)
     int b_group;                                      // plane tiles per weight-ring entry: 1, w_planes (one tap) or kmaj * w_planes (one filter column)
     int resident_b;                                   // 1: the whole weight set stays in shared memory (loaded once per CTA)
     int cb_base[kCvMaxSrc];                           // first K block of each source in the resident weight array
@@ -574,6 +576,27 @@ __device__ __forceinline__ void cv_tmem_load16(uint32_t *v, uint32_t taddr) {
         : "memory");
     tmem_ld_wait();
 }
+// merged-N mode: the accumulator is the sum of two column ranges (a_hi * w_hi + a_lo * w_hi | a_hi * w_lo)
+__device__ __forceinline__ void cv_tmem_load16_sum(uint32_t *v, uint32_t taddr, uint32_t second) {
+    uint32_t w[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+          "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+        : "r"(taddr + second)
+        : "memory");
+    tmem_ld_wait();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = __float_as_uint(__uint_as_float(v[k]) + __uint_as_float(w[k]));
+}
 // the warp has read everything it needs from the accumulator stage: hand it back to the MMA issuer
 template <bool kPair>
 __device__ __forceinline__ void cv_release_acc(uint64_t *bar, uint32_t cluster_addr, int lane) {
@@ -701,7 +724,50 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         if (!(RPE_CV_DBG(P) & 1) && elect_one()) {
             const int taps = P.kmin * P.kmaj;
             const int brow = kPair ? rank * (P.bn >> 1) : 0;          // this CTA's half of the weight rows
-            if (P.resident_b) {
+            if (kPair && P.merge_n) {
+                // Merged-N (pair mode only): per (K block, tap) this CTA holds X = all bn rows of ONE weight plane (rank 0: hi,
+                // rank 1: lo) -- together the N = 2 bn operand [w_hi ; w_lo] of the a_hi product -- followed by Y = its half of
+                // the hi plane, the N = bn operand of the a_lo product.
+                const uint32_t x_bytes = (uint32_t)P.bn * 128u, tile_bytes = x_bytes + x_bytes / 2;
+                if (P.resident_b) {
+                    uint32_t total = 0;
+                    for (int s = 0; s < P.n_src; ++s) total += (uint32_t)P.cblocks[s] * taps * tile_bytes;
+                    if (u_first < num_units) {
+                        if (rank == 0) mbar_expect_tx(&b_full[0], total * 2u);
+                        for (int s = 0; s < P.n_src; ++s)
+                            for (int cb = 0; cb < P.cblocks[s]; ++cb)
+                                for (int tap = 0; tap < taps; ++tap) {
+                                    uint8_t *dst = sB + (size_t)((P.cb_base[s] + cb) * taps + tap) * tile_bytes;
+                                    const uint32_t bar = mapa_shared(smem_u32(&b_full[0]), 0);
+                                    tma_load_3d_pair(dst, &P.wmapx[s][rank], bar, cb * kCvBK, 0, tap);
+                                    tma_load_3d_pair(dst + x_bytes, &P.wmap[s][0], bar, cb * kCvBK, brow, tap);
+                                }
+                    }
+                } else {
+                    int stage = 0, in_entry = 0;
+                    uint32_t phase = 0;
+                    const uint32_t entry_bytes = tile_bytes * (uint32_t)P.b_group;
+                    for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k)
+                        for (int s = 0; s < P.n_src; ++s)
+                            for (int cb = 0; cb < P.cblocks[s]; ++cb)
+                                for (int tm = 0; tm < P.kmin; ++tm)
+                                    for (int tj = 0; tj < P.kmaj; ++tj) {
+                                        const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
+                                        if (in_entry == 0) {
+                                            mbar_wait(&b_empty[stage], phase ^ 1);
+                                            if (rank == 0) mbar_expect_tx(&b_full[stage], entry_bytes * 2u);
+                                        }
+                                        uint8_t *dst = sB + (size_t)stage * entry_bytes + (size_t)in_entry * tile_bytes;
+                                        const uint32_t bar = mapa_shared(smem_u32(&b_full[stage]), 0);
+                                        tma_load_3d_pair(dst, &P.wmapx[s][rank], bar, cb * kCvBK, 0, tap);
+                                        tma_load_3d_pair(dst + x_bytes, &P.wmap[s][0], bar, cb * kCvBK, brow, tap);
+                                        if (++in_entry == P.b_group) {
+                                            in_entry = 0;
+                                            if (++stage == P.n_b_stages) stage = 0, phase ^= 1;
+                                        }
+                                    }
+                }
+            } else if (P.resident_b) {
                 // the whole weight set fits: one load per CTA, [source K block][tap][plane] tiles
                 uint32_t total = 0;
                 for (int s = 0; s < P.n_src; ++s) total += (uint32_t)P.cblocks[s] * taps * P.w_planes * P.b_plane_bytes;
@@ -778,6 +844,9 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         const uint32_t t_full_u = smem_u32(tmem_full), t_empty_u = smem_u32(tmem_empty);
         const int n_a = P.n_a_stages, n_b = P.n_b_stages, kmin = P.kmin, kmaj = P.kmaj, taps = P.kmin * P.kmaj, b_group = P.b_group;
         const uint32_t b_entry16 = b_plane16 * (uint32_t)P.b_group;
+        const bool merged = kPair && P.merge_n != 0;
+        const uint32_t m_x16 = ((uint32_t)P.bn * 128u) >> 4, m_tile16 = m_x16 + (m_x16 >> 1);         // merged-N tile: X (bn rows) | Y (bn / 2 rows)
+        const uint32_t idesc2 = (1u << 4) | ((uint32_t)(P.bn >> 2) << 17) | ((uint32_t)((kPair ? 256 : 128) >> 4) << 24);   // N = 2 bn
         uint32_t sa = 0, sb = 0, pa = 0, pb = 0, acc = 0, acc_phase = 0;
         bool b_ready = no_load;
         for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
@@ -795,7 +864,32 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                         for (int tj = 0; tj < kmaj; ++tj) {
                             if ((!reuse || tj == 0) && !no_load) mbar_wait_u32(a_full_u + sa * 8u, pa);
                             const uint32_t a_hi = a_base16 + sa * a_stage16 + (reuse ? (uint32_t)tj * 64u : 0u);   // tap shift: 1024 B
-                            if (resident) {
+                            if (merged) {
+                                // two MMAs per K step instead of three: a_hi x [w_hi ; w_lo] (N = 2 bn, columns [0, bn) and [bn, 2 bn))
+                                // and a_lo x w_hi (N = bn, columns [0, bn)); the epilogue adds the two column ranges
+                                uint32_t b_x;
+                                if (resident) {
+                                    if (!b_ready) {
+                                        mbar_wait_u32(b_full_u, 0);
+                                        b_ready = true;
+                                    }
+                                    const int tap = P.orient == 0 ? tj * P.kw + tm : tm * P.kw + tj;
+                                    b_x = b_base16 + (uint32_t)((P.cb_base[s] + cb) * taps + tap) * m_tile16;
+                                } else {
+                                    const bool col = b_group != 1;
+                                    if ((!col || tj == 0) && !no_load) mbar_wait_u32(b_full_u + sb * 8u, pb);
+                                    b_x = b_base16 + sb * m_tile16 * (uint32_t)b_group + (col ? (uint32_t)tj * m_tile16 : 0u);
+                                }
+                                tcgen05_fence_after();
+                                if (leader && !no_mma) {
+                                    cv_mma_k<kPair>(d_tmem, a_hi, b_x, idesc2, accumulate, ksteps);
+                                    cv_mma_k<kPair>(d_tmem, a_hi + a_plane16, b_x + m_x16, idesc, 1u, ksteps);
+                                }
+                                if (!resident && (b_group == 1 || tj == kmaj - 1)) {
+                                    if (leader && !no_load) cv_commit_u32<kPair>(b_empty_u + sb * 8u);
+                                    if (++sb == (uint32_t)n_b) sb = 0, pb ^= 1u;
+                                }
+                            } else if (resident) {
                                 if (!b_ready) {
                                     mbar_wait_u32(b_full_u, 0);
                                     b_ready = true;
@@ -921,7 +1015,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 if (c_begin >= c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);   // nothing to drain (bn = 16)
                 for (int c = c_begin; c < c_end; ++c) {
                     uint32_t v[16];
-                    cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
+                    if (kPair && kK != kKCorr && kK != kKGates && kK != kKState && P.merge_n) cv_tmem_load16_sum(v, taddr0 + (uint32_t)(c * 16), (uint32_t)P.bn);
+                    else cv_tmem_load16(v, taddr0 + (uint32_t)(c * 16));
                     if (c + 1 == c_end) cv_release_acc<kPair>(&tmem_empty[acc], empty_addr, lane);
                     if (RPE_CV_DBG(P) & 4) continue;
                     if (c + 1 < c_end) cv_side_load4<kK>(P, sd_next, co_lane + (c + 1) * 16, pix, inside_mask);
@@ -1012,7 +1107,7 @@ static int cv_load_encode() {
 // Probe / A-B switches from the environment, read once per process (not on every plan creation).
 struct CvEnv {
     bool no_pair, generic, corr_resident_a, corr_plain_stores;
-    int a_stages, dbg, b_group;
+    int a_stages, dbg, b_group, merge_max;
     CvEnv() {
         const char *e = getenv("RPE_CONV_PAIR");
         no_pair = e && e[0] == '0';
@@ -1023,6 +1118,8 @@ struct CvEnv {
         a_stages = e ? atoi(e) : 0;
         e = getenv("RPE_CONV_DEBUG");
         dbg = e ? atoi(e) : 0;
+        e = getenv("RPE_CONV_MERGE");           // A-B switch: largest bn that runs in merged-N mode (0 = off); default 128
+        merge_max = e ? atoi(e) : 128;
         e = getenv("RPE_CONV_BGROUP");          // A-B switch: weight-ring entries of 1 = a plane tile, 2 = a tap, 3 = a filter column; unset = auto
         b_group = e ? atoi(e) : 0;
     }
@@ -1111,10 +1208,21 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
     p.b_plane_bytes = (uint32_t)b_rows * 128;
     p.b_stage_bytes = p.b_plane_bytes * p.w_planes;
     const int taps = d->kh * d->kw;
+    // Merged-N (narrow layers with streamed weights, CTA pairs, plain epilogues): the hi and lo weight planes form ONE operand of
+    // 2 bn columns, so that a K step costs two MMAs (N = 2 bn, N = bn) instead of three of N = bn: fewer, longer MMAs and fewer
+    // activation-operand reads per flop.  Measured (profiles/r2_v_conv_probe_merged_n.txt): 96 -> 96 +18 %, 128 -> 64 +8 %,
+    // 256 -> 126 +5 %.  RPE_CONV_MERGE=0 disables, =<n> sets the largest bn.  Per (K block, tap) a CTA then holds bn + bn / 2
+    // weight rows instead of 2 * bn / 2.
+    p.merge_n = (pl->pair && p.n_planes == 2 && p.w_planes == 2 && n_blocks == 1 && d->mode == 0 && bn <= cv_env().merge_max) ? 1 : 0;
     // Weights resident in shared memory when the whole set fits beside two activation stages (small layers: every tile would
     // otherwise re-stream them); else a ring whose entries are single plane tiles, so that many small loads are in flight.
-    size_t total_b = 0;
-    for (int s = 0; s < d->n_sources; ++s) total_b += (size_t)((d->src[s].c_count + kCvBK - 1) / kCvBK) * taps * p.w_planes * p.b_plane_bytes;
+    size_t k_tiles = 0;
+    for (int s = 0; s < d->n_sources; ++s) k_tiles += (size_t)((d->src[s].c_count + kCvBK - 1) / kCvBK) * taps;
+    const size_t room = (size_t)kCvSmemData - 2 * (size_t)p.a_stage_bytes;
+    if (p.merge_n && k_tiles * 2 * p.b_plane_bytes <= room)
+        p.merge_n = 0;            // layers whose plain weight set stays resident gain nothing (64 -> 64: 1061 vs 1038 TFLOP/s) and would lose an activation stage
+    const size_t tile_b = p.merge_n ? 3 * (size_t)p.b_plane_bytes : (size_t)p.w_planes * p.b_plane_bytes;      // per (K block, tap)
+    const size_t total_b = k_tiles * tile_b;
     p.resident_b = (n_blocks == 1 && total_b + 2 * (size_t)p.a_stage_bytes <= (size_t)kCvSmemData) ? 1 : 0;
     if (p.resident_b) {
         p.n_a_stages = (int)(((size_t)kCvSmemData - total_b) / p.a_stage_bytes);
@@ -1131,13 +1239,18 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         // Ring entries: narrow layers (short MMAs) cannot hide one barrier round trip per plane tile in the issuer's instruction
         // stream, so their entries hold both planes of a tap, or of all taps of a filter column when three such entries fit.
         const size_t ring = (size_t)kCvSmemData - (size_t)p.n_a_stages * p.a_stage_bytes;
-        const int tap_tiles = p.w_planes, col_tiles = p.kmaj * p.w_planes;
-        int mode = cv_env().b_group;
-        if (mode == 0) mode = p.b_plane_bytes <= kCvGroupMaxTile ? 3 : 1;
-        if (mode == 3 && ring / ((size_t)col_tiles * p.b_plane_bytes) < 3) mode = 2;
-        if (mode == 2 && ring / ((size_t)tap_tiles * p.b_plane_bytes) < 3) mode = 1;
-        p.b_group = mode == 3 ? col_tiles : mode == 2 ? tap_tiles : 1;
-        p.n_b_stages = (int)(ring / ((size_t)p.b_group * p.b_plane_bytes));
+        if (p.merge_n) {         // entries of whole (X | Y) tiles: a filter column when three of them fit, else a tap
+            p.b_group = (cv_env().b_group != 1 && cv_env().b_group != 2 && ring / ((size_t)p.kmaj * tile_b) >= 3) ? p.kmaj : 1;
+            p.n_b_stages = (int)(ring / ((size_t)p.b_group * tile_b));
+        } else {
+            const int tap_tiles = p.w_planes, col_tiles = p.kmaj * p.w_planes;
+            int mode = cv_env().b_group;
+            if (mode == 0) mode = p.b_plane_bytes <= kCvGroupMaxTile ? 3 : 1;
+            if (mode == 3 && ring / ((size_t)col_tiles * p.b_plane_bytes) < 3) mode = 2;
+            if (mode == 2 && ring / ((size_t)tap_tiles * p.b_plane_bytes) < 3) mode = 1;
+            p.b_group = mode == 3 ? col_tiles : mode == 2 ? tap_tiles : 1;
+            p.n_b_stages = (int)(ring / ((size_t)p.b_group * p.b_plane_bytes));
+        }
         if (p.n_b_stages > kCvMaxBStages) p.n_b_stages = kCvMaxBStages;
         if (p.n_b_stages < 2) {
             delete pl;
@@ -1193,6 +1306,17 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
                     g_last_cuda_error = 100000 + (int)r;
                     delete pl;
                     return RPE_ERR_CUDA;
+                }
+                if (p.merge_n) {      // the same plane with a box of all bn rows
+                    cuuint32_t boxx[3] = {kCvBK, (cuuint32_t)bn, 1};
+                    r = g_cv_encode(&p.wmapx[s][pln], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(wgt), dims, strides, boxx, es,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) {
+                        g_last_cuda_error = 100000 + (int)r;
+                        delete pl;
+                        return RPE_ERR_CUDA;
+                    }
                 }
             }
         }
