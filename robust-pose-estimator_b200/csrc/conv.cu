@@ -68,6 +68,7 @@ struct alignas(64) ConvParams {
     int reuse;                                        // 1: one slab per filter column serves all kmaj taps (stride 1)
     uint32_t a_plane_bytes, a_stage_bytes, b_plane_bytes, b_stage_bytes;
     int n_a_stages, n_b_stages;
+    int side_prefetch;                                // GRU kinds: the idle warp prefetches the next unit's side inputs into L2
     int merge_n;                                      // 1: hi and lo weight planes side by side as ONE N = 2 bn operand (see conv_body)
     int b_group;                                      // plane tiles per weight-ring entry: 1, w_planes (one tap) or kmaj * w_planes (one filter column)
     int resident_b;                                   // 1: the whole weight set stays in shared memory (loaded once per CTA)
@@ -825,6 +826,29 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
                 }
             }
         }
+    } else if (warp == 2 && (kK == kKState || kK == kKGates) && P.side_prefetch) {
+        // ===================== side-input prefetcher (GRU epilogues) =====================
+        // The GRU epilogues read 1.0-1.5 KB of fp32 side inputs per pixel (hoisted context term, update gate, hidden state) that were
+        // written by earlier kernels and left the L2 since.  When the accumulator of unit k is complete (its epilogue starts), this
+        // otherwise idle warp asks the L2 for the side inputs of unit k + 1: one bulk prefetch per pixel row of the tile and tensor.
+        const int rows = P.orient == 0 ? 16 : 8, cols = P.orient == 0 ? 8 : 16;       // image rows / contiguous pixels of a tile
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int k = 0, u; (u = cv_unit<kK>(P, k, u_first, u_step)) < num_units; ++k) {
+            const int un = cv_unit<kK>(P, k + 1, u_first, u_step);
+            mbar_wait(&tmem_full[acc], acc_phase);
+            if (++acc == kCvAcc) acc = 0, acc_phase ^= 1;
+            if (un >= num_units) break;
+            const CvTile t = cv_decode<kPair>(P, un, rank);
+            if (t.ghost || lane >= rows) continue;
+            const int y = (P.orient == 0 ? t.omaj0 : t.omin0) + lane, x0 = P.orient == 0 ? t.omin0 : t.omaj0;
+            if (y >= P.OH || x0 >= P.OW) continue;
+            const int npx = min(cols, P.OW - x0);
+            const size_t pix = ((size_t)t.img * P.OH + y) * P.OW + x0;
+            prefetch_l2_bulk(P.pre + pix * P.pre_ld, (uint32_t)(npx * P.pre_ld * 4));
+            prefetch_l2_bulk(P.aux + pix * P.aux_ld, (uint32_t)(npx * P.aux_ld * 4));
+            if (kK == kKState) prefetch_l2_bulk(P.aux2 + pix * P.aux2_ld, (uint32_t)(npx * P.aux2_ld * 4));
+        }
     } else if (warp == 1 && rank == 0) {
         // ===================== MMA issuer (the leader CTA in pair mode) =====================
         // The WHOLE warp walks the loop nest, so that every address / descriptor / barrier computation is warp-uniform (uniform
@@ -1108,6 +1132,7 @@ static int cv_load_encode() {
 struct CvEnv {
     bool no_pair, generic, corr_resident_a, corr_plain_stores;
     int a_stages, dbg, b_group, merge_max;
+    bool side_prefetch;
     CvEnv() {
         const char *e = getenv("RPE_CONV_PAIR");
         no_pair = e && e[0] == '0';
@@ -1118,6 +1143,11 @@ struct CvEnv {
         a_stages = e ? atoi(e) : 0;
         e = getenv("RPE_CONV_DEBUG");
         dbg = e ? atoi(e) : 0;
+        // A-B switch, off by default: L2 prefetch of the GRU epilogues' side inputs one unit ahead by the idle warp.  Measured on B200
+        // (profiles/r2_y_conv_probe_side_prefetch.txt, 64 samples): q1 314 -> 337 us, zr1 460 -> 471 us -- the prefetches compete with
+        // the operand loads for the same L2 / HBM bandwidth and the epilogue's own loads were not the exposed latency.
+        e = getenv("RPE_CONV_SIDE_PREFETCH");
+        side_prefetch = e && e[0] == '1';
         e = getenv("RPE_CONV_MERGE");           // A-B switch: largest bn that runs in merged-N mode (0 = off); default 128
         merge_max = e ? atoi(e) : 128;
         e = getenv("RPE_CONV_BGROUP");          // A-B switch: weight-ring entries of 1 = a plane tile, 2 = a tap, 3 = a filter column; unset = auto
@@ -1380,6 +1410,7 @@ int rpe_conv_plan_create(const rpe_conv_desc *d, void **plan_out) {
         if (d->out_hi && d->out_lo && !d->out_f32 && d->out_scale == 1.0f) pl->kind = kKPlanes;
         else if (d->out_f32 && !d->out_hi) pl->kind = kKF32;
     }
+    p.side_prefetch = ((p.mode == 1 || p.mode == 2) && cv_env().side_prefetch && n_blocks == 1) ? 1 : 0;
     p.stat_part = d->stat_partials;
     if (d->stat_partials) {      // instance-norm partial sums ride on the fp32-only epilogue
         if (p.mode != 0 || d->pre || d->res || d->activation > 1 || !d->out_f32 || d->out_hi || d->out_scale != 1.0f || (d->cout % 16) ||

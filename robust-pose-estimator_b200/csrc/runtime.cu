@@ -53,7 +53,7 @@ inline void qrot(const float *q, const float *p, float *o) {
 
 int rpe_compose_trajectory_host(const float *rel_host, const float *log_host, int n, const float *init_pose_host,
                                 float inv_scale, float *abs_out_host, unsigned char *failed_out_host) {
-    if (!rel_host || !log_host || !init_pose_host || !abs_out_host || n < 0) return RPE_ERR_INVALID_ARG;
+    if (!init_pose_host || !abs_out_host || n < 0 || (n > 0 && (!rel_host || !log_host))) return RPE_ERR_INVALID_ARG;    // n = 0: a one-frame sequence
     float last[7];
     for (int k = 0; k < 7; ++k) last[k] = abs_out_host[k] = init_pose_host[k];
     for (int i = 0; i < n; ++i) {

@@ -48,6 +48,37 @@ def test_host_only_entry_points():
     assert l.rpe_pose_set_groups(0) == -1 and l.rpe_pose_set_groups(8) == 0
 
 
+def test_compose_trajectory_host_matches_the_oracle():
+    """Stage a13 (pose_estimator.py:81-91) is host C: failure guard, rel.scale(1 / scale), last <- last * rel^-1 in fp32 --
+    against the numpy restatement, including a failed pair (kept pose) and the empty sequence (n = 0: one frame, no pair)."""
+    import numpy as np
+    import rpe_b200  # noqa: F401
+    from rpe_b200 import _lib
+    from oracle import se3_np
+    from oracle.detrand import det_uniform
+    l = _lib.lib()
+    n = 6
+    xi = det_uniform((n, 6), 77, -0.02, 0.02).astype(np.float64)
+    rel = np.stack([se3_np.exp(x) for x in xi]).astype(np.float32)
+    log = xi.astype(np.float32)
+    log[3, 1] = 0.2                                        # |log| > 0.1: the pair failed, the pose is kept
+    rel[4, 0] = np.nan                                     # NaN pose: failed as well
+    init = np.array([1.0, -2.0, 3.0, 0.0, 0.0, np.sin(0.05), np.cos(0.05)], np.float32)
+    out, failed = np.zeros((n + 1, 7), np.float32), np.zeros((n,), np.uint8)
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert l.rpe_compose_trajectory_host(ptr(rel), ptr(log), n, ptr(init), 250.0, ptr(out), ptr(failed)) == 0
+    assert failed.tolist() == [0, 0, 0, 1, 1, 0]
+    last = init.astype(np.float64)
+    assert np.array_equal(out[0], init)
+    for i in range(n):
+        if not failed[i]:
+            last = se3_np.mul(last, se3_np.inv(se3_np.scale(rel[i].astype(np.float64), 250.0)))
+        assert np.abs(out[i + 1] - last).max() < 1e-4 * max(1.0, np.abs(last[:3]).max()), (i, out[i + 1], last)
+    out0 = np.zeros((1, 7), np.float32)
+    assert l.rpe_compose_trajectory_host(None, None, 0, ptr(init), 250.0, ptr(out0), None) == 0 and np.array_equal(out0[0], init)
+    assert l.rpe_compose_trajectory_host(None, None, 2, ptr(init), 250.0, ptr(out0), None) != 0
+
+
 def test_ops_refuse_cpu_tensors():
     import torch
     import rpe_b200  # noqa: F401

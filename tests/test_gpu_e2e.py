@@ -253,3 +253,34 @@ def test_batched_engine_matches_reference(golden_dir, chunk, graphs, precision):
         assert rot < 1e-4 and trans < 1e-4, f"frame {k}: rot {rot:.2e} trans {trans:.2e}"
     if precision == "fp32":                 # identical evaluation count of the reference's L-BFGS run
         assert est.last_evals[:2].tolist() == [len(g["pair0_eval_pose"]), len(g["pair1_eval_pose"])]
+
+
+def test_sequence_edge_cases_and_chunk_invariance(golden_dir):
+    """Empty and ragged inputs of the throughput path: one frame (no pair), two frames, chunks that do not divide the sequence,
+    a chunk larger than the sequence -- and the result does not depend on the chunking at all (bit-identical poses)."""
+    _need_ckpt()
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_estimator import PoseEstimator
+    from rpe_b200.lie import SE3
+    g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
+    W, H = [int(v) for v in g["size"]]
+    est = PoseEstimator(dict(SLAM, precision="fp16x3"), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    idx = [0, 1, 2, 1, 0, 2]
+    L = torch.from_numpy(g["imgs_l"])[idx].cuda()
+    R = torch.from_numpy(g["imgs_r"])[idx].cuda()
+    M = torch.from_numpy(np.stack([unpack(g["masks_in"][i], (1, H, W)) for i in range(3)]))[idx].cuda()
+
+    def run(T, chunk):
+        est.last_pose = SE3.Identity(1, device="cuda")
+        return est.infer_sequence(L[:T], R[:T], M[:T], chunk=chunk)
+
+    traj, failed = run(1, 4)
+    assert traj.shape == (1, 7) and failed.shape == (0,) and traj[0].tolist() == [0, 0, 0, 0, 0, 0, 1]
+    traj2, failed2 = run(2, 4)
+    assert traj2.shape == (2, 7) and failed2.shape == (1,) and not failed2.any()
+    ref, _ = run(6, 8)                                    # one chunk holds the whole sequence
+    assert torch.equal(ref[:2], traj2)
+    for chunk in (1, 2, 4, 5):
+        got, failed = run(6, chunk)
+        assert got.shape == (6, 7) and failed.shape == (5,) and not failed.any()
+        assert torch.equal(got, ref), f"chunk {chunk}: max diff {float((got - ref).abs().max()):.3e}"
