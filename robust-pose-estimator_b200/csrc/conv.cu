@@ -355,16 +355,22 @@ __device__ __forceinline__ void cv_epilogue_half_stats(const ConvParams &P, cons
 constexpr int kCvProj = 18;
 __device__ __forceinline__ void cv_project_chunk(const ConvParams &P, const uint32_t *v, const float *sbias, const float *w2s, int co,
                                                  float *acc) {
+    // w2s: [256][16] floats (taps 0..15, read as four 16-byte broadcasts) followed by [256][2] (taps 16, 17)
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         const float y = cv_activate_rt(fmaf(__uint_as_float(v[j]), P.acc_scale, sbias[co + j]), P.act) * P.scale;
-        const float2 *w = reinterpret_cast<const float2 *>(w2s + (co + j) * kCvProj);
+        const float4 *w = reinterpret_cast<const float4 *>(w2s + (co + j) * 16);
 #pragma unroll
-        for (int k = 0; k < kCvProj / 2; ++k) {
-            const float2 wk = w[k];
-            acc[2 * k] = fmaf(y, wk.x, acc[2 * k]);
-            acc[2 * k + 1] = fmaf(y, wk.y, acc[2 * k + 1]);
+        for (int k = 0; k < 4; ++k) {
+            const float4 wk = w[k];
+            acc[4 * k] = fmaf(y, wk.x, acc[4 * k]);
+            acc[4 * k + 1] = fmaf(y, wk.y, acc[4 * k + 1]);
+            acc[4 * k + 2] = fmaf(y, wk.z, acc[4 * k + 2]);
+            acc[4 * k + 3] = fmaf(y, wk.w, acc[4 * k + 3]);
         }
+        const float2 wt = *reinterpret_cast<const float2 *>(w2s + 256 * 16 + (co + j) * 2);
+        acc[16] = fmaf(y, wt.x, acc[16]);
+        acc[17] = fmaf(y, wt.y, acc[17]);
     }
 }
 
@@ -641,8 +647,11 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         for (int i = threadIdx.x; i < P.bn * P.n_blocks; i += kCvThreads) sbias[i] = (P.bias != nullptr && i < P.cout) ? P.bias[i] : 0.0f;
     // mode 3: projection weights [cout <= 256][18] fp32 behind the bias (rest of the bias area + the unused staging tiles)
     float *w2s = sbias + 256;
-    if (kK == kKProj)
-        for (int i = threadIdx.x; i < P.cout * kCvProj; i += kCvThreads) w2s[i] = P.aux2[i];
+    if (kK == kKProj)      // [cout][18] in global -> [256][16] | [256][2] (see cv_project_chunk)
+        for (int i = threadIdx.x; i < P.cout * kCvProj; i += kCvThreads) {
+            const int c = i / kCvProj, k = i - c * kCvProj;
+            w2s[k < 16 ? c * 16 + k : 256 * 16 + c * 2 + (k - 16)] = P.aux2[i];
+        }
 
     // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the role loops in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
