@@ -599,7 +599,7 @@ def main():
                     "peak_source": peak_src,
                     "avg_launch_us": 1e3 * conv_ms / n_launch, "algorithmic_flops_per_launch": flops_exec / split / n_launch,
                     "executed_tflops": flops_exec / (conv_ms * 1e-3) / 1e12, "executed_frac": flops_exec / (conv_ms * 1e-3) / 1e12 / tc_peak,
-                    "note": "algorithmic = fp32-equivalent convolution flops; the fp16x3 split executes 3 bf16 MMAs per multiply-add, "
+                    "note": "algorithmic = fp32-equivalent convolution flops; the fp16x3 split executes 3 fp16 tensor-core products per multiply-add, "
                             "so executed_frac is the tensor-pipe figure and frac <= 1/3 by construction"}
     else:
         dom = max(own, key=lambda k: own[k]["total_ms"])
