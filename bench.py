@@ -559,7 +559,7 @@ def main():
     except (OSError, KeyError, ValueError):
         pass
     # per-kernel rooflines from the in-run CUDA-event timers.  Convolution stages carry their executed tensor-core flops
-    # as "units" (3 bf16 MMAs per multiply-add in the fp16x3 split); the algorithmic (fp32-equivalent) flops are a third.
+    # as "units" (3 fp16 tensor-core products per multiply-add in the fp16x3 split); the algorithmic (fp32-equivalent) flops are a third.
     split = 3.0 if args.precision == "fp16x3" else 1.0
     kernels = {}
     for name, d in stage.items():
