@@ -1,5 +1,9 @@
 #!/bin/bash
-# debug-switch probe of the convolution kernel (library built with -DRPE_CONV_DEBUG_BUILD, swapped in on the GPU box only)
+# debug-switch probe of the convolution kernel (library built with -DRPE_CONV_DEBUG_BUILD, swapped in on the GPU box only).
+# Build it first, in the container:
+#   cd robust-pose-estimator_b200 && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr \
+#        -DRPE_CONV_DEBUG_BUILD -c csrc/conv.cu -o /tmp/conv_dbg.o && \
+#   nvcc -shared -o build/librpe_b200_dbg.so /tmp/conv_dbg.o $(ls build/*.o | grep -v build/conv.o) -gencode arch=compute_100a,code=sm_100a
 set -u
 O=gpurun_out/r2_u
 mkdir -p $O
