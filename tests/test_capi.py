@@ -32,6 +32,12 @@ def test_ctypes_binding_covers_header():
     assert set(_declared_symbols()) == set(_lib.SIGNATURES)
 
 
+def test_integration_doc_lists_every_entry_point():
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared_symbols() if n not in doc and not any(g in doc for g in (n.rsplit("_", 1)[0] + "/",))]
+    assert not missing, f"INTEGRATION.md does not mention {missing}"
+
+
 def test_host_only_entry_points():
     import rpe_b200  # noqa: F401
     from rpe_b200 import _lib
