@@ -212,7 +212,7 @@ __device__ __forceinline__ void cv_side_load(const ConvParams &P, CvSide &sd, in
     } else {
         sd.pre = __ldg(reinterpret_cast<const float4 *>(P.pre + (pix * (uint32_t)P.pre_ld + co)));
         sd.z = __ldg(reinterpret_cast<const float4 *>(P.aux2 + (pix * (uint32_t)P.aux2_ld + co)));
-        sd.a = __ldg(reinterpret_cast<const float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co)));
+        sd.a = *reinterpret_cast<const float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co));        // (plain load: the state is updated in place by this kernel)
     }
 }
 
@@ -695,8 +695,8 @@ __device__ __forceinline__ void conv_body(const ConvParams &P) {
         }
     }
     tcgen05_fence_before();
-    if (kPair) cluster_sync_all();
-    else __syncthreads();
+    __syncthreads();                     // CTA scope: barrier initialisation, bias staging and the TMEM base address written by tcgen05.alloc
+    if (kPair) cluster_sync_all();       // cluster scope: the peer's barriers are initialised before anything arrives on them
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
