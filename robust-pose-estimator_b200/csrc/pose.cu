@@ -378,10 +378,17 @@ __device__ __forceinline__ double dot6(const double *a, const double *b) {
     return s;
 }
 
+// tensor.abs().max() of torch: a NaN component makes the result NaN (fmax alone would drop it), so that every stopping test of
+// torch.optim.LBFGS fails on a non-finite gradient exactly like the reference's and the NaN pose reaches the tracker's guard
 __device__ __forceinline__ double absmax6(const double *a) {
     double m = 0.0;
-    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(a[k]));
-    return m;
+    bool nan = false;
+    for (int k = 0; k < 6; ++k) {
+        const double v = fabs(a[k]);
+        nan = nan || (v != v);
+        m = fmax(m, v);
+    }
+    return nan ? __longlong_as_double(0x7ff8000000000000LL) : m;
 }
 
 // One pass of the body of torch.optim.LBFGS.step's while loop up to (and including) the parameter
@@ -460,9 +467,9 @@ __device__ bool lbfgs_post_eval_stop(const SolverState &S, int max_iter) {
     if (S.n_iter == max_iter) return true;
     if (S.evals >= max_eval) return true;
     if (absmax6(S.g) <= 1e-7) return true;
-    double m = 0.0;
-    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(S.d[k] * S.t));
-    if (m <= 1e-9) return true;
+    double dt[6];
+    for (int k = 0; k < 6; ++k) dt[k] = S.d[k] * S.t;
+    if (absmax6(dt) <= 1e-9) return true;
     if (fabs(S.loss - S.prev_loss) < 1e-9) return true;
     return false;
 }

@@ -253,6 +253,56 @@ def test_pose_full_size_vs_oracle(ops):
     assert np.abs(lg - rng_pose).max() < 5e-3                                # and it recovers the motion
 
 
+def _small_problem(H=48, W=64, seed=70):
+    from oracle import se3_np
+    T = se3_np.exp(np.array([0.01, -0.006, 0.015, 0.003, -0.004, 0.002]))
+    K = np.array([[60.0, 0, W / 2], [0, 60.0, H / 2], [0, 0, 1]], np.float32)
+    pcl1 = geom_np.proj(det_uniform((H, W), seed, 0.2, 0.9), K)
+    p2 = (se3_np.act(T, pcl1.reshape(3, -1).T.astype(np.float64)).T).reshape(3, H, W)
+    q = K.astype(np.float64) @ p2.reshape(3, -1)
+    uv = geom_np.img_coords(H, W)[:2].astype(np.float64)
+    flow = (q[:2] / q[2] - uv).reshape(2, H, W).astype(np.float32)
+    ones = np.ones((H, W), np.float32)
+    return [flow, pcl1, p2.astype(np.float32), ones.copy(), ones.copy(), np.ones((H, W), bool), np.ones((H, W), bool), K,
+            np.array([0.9296, 1.0004], np.float32)]
+
+
+def test_pose_degenerate_inputs_match_the_oracle(ops):
+    """The domain's nulls: a pair without a single valid pixel (objective and gradient are exactly 0: one evaluation, identity pose,
+    not flagged), non-finite flow / points / weights on valid pixels (pose_head.py:26 zeroes non-finite 2-D residuals; everything
+    else propagates like the reference's arithmetic does), and a singular Gauss-Newton system."""
+    # (a) nothing valid
+    args = _small_problem()
+    args[5] = np.zeros_like(args[5])
+    X, lg, ne = pose_np.lbfgs_solve(*args, max_iter=20)
+    sol = ops.pose_solve(*_to_dev(args), max_iter=20)
+    out = sol.out.cpu().numpy()[0]
+    assert ne == 1 and int(out[16]) == 1
+    assert np.array_equal(out[:7], np.array([0, 0, 0, 0, 0, 0, 1.0])) and np.array_equal(X, out[:7])
+    assert np.array_equal(sol.log.cpu().numpy()[0], np.zeros(6, np.float32))
+    # (b) a non-finite flow on a valid pixel: the reference zeroes the residual (pose_head.py:26) but its autograd still multiplies the
+    #     zero gradient by the non-finite difference, so the pose comes out NaN (checked with oracle/pose_torch.py, the autograd
+    #     restatement) and the tracker's guard keeps the previous pose (pose_estimator.py:81-85).  Same here, on both sides.
+    for seed, (c, y, x, v) in ((71, (0, 3, 5, np.nan)), (72, (1, 7, 9, np.inf))):
+        args = _small_problem(seed=seed)
+        args[0][c, y, x] = v
+        X, _, _ = pose_np.lbfgs_solve(*args, max_iter=20)
+        out = ops.pose_solve(*_to_dev(args), max_iter=20).out.cpu().numpy()[0]
+        assert np.isnan(X).any() and np.isnan(out[:7]).any(), (X, out[:7])
+    # (c) a NaN point poisons the 3-D term the same way
+    args = _small_problem(seed=73)
+    args[1][2, 11, 13] = np.nan
+    X, _, _ = pose_np.lbfgs_solve(*args, max_iter=20)
+    out = ops.pose_solve(*_to_dev(args), max_iter=20).out.cpu().numpy()[0]
+    assert np.isnan(X).any() and np.isnan(out[:7]).any()
+    # (d) Gauss-Newton without a valid pixel: singular normal equations -> flagged, identity kept
+    args = _small_problem(seed=73)
+    args[5] = np.zeros_like(args[5])
+    sol = ops.pose_solve(*_to_dev(args), mode=ops.SOLVER_GN, max_iter=10)
+    out = sol.out.cpu().numpy()[0]
+    assert np.array_equal(out[:7], np.array([0, 0, 0, 0, 0, 0, 1.0]))
+
+
 def test_pose_rejects_bad_arguments(ops):
     from rpe_b200._lib import RpeError
     z = torch.zeros((1, 2, 8, 6), device="cuda")                            # H*W = 48 ok, but wrong companions
