@@ -284,3 +284,30 @@ def test_sequence_edge_cases_and_chunk_invariance(golden_dir):
         got, failed = run(6, chunk)
         assert got.shape == (6, 7) and failed.shape == (5,) and not failed.any()
         assert torch.equal(got, ref), f"chunk {chunk}: max diff {float((got - ref).abs().max()):.3e}"
+
+
+def test_fully_masked_frame_keeps_the_pose(golden_dir):
+    """A frame whose mask is empty (instrument covering the view).  As the CURRENT frame of a pair it only removes the 3-D term (the 2-D
+    term is gated by the previous frame's mask alone, pose_head.py:24-28); as the PREVIOUS frame it leaves no valid pixel at all: the
+    objective and its gradient are exactly zero, the solver stops at its first evaluation and the pose stays where it was -- no NaN,
+    no failure flag, and the frames before it are tracked as before."""
+    _need_ckpt()
+    import rpe_b200  # noqa: F401
+    from rpe_b200.core.pose.pose_estimator import PoseEstimator
+    from rpe_b200.lie import SE3
+    g = np.load(os.path.join(golden_dir, "e2e_384x352.npz"))
+    W, H = [int(v) for v in g["size"]]
+    est = PoseEstimator(dict(SLAM, precision="fp16x3"), torch.tensor(g["K"]), float(g["bf"]), CKPT, (W, H)).cuda()
+    idx = [0, 1, 2, 1, 0]
+    L = torch.from_numpy(g["imgs_l"])[idx].cuda()
+    R = torch.from_numpy(g["imgs_r"])[idx].cuda()
+    M = torch.from_numpy(np.stack([unpack(g["masks_in"][i], (1, H, W)) for i in range(3)]))[idx].cuda()
+    ref, failed_ref = est.infer_sequence(L, R, M, chunk=4)
+    M2 = M.clone()
+    M2[2] = False
+    est.last_pose = SE3.Identity(1, device="cuda")
+    got, failed = est.infer_sequence(L, R, M2, chunk=4)
+    assert torch.isfinite(got).all() and not failed.any() and not failed_ref.any()
+    assert torch.equal(got[1], ref[1])                       # pair 0 -> 1 does not see frame 2
+    assert est.last_evals[1] > 1                             # pair 1 -> 2: the 2-D term alone still constrains the pose
+    assert torch.equal(got[3], got[2]) and est.last_evals[2] == 1          # pair 2 -> 3: nothing valid, pose kept
