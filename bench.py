@@ -192,7 +192,7 @@ def _state_dict(torch):
                     "dropout": 0.0}).state_dict()
 
 
-def cpu_baseline(L, R, M, seq, budget_pairs=3):
+def cpu_baseline(L, R, M, seq, budget_pairs=8):          # ~10-15 s of host work on 16 cores
     """The oracle port timed on the host cores over a bounded sample of the same workload."""
     import torch
     cores = os.cpu_count() or 1
