@@ -92,8 +92,12 @@ class UpdateTC:
         else:
             pl["fh1"] = self._plan(st, "flow_head.conv1", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["fh"])
             pl["fh2"] = self._plan(st, "flow_head.conv2", [(st["fh"], 0, 256, 0)], 3, 3, 2, "none", out_f32=st["delta"])
-        pl["mask0"] = self._plan(st, "mask.0", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["mk"])
-        pl["mask2"] = self._plan(st, "mask.2", [(st["mk"], 0, 256, 0)], 1, 1, 576, "none", out_f32=st["mask"], scale=0.25)
+        # The mask head only shapes the convex up-sampling of the last iteration; the per-layer study (profiles/
+        # r2_precision_study_per_layer.txt) puts the effect of ONE weight plane there at 3.5e-7 relative translation / 1e-8 rad,
+        # against 1e-3 ... 3e-3 for every other layer group -- so it runs two products per multiply-add (RPE_MASK_HEAD_X3=1: three)
+        ws = os.environ.get("RPE_MASK_HEAD_X3", "0") != "1"
+        pl["mask0"] = self._plan(st, "mask.0", [(st["hp"], 0, 128, 0)], 3, 3, 256, "relu", out_planes=st["mk"], weight_single=ws)
+        pl["mask2"] = self._plan(st, "mask.2", [(st["mk"], 0, 256, 0)], 1, 1, 576, "none", out_f32=st["mask"], scale=0.25, weight_single=ws)
         st["plans"] = pl
         self._shapes[key] = st
         return st

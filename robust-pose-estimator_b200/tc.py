@@ -83,7 +83,7 @@ class ConvPlan:
 
     def __init__(self, name, inputs, dims, kh, kw, cout, act="none", bias=None, stride=1, out_f32=None, f32_off=0, out_planes=None,
                  bf_off=0, scale=1.0, pre=None, res=None, single_pass=False, mode=0, aux=None, aux2=None, stat_partials=None,
-                 act_single=False, res_planes=None):
+                 act_single=False, res_planes=None, weight_single=False):
         n, h, w = dims
         cout_pad = (cout + 15) // 16 * 16
         d = _lib.ConvDesc()
@@ -105,7 +105,9 @@ class ConvPlan:
             # act_single: the activations are exact in their hi plane (raw uint8 frames); the weights keep both planes
             s.act_hi, s.act_lo = planes.hi.data_ptr(), (0 if (single_pass or act_single) else planes.lo.data_ptr())
             s.c_total, s.c_offset, s.c_count = planes.c, c_off, (c_cnt + 15) // 16 * 16
-            s.w_hi, s.w_lo, s.w_cstride = w_hi.data_ptr(), (0 if single_pass else w_lo.data_ptr()), w_hi.shape[-1]
+            # weight_single: only the hi plane of the weights (two products per multiply-add: a_hi w_hi + a_lo w_hi); for layers whose
+            # rounding to 11 weight bits is invisible downstream (the mask head, profiles/r2_precision_study_per_layer.txt)
+            s.w_hi, s.w_lo, s.w_cstride = w_hi.data_ptr(), (0 if (single_pass or weight_single) else w_lo.data_ptr()), w_hi.shape[-1]
             self._keep += [planes, w_hi, w_lo]
         d.n_sources = len(inputs)
         d.N, d.H, d.W = n, h, w
