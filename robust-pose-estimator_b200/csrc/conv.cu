@@ -34,7 +34,7 @@
 
 namespace rpe {
 
-// RPE_CONV_DEBUG (probe switches: 1 no loads, 2 no MMAs, 4 no epilogue memory traffic) exists only in builds made with
+// RPE_CONV_DEBUG (probe switches: 1 no loads, 2 no MMAs, 4 no epilogue memory traffic, 8 no fp32 store of the GRU state) exists only in builds made with
 // -DRPE_CONV_DEBUG_BUILD; in the production library every test of it folds to a constant.
 #ifdef RPE_CONV_DEBUG_BUILD
 #define RPE_CV_DBG(P) ((P).dbg)
@@ -276,7 +276,8 @@ __device__ __forceinline__ void cv_epilogue_group(const ConvParams &P, const flo
             o[1] = (1.0f - sd.z.y) * sd.a.y + sd.z.y * o[1];
             o[2] = (1.0f - sd.z.z) * sd.a.z + sd.z.z * o[2];
             o[3] = (1.0f - sd.z.w) * sd.a.w + sd.z.w * o[3];
-            *reinterpret_cast<float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co)) = make_float4(o[0], o[1], o[2], o[3]);
+            if (!(RPE_CV_DBG(P) & 8))        // (probe bit 8: what would a state kept in planes only save?  measured: see DESIGN)
+                *reinterpret_cast<float4 *>(P.aux + (pix * (uint32_t)P.aux_ld + co)) = make_float4(o[0], o[1], o[2], o[3]);
             cv_store_split4<true>(P, pix * (uint32_t)P.bf_ld + P.bf_off + co, o);
         }
     } else if (kK == kKGeneric || kK == kKPlanes || kK == kKF32) {      // ragged tail of a channel count that is not a multiple of 4
