@@ -38,6 +38,9 @@ int rpe_version(void);
 const char *rpe_status_string(int status);
 int rpe_last_cuda_error(void);                 /* cudaError_t of the last failing CUDA call      */
 int rpe_device_sm_count(void);
+/* cudaLimitMaxL2FetchGranularity of the current device: sets it when bytes > 0 (32, 64 or 128 -- a hint), returns the value in force
+ * (or a negative status).  The windowed gathers of the correlation lookup touch 40-byte rows; see DESIGN.md for the measurement. */
+int rpe_l2_fetch_granularity(int bytes);
 long long rpe_launch_count(void);               /* kernels launched by this library so far        */
 
 /* ------------------------------------------------------------------------------------------------

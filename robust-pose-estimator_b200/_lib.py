@@ -45,6 +45,7 @@ SIGNATURES = {
     "rpe_status_string": (C.c_char_p, [_I]),
     "rpe_last_cuda_error": (_I, []),
     "rpe_device_sm_count": (_I, []),
+    "rpe_l2_fetch_granularity": (_I, [_I]),
     "rpe_launch_count": (C.c_longlong, []),
     "rpe_mask_specularities": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rpe_depth_proj": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),

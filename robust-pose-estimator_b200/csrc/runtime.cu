@@ -39,6 +39,20 @@ int rpe_device_sm_count(void) { return rpe::sm_count(); }
 
 long long rpe_launch_count(void) { return rpe::g_launch_count; }
 
+int rpe_l2_fetch_granularity(int bytes) {
+    if (bytes > 0) {
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes);
+        if (e != cudaSuccess) {
+            rpe::g_last_cuda_error = (int)e;
+            (void)cudaGetLastError();
+            return RPE_ERR_CUDA;
+        }
+    }
+    size_t v = 0;
+    if (cudaDeviceGetLimit(&v, cudaLimitMaxL2FetchGranularity) != cudaSuccess) return RPE_ERR_CUDA;
+    return (int)v;
+}
+
 // ---- host-side trajectory composition (fp32, same operation order as the reference's lietorch calls) ----
 namespace {
 inline void qrot(const float *q, const float *p, float *o) {
